@@ -1,0 +1,199 @@
+/*
+ * rbpr.h — C ABI of the B200-native BPR hot path (librbpr.so).
+ *
+ * Plain C, no torch types: raw device/host pointers and sizes only.  Every entry
+ * point returns 0 on success or a negative rbpr_status; the message for the last
+ * failure of a context is available from rbpr_last_error().  No C++ exception
+ * crosses this boundary.
+ *
+ * The reference (Nemexur/revisit-bpr) has no FFI: its hot path is a sequence of
+ * PyTorch calls.  Each entry point below names the reference call sites it
+ * replaces (paths relative to the reference repo root).
+ *
+ * Ownership: embedding tables, optimizer state and CSR arrays are OWNED BY THE
+ * CALLER (PyTorch storages in the shipped host shell); the library borrows the
+ * pointers, updates tables in place, and never frees or reallocates them.  The
+ * context owns only scratch (sorted batch, dense item-gradient accumulator,
+ * touched flags, step statistics).
+ *
+ * Threading: a context is not thread-safe; one context per device per process.
+ * All device work is enqueued on the cudaStream_t passed in (as void*).
+ */
+#ifndef RBPR_H_
+#define RBPR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBPR_ABI_VERSION 1
+
+typedef struct rbpr_ctx rbpr_ctx;
+
+typedef enum {
+  RBPR_OK = 0,
+  RBPR_ERR_ARG = -1,   /* bad argument / shape mismatch / not bound */
+  RBPR_ERR_CUDA = -2,  /* CUDA runtime error */
+  RBPR_ERR_STATE = -3, /* call order violated */
+  RBPR_ERR_DATA = -4   /* invalid data (e.g. a user who has seen every item) */
+} rbpr_status;
+
+typedef enum { RBPR_OPT_SGD = 0, RBPR_OPT_ADAM = 1 } rbpr_optimizer;
+
+typedef enum {
+  RBPR_SAMPLER_UNIFORM = 0,  /* uniform over {1..I-1} \ seen(u)                */
+  RBPR_SAMPLER_WEIGHTED = 1, /* ∝ item_weight over {1..I-1} \ seen(u) (alias)  */
+  RBPR_SAMPLER_INJECTED = 2  /* negatives supplied by the caller (neg_in)      */
+} rbpr_sampler;
+
+/* Hyper-parameters of one training call.
+ * reg_*: replaces Model.regularization (revisit_bpr/models/bpr/model.py:70-93) —
+ *        the host resolves `all`/`neg` defaulting before filling these.
+ * optimizer fields: torch.optim.{SGD,Adam} param_groups as instantiated by
+ *        experiments/bpr/exp.py:103-105. */
+typedef struct {
+  int32_t optimizer; /* rbpr_optimizer */
+  int32_t sampler;   /* rbpr_sampler   */
+  float lr;
+  float beta1, beta2, eps; /* Adam */
+  float reg_user, reg_item, reg_neg;
+  float reserved0;
+} rbpr_hparams;
+
+/* Per-step statistics written by the training entry points (doubles). */
+#define RBPR_STATS_PER_STEP 4
+/* [0] bpr_loss = Σ -logσ(x)      (model.py:65, loss.py:19-21)
+ * [1] l2_reg   = Σ reg terms     (model.py:66)
+ * [2] Σ|x|     (logits_diff numerator, experiments/bpr/exp.py:391)
+ * [3] number of triples in the step */
+
+int rbpr_abi_version(void);
+
+/* Create / destroy a context on CUDA device `device`. */
+int rbpr_create(int device, rbpr_ctx** out);
+void rbpr_destroy(rbpr_ctx* ctx);
+const char* rbpr_last_error(const rbpr_ctx* ctx);
+
+/* Borrow the model tables.  Replaces nothing by itself; these are the storages of
+ * MF._user_emb.weight (U,D), MF._item_emb.weight (I,D) and MF._item_bias (I,) or
+ * NULL (revisit_bpr/models/bpr/model.py:96-129,147-153).  Row 0 of both tables is
+ * the padding row.  D must be a multiple of 4, 4 <= D <= 1024; rows 16-byte aligned. */
+int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* item_emb,
+                     int64_t num_items, int32_t dim, float* item_bias);
+
+/* Borrow Adam state (same shapes as the tables; all zero-initialised by the caller).
+ * user_last_step (U,) int32 holds, per user row, the number of optimizer steps already
+ * applied to it (lazy dense-Adam catch-up).  Replaces the state that
+ * torch.optim.Adam keeps (experiments/trainer.py:79). bias_* may be NULL iff no bias. */
+int rbpr_bind_adam_state(rbpr_ctx* ctx, float* user_m, float* user_v, int32_t* user_last_step,
+                         float* item_m, float* item_v, float* bias_m, float* bias_v);
+
+/* Borrow the training interaction matrix in CSR form (device pointers):
+ * indptr (U+1,) int64, indices (nnz,) int32 item ids, sorted ascending within a row.
+ * Triple t (0 <= t < nnz) is (user = row containing t, item = indices[t]): the COO
+ * flattening of experiments/bpr/dataset.py:153-156; the row doubles as the user's
+ * seen_items list (dataset.py:157-163) used to reject negatives.
+ * Fails with RBPR_ERR_DATA if some user has seen every non-padding item (the reference's
+ * torch.multinomial raises on such a row). Synchronises the stream once. */
+int rbpr_bind_csr(rbpr_ctx* ctx, const int64_t* indptr, const int32_t* indices, int64_t num_users,
+                  int64_t nnz, void* stream);
+
+/* Optional: Walker alias table over items for the popularity-weighted static sampler
+ * (experiments/bpr/exp.py:85-91,282-293: weights = count^alpha).  prob (I,) float in [0,1],
+ * alias (I,) int32; entry 0 (padding) must have prob 0 and a non-zero alias. Device ptrs. */
+int rbpr_bind_item_alias(rbpr_ctx* ctx, const float* prob, const int32_t* alias);
+
+/* Negative sampler alone: for each triple id t = triple_idx[k] draw
+ * neg_out[k] = f(seed, step, t, CSR) — the counter-based specification in DESIGN.md §3
+ * (Philox4x32-10, key = seed, subsequence = t, offset = (step<<8 | block)), rejecting
+ * item 0 and the user's seen items.  Replaces UniformSampler.sample
+ * (revisit_bpr/modules/neg_samplers.py:31-37) and BPRExperiment._static_sampling
+ * (experiments/bpr/exp.py:290-293).  All pointers are device pointers. */
+int rbpr_sample_negatives(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t seed,
+                          uint64_t step, int32_t sampler, int64_t* neg_out, void* stream);
+
+/* The fused training path.  Splits triple_idx[0..n) into ceil(n/batch) consecutive
+ * minibatches; for each: sample negatives, gather (u,i+,i-), x = u·(i+ - i-) [+ bias],
+ * loss = Σ softplus(-x) + L2, exact synchronous-minibatch gradients (duplicates summed),
+ * optimizer update in place.  Step s uses global step number step0 + s for the sampler
+ * and the Adam bias correction (step0 = optimizer steps taken so far).
+ * Replaces, per step: BPRExperiment._train_batch (experiments/bpr/exp.py:356-367),
+ * Model.forward train branch (model.py:48-68), MF.forward (model.py:131-145),
+ * Loss.forward (loss.py:19-21), Model.regularization (model.py:70-93),
+ * accelerator.backward + optimizer.step + zero_grad (experiments/trainer.py:76-81).
+ *   triple_idx : device int64 (n,)  — a slice of the epoch permutation of [0,nnz)
+ *   neg_in     : device int64 (n,) or NULL — required iff hp->sampler == INJECTED
+ *   neg_out    : device int64 (n,) or NULL — negatives used, aligned with triple_idx
+ *   stats_out  : device double (ceil(n/batch), RBPR_STATS_PER_STEP) or NULL */
+int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t batch,
+                     uint64_t seed, uint64_t step0, const rbpr_hparams* hp, const int64_t* neg_in,
+                     int64_t* neg_out, double* stats_out, void* stream);
+
+/* Synchronise `stream` and report (then clear) any error raised on the device by earlier
+ * asynchronous calls (sampler exhaustion, out-of-range triple index).  The *_host entry
+ * points do this themselves. */
+int rbpr_sync_check(rbpr_ctx* ctx, void* stream);
+
+/* Same call with HOST buffers: triple_idx (and neg_in) are copied host→device, stats (and
+ * neg_out) device→host, and the stream is synchronised before returning. */
+int rbpr_train_steps_host(rbpr_ctx* ctx, const int64_t* triple_idx_host, int64_t n, int64_t batch,
+                          uint64_t seed, uint64_t step0, const rbpr_hparams* hp,
+                          const int64_t* neg_in_host, int64_t* neg_out_host,
+                          double* stats_out_host, void* stream);
+
+/* Data-parallel split of one step (experiments/launcher.py:35-73 + DDP allreduce inside
+ * accelerator.backward, experiments/trainer.py:76).  Each rank calls rbpr_grad_step on its
+ * local batch (users owned by the rank: user rows are updated locally), then all ranks
+ * all-reduce(sum) the buffer returned by rbpr_item_grad_buffer, then each rank calls
+ * rbpr_apply_item_grads (dense, identical on every rank). */
+int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t seed,
+                   uint64_t step, const rbpr_hparams* hp, const int64_t* neg_in, int64_t* neg_out,
+                   double* stats_out, void* stream);
+int rbpr_item_grad_buffer(rbpr_ctx* ctx, float** ptr, int64_t* numel);
+int rbpr_apply_item_grads(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* stream);
+
+/* Bring every lazily-updated user row up to `step` optimizer steps (dense-Adam semantics
+ * of torch.optim.Adam: rows with zero gradient still move).  Call before reading the user
+ * table (eval, checkpoint).  No-op for SGD. */
+int rbpr_flush_lazy(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* stream);
+
+/* Full-catalog scoring + top-k + ranking metrics for a block of users.
+ * Replaces eval Model.forward/MF.forward over AllItemsCollator batches
+ * (model.py:43-47,131-145; experiments/bpr/dataset.py:274-296), _remove_seen_items
+ * (experiments/bpr/exp.py:369-374), prepare_target (revisit_bpr/metrics/metric.py:110-113),
+ * NDCG.compute (metrics/ndcg.py:8-13,69-78) and Recall.compute (metrics/recall.py:44-51).
+ *   users            device int64 (n_users,)
+ *   seen_indptr/idx  device CSR (row per entry of `users`, local numbering 0..n_users) of items
+ *                    to mask to -1e13 (NULL,NULL = no masking); item 0 is always masked
+ *   held_indptr/idx  device CSR (same local numbering) of held-out positives, sorted per row
+ *   k_max            top-k depth kept (1..RBPR_MAX_TOPK)
+ *   ks, n_ks         host array of cut-offs (each <= k_max)
+ *   topk_items       device int32 (n_users,k_max) or NULL;  topk_scores device float or NULL
+ *   ndcg_out, recall_out  device float (n_users, n_ks) or NULL                                  */
+#define RBPR_MAX_TOPK 128
+int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                    const int64_t* seen_indptr, const int32_t* seen_indices,
+                    const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
+                    const int32_t* ks, int32_t n_ks, int32_t* topk_items, float* topk_scores,
+                    float* ndcg_out, float* recall_out, void* stream);
+
+/* Dense scores for a block of users: out (n_users, I) float, masked like above.
+ * The eval-mode Model.forward output `logits` (model.py:43-47) for drop-in callers that
+ * want the full matrix (revisit_bpr.metrics on dense tensors). */
+int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                     const int64_t* seen_indptr, const int32_t* seen_indices, float* out,
+                     void* stream);
+
+/* Instrumentation: number of kernels this context has launched so far, and the device time
+ * (ms, CUDA events on the launch stream) spent in the dominant training kernel since the
+ * last reset, with its launch count.  Timing is off unless enabled (adds 2 events/launch). */
+int64_t rbpr_launch_count(const rbpr_ctx* ctx);
+int rbpr_kernel_timing(rbpr_ctx* ctx, int32_t enable);
+int rbpr_kernel_time_ms(rbpr_ctx* ctx, double* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBPR_H_ */

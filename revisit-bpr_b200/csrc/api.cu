@@ -1,0 +1,127 @@
+// Context management and table binding for librbpr.so (C ABI in include/rbpr.h).
+#include "common.cuh"
+
+extern "C" {
+
+int rbpr_abi_version(void) { return RBPR_ABI_VERSION; }
+
+int rbpr_create(int device, rbpr_ctx** out) {
+  if (!out) return RBPR_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return RBPR_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return RBPR_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RBPR_ERR_CUDA;
+  if (prop.major != 10) return RBPR_ERR_CUDA;  // sm_100a cubin only: no fallback path exists
+  rbpr_ctx* ctx = new (std::nothrow) rbpr_ctx();
+  if (!ctx) return RBPR_ERR_CUDA;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc(&ctx->flag, sizeof(int32_t)) != cudaSuccess ||
+      cudaMemset(ctx->flag, 0, sizeof(int32_t)) != cudaSuccess) {
+    delete ctx;
+    return RBPR_ERR_CUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void rbpr_destroy(rbpr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->coo_user);
+  cudaFree(ctx->item_grad);
+  cudaFree(ctx->touched);
+  cudaFree(ctx->keys_in);
+  cudaFree(ctx->keys_out);
+  cudaFree(ctx->pos_in);
+  cudaFree(ctx->pos_out);
+  cudaFree(ctx->cub_tmp);
+  cudaFree(ctx->stats);
+  cudaFree(ctx->flag);
+  cudaFree(ctx->stage_idx);
+  cudaFree(ctx->stage_neg);
+  cudaFree(ctx->score_buf);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  delete ctx;
+}
+
+const char* rbpr_last_error(const rbpr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* item_emb,
+                     int64_t num_items, int32_t dim, float* item_bias) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!user_emb || !item_emb) RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: null table pointer");
+  if (num_users < 2 || num_items < 3)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: need >=2 user rows and >=3 item rows (row 0 pads)");
+  if (num_items >= (1ll << 31) || num_users >= (1ll << 31))
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: ids must fit int32");
+  if (dim < 4 || dim > 1024 || dim % 4 != 0)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: dim=%d must be a multiple of 4 in [4,1024]", dim);
+  if (((uintptr_t)user_emb | (uintptr_t)item_emb) & 15u)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: tables must be 16-byte aligned");
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaFree(ctx->item_grad);
+  cudaFree(ctx->touched);
+  ctx->item_grad = nullptr;
+  ctx->touched = nullptr;
+  const size_t gbytes = ((size_t)num_items * dim + (size_t)num_items) * sizeof(float);
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->item_grad, gbytes));
+  RBPR_CUDA(ctx, cudaMemset(ctx->item_grad, 0, gbytes));
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->touched, num_items * sizeof(uint32_t)));
+  RBPR_CUDA(ctx, cudaMemset(ctx->touched, 0, num_items * sizeof(uint32_t)));
+  ctx->user_emb = user_emb;
+  ctx->item_emb = item_emb;
+  ctx->item_bias = item_bias;
+  ctx->U = num_users;
+  ctx->I = num_items;
+  ctx->D = dim;
+  return 0;
+}
+
+int rbpr_bind_adam_state(rbpr_ctx* ctx, float* user_m, float* user_v, int32_t* user_last_step,
+                         float* item_m, float* item_v, float* bias_m, float* bias_v) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!user_m || !user_v || !user_last_step || !item_m || !item_v)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_adam_state: null pointer");
+  if (((uintptr_t)user_m | (uintptr_t)user_v | (uintptr_t)item_m | (uintptr_t)item_v) & 15u)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_adam_state: state must be 16-byte aligned");
+  ctx->user_m = user_m;
+  ctx->user_v = user_v;
+  ctx->user_last = user_last_step;
+  ctx->item_m = item_m;
+  ctx->item_v = item_v;
+  ctx->bias_m = bias_m;
+  ctx->bias_v = bias_v;
+  return 0;
+}
+
+int64_t rbpr_launch_count(const rbpr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rbpr_kernel_timing(rbpr_ctx* ctx, int32_t enable) {
+  if (!ctx) return RBPR_ERR_ARG;
+  ctx->timing = enable != 0;
+  return 0;
+}
+
+int rbpr_kernel_time_ms(rbpr_ctx* ctx, double* ms_out, int64_t* launches_out) {
+  if (!ctx) return RBPR_ERR_ARG;
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (size_t k = 0; k + 1 < ctx->ev_used; k += 2) {
+    RBPR_CUDA(ctx, cudaEventSynchronize(ctx->ev[k + 1]));
+    float ms = 0.f;
+    RBPR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));
+    ctx->timed_ms += ms;
+    ctx->timed_launches++;
+  }
+  ctx->ev_used = 0;
+  if (ms_out) *ms_out = ctx->timed_ms;
+  if (launches_out) *launches_out = ctx->timed_launches;
+  ctx->timed_ms = 0.0;
+  ctx->timed_launches = 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Shared context + helpers for librbpr.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rbpr.h"
+
+struct rbpr_ctx {
+  int device = 0;
+  std::string err;
+  // borrowed tables
+  float* user_emb = nullptr;
+  float* item_emb = nullptr;
+  float* item_bias = nullptr;
+  int64_t U = 0, I = 0;
+  int D = 0;
+  // borrowed Adam state
+  float *user_m = nullptr, *user_v = nullptr, *item_m = nullptr, *item_v = nullptr;
+  float *bias_m = nullptr, *bias_v = nullptr;
+  int32_t* user_last = nullptr;
+  // borrowed CSR
+  const int64_t* indptr = nullptr;
+  const int32_t* indices = nullptr;
+  int64_t csr_users = 0, nnz = 0;
+  // borrowed alias table
+  const float* alias_prob = nullptr;
+  const int32_t* alias_idx = nullptr;
+  // owned scratch
+  int32_t* coo_user = nullptr;  // (nnz) triple -> user
+  float* item_grad = nullptr;   // (I*D + I) dense item (+bias) gradient accumulator
+  uint32_t* touched = nullptr;  // (I) item touched in this step
+  uint64_t* keys_in = nullptr;  // (cap) (step<<32 | triple)
+  uint64_t* keys_out = nullptr;
+  int32_t* pos_in = nullptr;  // (cap) original position
+  int32_t* pos_out = nullptr;
+  int64_t cap = 0;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  double* stats = nullptr;  // (stats_cap steps, 4)
+  int64_t stats_cap = 0;
+  int32_t* flag = nullptr;  // device error flag
+  int64_t* stage_idx = nullptr;  // staging for the *_host entry point
+  int64_t* stage_neg = nullptr;
+  int64_t stage_cap = 0;
+  // score scratch
+  float* score_buf = nullptr;
+  size_t score_buf_bytes = 0;
+  // instrumentation
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  size_t ev_used = 0;
+  double timed_ms = 0.0;
+  int64_t timed_launches = 0;
+  int sm_count = 148;
+};
+
+#define RBPR_FAIL(ctx, code, ...)                     \
+  do {                                                \
+    char _b[512];                                     \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+    (ctx)->err = _b;                                  \
+    return (code);                                    \
+  } while (0)
+
+#define RBPR_CUDA(ctx, expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      RBPR_FAIL(ctx, RBPR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                __FILE__, __LINE__);                                                    \
+  } while (0)
+
+// Group geometry for a row of D floats: LANES lanes (power of two, <=32) each holding NV
+// float4 vectors; column of vector v on lane gl is 4*(gl + LANES*v).
+static inline void rbpr_geometry(int D, int* lanes, int* nv) {
+  int vecs = (D + 3) / 4;
+  int l = 1;
+  while (l < vecs && l < 32) l <<= 1;
+  *lanes = l;
+  *nv = (vecs + l - 1) / l;
+}
+
+int rbpr_score_free(rbpr_ctx* ctx);

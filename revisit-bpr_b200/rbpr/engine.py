@@ -1,0 +1,283 @@
+"""One native context bound to a (tables, interaction matrix) pair.
+
+PyTorch owns every tensor (so `state_dict`, checkpointing and `MF.get_features()` keep
+working); this class hands raw device pointers to librbpr.so and keeps the tensors alive.
+All work is enqueued on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from rbpr import native
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def resolve_reg(reg_alphas: dict | None) -> tuple[float, float, float]:
+    """(user, item, neg) coefficients with the reference's defaulting rules
+    (revisit_bpr/models/bpr/model.py:74-86: `all` overrides; `neg` defaults to `item`)."""
+    r = reg_alphas or {}
+    all_reg, user, item, neg = r.get("all"), r.get("user"), r.get("item"), r.get("neg")
+    if all(v is None for v in (all_reg, user, item, neg)):
+        return 0.0, 0.0, 0.0
+    if all_reg is not None:
+        user = item = neg = all_reg
+    user = user or 0
+    item = item or 0
+    neg = neg or item
+    return float(user), float(item), float(neg)
+
+
+class Engine:
+    def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor,
+                 item_bias: torch.Tensor | None = None) -> None:
+        if not user_emb.is_cuda:
+            raise native.NativeError("the BPR hot path runs on a B200 only: tables must be CUDA tensors")
+        for t in (user_emb, item_emb) + ((item_bias,) if item_bias is not None else ()):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("tables must be contiguous float32")
+        if user_emb.size(1) != item_emb.size(1):
+            raise ValueError("user and item tables must share the embedding dim")
+        self.lib = native.load()
+        self.device = user_emb.device
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.ctx = C.c_void_p()
+        rc = self.lib.rbpr_create(dev_index, C.byref(self.ctx))
+        if rc != 0:
+            raise native.NativeError(f"rbpr_create failed ({rc}): needs a compute-capability 10.x device")
+        self.user_emb, self.item_emb, self.item_bias = user_emb, item_emb, item_bias
+        self.U, self.D = user_emb.shape
+        self.I = item_emb.size(0)
+        self._check(self.lib.rbpr_bind_tables(self.ctx, _ptr(user_emb), self.U, _ptr(item_emb),
+                                              self.I, self.D, _ptr(item_bias)))
+        self.hp = native.HParams()
+        self.hp.optimizer = native.OPT_SGD
+        self.hp.sampler = native.SAMPLER_UNIFORM
+        self.hp.lr = 0.0
+        self.hp.beta1, self.hp.beta2, self.hp.eps = 0.9, 0.999, 1e-8
+        self.adam_state: dict[str, torch.Tensor] | None = None
+        self.indptr = self.indices = None
+        self.nnz = 0
+        self._alias = None
+
+    def __del__(self) -> None:
+        try:
+            if getattr(self, "ctx", None) is not None and self.ctx.value:
+                self.lib.rbpr_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        native.check(self.lib, self.ctx, rc)
+
+    # ---- configuration -------------------------------------------------------------------
+    def set_reg(self, reg_alphas: dict | None) -> None:
+        self.hp.reg_user, self.hp.reg_item, self.hp.reg_neg = resolve_reg(reg_alphas)
+
+    def set_sgd(self, lr: float) -> None:
+        self.hp.optimizer = native.OPT_SGD
+        self.hp.lr = lr
+
+    def set_adam(self, lr: float, betas: Sequence[float] = (0.9, 0.999), eps: float = 1e-8,
+                 state: dict[str, torch.Tensor] | None = None) -> dict[str, torch.Tensor]:
+        """Bind (or create zeroed) Adam state: user_m/v, user_last (int32), item_m/v, bias_m/v."""
+        self.hp.optimizer = native.OPT_ADAM
+        self.hp.lr, self.hp.beta1, self.hp.beta2, self.hp.eps = lr, betas[0], betas[1], eps
+        if state is None:
+            state = self.adam_state
+        if state is None:
+            z = torch.zeros_like
+            state = {"user_m": z(self.user_emb), "user_v": z(self.user_emb),
+                     "user_last": torch.zeros(self.U, dtype=torch.int32, device=self.device),
+                     "item_m": z(self.item_emb), "item_v": z(self.item_emb)}
+            if self.item_bias is not None:
+                state["bias_m"], state["bias_v"] = z(self.item_bias), z(self.item_bias)
+        self.adam_state = state
+        self._check(self.lib.rbpr_bind_adam_state(
+            self.ctx, _ptr(state["user_m"]), _ptr(state["user_v"]), _ptr(state["user_last"]),
+            _ptr(state["item_m"]), _ptr(state["item_v"]), _ptr(state.get("bias_m")),
+            _ptr(state.get("bias_v"))))
+        return state
+
+    def set_sampler(self, kind: int) -> None:
+        self.hp.sampler = kind
+
+    def bind_csr(self, indptr: torch.Tensor, indices: torch.Tensor) -> None:
+        """indptr (U+1,) int64, indices (nnz,) int32 ascending per row; moved to the device."""
+        indptr = indptr.to(self.device, torch.int64).contiguous()
+        indices = indices.to(self.device, torch.int32).contiguous()
+        if indptr.numel() != self.U + 1:
+            raise ValueError(f"indptr has {indptr.numel()} entries, expected num_users+1={self.U + 1}")
+        self.indptr, self.indices, self.nnz = indptr, indices, indices.numel()
+        self._check(self.lib.rbpr_bind_csr(self.ctx, _ptr(indptr), _ptr(indices), self.U, self.nnz,
+                                           _stream()))
+
+    def bind_item_weights(self, weights: torch.Tensor) -> None:
+        """Popularity weights (I,) -> Walker alias table (weights[0] is forced to 0)."""
+        w = weights.detach().double().cpu().numpy().copy()
+        w[0] = 0.0
+        prob, alias = build_alias(w)
+        self._alias = (torch.from_numpy(prob).to(self.device), torch.from_numpy(alias).to(self.device))
+        self._check(self.lib.rbpr_bind_item_alias(self.ctx, _ptr(self._alias[0]), _ptr(self._alias[1])))
+
+    # ---- hot path --------------------------------------------------------------------------
+    def sample(self, triple_idx: torch.Tensor, seed: int, step: int, sampler: int | None = None) -> torch.Tensor:
+        triple_idx = triple_idx.to(self.device, torch.int64).contiguous()
+        out = torch.empty_like(triple_idx)
+        kind = self.hp.sampler if sampler is None else sampler
+        self._check(self.lib.rbpr_sample_negatives(self.ctx, _ptr(triple_idx), triple_idx.numel(),
+                                                   seed, step, kind, _ptr(out), _stream()))
+        return out
+
+    def train_steps(self, triple_idx: torch.Tensor, batch: int, seed: int, step0: int,
+                    neg_in: torch.Tensor | None = None, want_neg: bool = False,
+                    want_stats: bool = True):
+        """Device-resident call. Returns (stats (steps,4) float64 device tensor | None, negs | None)."""
+        n = triple_idx.numel()
+        steps = (n + batch - 1) // batch
+        stats = torch.empty((steps, native.STATS_PER_STEP), dtype=torch.float64, device=self.device) \
+            if want_stats else None
+        neg_out = torch.empty(n, dtype=torch.int64, device=self.device) if want_neg else None
+        self._check(self.lib.rbpr_train_steps(self.ctx, _ptr(triple_idx), n, batch, seed, step0,
+                                              C.byref(self.hp), _ptr(neg_in), _ptr(neg_out),
+                                              _ptr(stats), _stream()))
+        return stats, neg_out
+
+    def train_steps_host(self, triple_idx: torch.Tensor, batch: int, seed: int, step0: int,
+                         neg_in: torch.Tensor | None = None, want_neg: bool = False):
+        """Host-buffer call (pinned CPU int64 in, CPU float64 stats out); synchronises."""
+        assert not triple_idx.is_cuda and triple_idx.dtype == torch.int64
+        n = triple_idx.numel()
+        steps = (n + batch - 1) // batch
+        stats = torch.empty((steps, native.STATS_PER_STEP), dtype=torch.float64).pin_memory()
+        neg_out = torch.empty(n, dtype=torch.int64).pin_memory() if want_neg else None
+        self._check(self.lib.rbpr_train_steps_host(self.ctx, _ptr(triple_idx), n, batch, seed, step0,
+                                                   C.byref(self.hp), _ptr(neg_in), _ptr(neg_out),
+                                                   _ptr(stats), _stream()))
+        return stats, neg_out
+
+    def sync_check(self) -> None:
+        self._check(self.lib.rbpr_sync_check(self.ctx, _stream()))
+
+    # ---- data-parallel split ---------------------------------------------------------------
+    def grad_step(self, triple_idx: torch.Tensor, seed: int, step: int,
+                  neg_in: torch.Tensor | None = None, want_neg: bool = False):
+        n = triple_idx.numel()
+        stats = torch.empty((1, native.STATS_PER_STEP), dtype=torch.float64, device=self.device)
+        neg_out = torch.empty(n, dtype=torch.int64, device=self.device) if want_neg else None
+        self._check(self.lib.rbpr_grad_step(self.ctx, _ptr(triple_idx), n, seed, step,
+                                            C.byref(self.hp), _ptr(neg_in), _ptr(neg_out),
+                                            _ptr(stats), _stream()))
+        return stats, neg_out
+
+    def item_grad_tensor(self) -> torch.Tensor:
+        """The context's dense item(+bias) gradient accumulator viewed as a torch tensor
+        (for torch.distributed.all_reduce). The memory stays owned by the context."""
+        ptr, numel = C.c_void_p(), C.c_int64()
+        self._check(self.lib.rbpr_item_grad_buffer(self.ctx, C.byref(ptr), C.byref(numel)))
+        return _wrap_device_f32(ptr.value, numel.value, self.device)
+
+    def apply_item_grads(self, step: int) -> None:
+        self._check(self.lib.rbpr_apply_item_grads(self.ctx, step, C.byref(self.hp), _stream()))
+
+    def flush_lazy(self, step: int) -> None:
+        self._check(self.lib.rbpr_flush_lazy(self.ctx, step, C.byref(self.hp), _stream()))
+
+    # ---- scoring ---------------------------------------------------------------------------
+    def score_topk(self, users: torch.Tensor, seen: tuple[torch.Tensor, torch.Tensor] | None,
+                   held: tuple[torch.Tensor, torch.Tensor] | None, ks: Sequence[int],
+                   k_max: int | None = None, want_items: bool = True) -> dict[str, torch.Tensor]:
+        users = users.to(self.device, torch.int64).contiguous()
+        n = users.numel()
+        ks = [int(k) for k in ks]
+        k_max = int(k_max or max(ks))
+        dev = self.device
+        seen_p = seen_i = held_p = held_i = None
+        if seen is not None:
+            seen_p, seen_i = seen[0].to(dev, torch.int64).contiguous(), seen[1].to(dev, torch.int32).contiguous()
+        if held is not None:
+            held_p, held_i = held[0].to(dev, torch.int64).contiguous(), held[1].to(dev, torch.int32).contiguous()
+        out: dict[str, torch.Tensor] = {}
+        items = scores = ndcg = recall = None
+        if want_items:
+            items = out["items"] = torch.empty((n, k_max), dtype=torch.int32, device=dev)
+            scores = out["scores"] = torch.empty((n, k_max), dtype=torch.float32, device=dev)
+        if held is not None and ks:
+            ndcg = out["ndcg"] = torch.empty((n, len(ks)), dtype=torch.float32, device=dev)
+            recall = out["recall"] = torch.empty((n, len(ks)), dtype=torch.float32, device=dev)
+        ks_arr = (C.c_int32 * max(len(ks), 1))(*ks)
+        self._check(self.lib.rbpr_score_topk(self.ctx, _ptr(users), n, _ptr(seen_p), _ptr(seen_i),
+                                             _ptr(held_p), _ptr(held_i), k_max, ks_arr, len(ks),
+                                             _ptr(items), _ptr(scores), _ptr(ndcg), _ptr(recall),
+                                             _stream()))
+        return out
+
+    def score_dense(self, users: torch.Tensor,
+                    seen: tuple[torch.Tensor, torch.Tensor] | None = None) -> torch.Tensor:
+        users = users.to(self.device, torch.int64).contiguous()
+        out = torch.empty((users.numel(), self.I), dtype=torch.float32, device=self.device)
+        seen_p = seen_i = None
+        if seen is not None:
+            seen_p = seen[0].to(self.device, torch.int64).contiguous()
+            seen_i = seen[1].to(self.device, torch.int32).contiguous()
+        self._check(self.lib.rbpr_score_dense(self.ctx, _ptr(users), users.numel(), _ptr(seen_p),
+                                              _ptr(seen_i), _ptr(out), _stream()))
+        return out
+
+    # ---- instrumentation -------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.rbpr_launch_count(self.ctx))
+
+    def kernel_timing(self, enable: bool) -> None:
+        self._check(self.lib.rbpr_kernel_timing(self.ctx, int(enable)))
+
+    def kernel_time_ms(self) -> tuple[float, int]:
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.rbpr_kernel_time_ms(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def _wrap_device_f32(ptr: int, numel: int, device: torch.device) -> torch.Tensor:
+    class _Arr:  # __cuda_array_interface__ carrier
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False),
+                                  "version": 2, "strides": None}
+    return torch.as_tensor(a, device=device)
+
+
+def build_alias(w: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Walker/Vose alias table for weights w (float64, w>=0, sum>0): column k is accepted
+    with probability prob[k], else alias[k] is returned.  Deterministic (stack order)."""
+    n = w.size
+    p = w * (n / w.sum())
+    prob = np.zeros(n, dtype=np.float64)
+    alias = np.zeros(n, dtype=np.int32)
+    small = [i for i in range(n - 1, -1, -1) if p[i] < 1.0]
+    large = [i for i in range(n - 1, -1, -1) if p[i] >= 1.0]
+    while small and large:
+        s, l = small.pop(), large.pop()
+        prob[s], alias[s] = p[s], l
+        p[l] = (p[l] + p[s]) - 1.0
+        (small if p[l] < 1.0 else large).append(l)
+    for i in large:
+        prob[i], alias[i] = 1.0, i
+    for i in small:  # numerical leftovers
+        prob[i], alias[i] = 1.0, i
+    # a zero-weight column must never return itself
+    heavy = int(np.argmax(w))
+    zero = w <= 0
+    prob[zero] = 0.0
+    alias[zero & (alias == np.arange(n))] = heavy
+    return prob.astype(np.float32), alias

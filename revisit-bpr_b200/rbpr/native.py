@@ -1,0 +1,93 @@
+"""ctypes binding of include/rbpr.h.  Loads the in-tree librbpr.so; raises if it is absent."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent.parent / "librbpr.so"
+
+OPT_SGD, OPT_ADAM = 0, 1
+SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED = 0, 1, 2
+STATS_PER_STEP = 4
+MAX_TOPK = 128
+ABI_VERSION = 1
+
+# Every symbol include/rbpr.h declares (tests check the library exports all of them).
+SYMBOLS = (
+    "rbpr_abi_version", "rbpr_create", "rbpr_destroy", "rbpr_last_error", "rbpr_bind_tables",
+    "rbpr_bind_adam_state", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_sample_negatives",
+    "rbpr_train_steps", "rbpr_sync_check", "rbpr_train_steps_host", "rbpr_grad_step",
+    "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
+    "rbpr_score_dense", "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
+)
+
+
+class HParams(C.Structure):
+    _fields_ = [
+        ("optimizer", C.c_int32), ("sampler", C.c_int32), ("lr", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("reg_user", C.c_float), ("reg_item", C.c_float), ("reg_neg", C.c_float),
+        ("reserved0", C.c_float),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load librbpr.so (once).  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("RBPR_LIB", LIB_PATH))
+    if not path.exists():
+        raise NativeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the BPR hot path."
+        )
+    lib = C.CDLL(str(path))
+    vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64
+    hp = C.POINTER(HParams)
+    sig = {
+        "rbpr_abi_version": (C.c_int, []),
+        "rbpr_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "rbpr_destroy": (None, [vp]),
+        "rbpr_last_error": (C.c_char_p, [vp]),
+        "rbpr_bind_tables": (C.c_int, [vp, vp, i64, vp, i64, i32, vp]),
+        "rbpr_bind_adam_state": (C.c_int, [vp] * 8),
+        "rbpr_bind_csr": (C.c_int, [vp, vp, vp, i64, i64, vp]),
+        "rbpr_bind_item_alias": (C.c_int, [vp, vp, vp]),
+        "rbpr_sample_negatives": (C.c_int, [vp, vp, i64, u64, u64, i32, vp, vp]),
+        "rbpr_train_steps": (C.c_int, [vp, vp, i64, i64, u64, u64, hp, vp, vp, vp, vp]),
+        "rbpr_sync_check": (C.c_int, [vp, vp]),
+        "rbpr_train_steps_host": (C.c_int, [vp, vp, i64, i64, u64, u64, hp, vp, vp, vp, vp]),
+        "rbpr_grad_step": (C.c_int, [vp, vp, i64, u64, u64, hp, vp, vp, vp, vp]),
+        "rbpr_item_grad_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "rbpr_apply_item_grads": (C.c_int, [vp, u64, hp, vp]),
+        "rbpr_flush_lazy": (C.c_int, [vp, u64, hp, vp]),
+        "rbpr_score_topk": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
+                                      vp, vp, vp, vp, vp]),
+        "rbpr_score_dense": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "rbpr_launch_count": (i64, [vp]),
+        "rbpr_kernel_timing": (C.c_int, [vp, i32]),
+        "rbpr_kernel_time_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rbpr_abi_version() != ABI_VERSION:
+        raise NativeError(f"librbpr.so ABI {lib.rbpr_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(lib: C.CDLL, ctx, rc: int) -> None:
+    if rc != 0:
+        msg = lib.rbpr_last_error(ctx)
+        raise NativeError(f"librbpr error {rc}: {msg.decode() if msg else '?'}")
