@@ -188,7 +188,8 @@ int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
 
 /* Instrumentation: number of kernels this context has launched so far, and the device time
  * (ms, CUDA events on the launch stream) spent in the dominant training kernel since the
- * last reset, with its launch count.  Timing is off unless enabled (adds 2 events/launch). */
+ * last reset, with the number of launches sampled.  Timing is off unless enabled; when on,
+ * every 8th launch of the kernel is bracketed by an event pair. */
 int64_t rbpr_launch_count(const rbpr_ctx* ctx);
 int rbpr_kernel_timing(rbpr_ctx* ctx, int32_t enable);
 int rbpr_kernel_time_ms(rbpr_ctx* ctx, double* ms_out, int64_t* launches_out);

@@ -40,6 +40,8 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->pos_out);
   cudaFree(ctx->cub_tmp);
   cudaFree(ctx->stats);
+  cudaFree(ctx->partials);
+  cudaFree(ctx->records);
   cudaFree(ctx->flag);
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);
@@ -103,6 +105,14 @@ int64_t rbpr_launch_count(const rbpr_ctx* ctx) { return ctx ? ctx->launches : 0;
 int rbpr_kernel_timing(rbpr_ctx* ctx, int32_t enable) {
   if (!ctx) return RBPR_ERR_ARG;
   ctx->timing = enable != 0;
+  if (ctx->timing) {  // pre-create events so that no cudaEventCreate lands inside a timed region
+    RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+    while (ctx->ev.size() < 2048) {
+      cudaEvent_t e;
+      RBPR_CUDA(ctx, cudaEventCreate(&e));
+      ctx->ev.push_back(e);
+    }
+  }
   return 0;
 }
 

@@ -3,9 +3,16 @@
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="$here/../librbpr.so"
+obj="$here/../build"
+mkdir -p "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-srcs=("$here"/api.cu "$here"/train.cu "$here"/score.cu)
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  -Xptxas -v -Xcompiler -fPIC,-O3 -shared \
-  -o "$out" "${srcs[@]}" 2> "$here/../build.log" || { cat "$here/../build.log"; exit 1; }
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xptxas -v -Xcompiler -fPIC,-O3)
+pids=()
+for f in api train train_sgd train_adam score; do
+  ( "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$obj/$f.o" > "$obj/$f.log" 2>&1 || { cat "$obj/$f.log"; exit 1; } ) &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "$obj"/{api,train,train_sgd,train_adam,score}.o
+cat "$obj"/*.log > "$here/../build.log"
 echo "built $out"

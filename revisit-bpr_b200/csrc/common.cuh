@@ -41,6 +41,10 @@ struct rbpr_ctx {
   int64_t cap = 0;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  void* records = nullptr;  // (records_cap) int4 {u, i+, i-, head} of the current step
+  int64_t records_cap = 0;
+  float* partials = nullptr;  // per-warp step statistics (float4 each)
+  int64_t partials_cap = 0;
   double* stats = nullptr;  // (stats_cap steps, 4)
   int64_t stats_cap = 0;
   int32_t* flag = nullptr;  // device error flag
@@ -53,6 +57,7 @@ struct rbpr_ctx {
   // instrumentation
   int64_t launches = 0;
   bool timing = false;
+  uint64_t timing_tick = 0;
   std::vector<cudaEvent_t> ev;  // pairs
   size_t ev_used = 0;
   double timed_ms = 0.0;
@@ -79,11 +84,11 @@ struct rbpr_ctx {
 // Group geometry for a row of D floats: LANES lanes (power of two, <=32) each holding NV
 // float4 vectors; column of vector v on lane gl is 4*(gl + LANES*v).
 static inline void rbpr_geometry(int D, int* lanes, int* nv) {
-  int vecs = (D + 3) / 4;
+  const int vecs = (D + 3) / 4;
+  const int want = (vecs + 3) / 4;  // aim for 4 float4 per lane: 32/LANES triples per warp
   int l = 1;
-  while (l < vecs && l < 32) l <<= 1;
+  while (l < want && l < 32) l <<= 1;
   *lanes = l;
   *nv = (vecs + l - 1) / l;
 }
 
-int rbpr_score_free(rbpr_ctx* ctx);

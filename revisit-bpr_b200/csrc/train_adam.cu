@@ -1,0 +1,51 @@
+// ADAM instantiations of the fused training kernels (see train_kernels.cuh).
+#include "train_kernels.cuh"
+
+using namespace rbpr_dev;
+
+int rbpr_launch_phase_a_adam(rbpr_ctx* ctx, const TrainParams& p, int lanes, int nv,
+                              const int4* records, int* warps_out, cudaStream_t st) {
+  const int groups_per_block = kPhaseAThreads / lanes;
+  const int64_t groups = ((int64_t)p.n + p.chunk - 1) / p.chunk;
+  const int blocks = (int)((groups + groups_per_block - 1) / groups_per_block);
+  *warps_out = blocks * (kPhaseAThreads / 32);
+#define X(L, V)                                                       \
+  if (lanes == L && nv == V) {                                        \
+    bpr_phase_a<L, V, RBPR_OPT_ADAM><<<blocks, kPhaseAThreads, 0, st>>>(p, records);  \
+    return 0;                                                         \
+  }
+  RBPR_FOR_EACH_GEOMETRY(X)
+#undef X
+  RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
+}
+
+int rbpr_launch_apply_adam(rbpr_ctx* ctx, const ApplyParams& p, int lanes, int nv,
+                            cudaStream_t st) {
+  const int groups_per_block = 256 / lanes;
+  const int64_t blocks64 = (p.I + groups_per_block - 1) / groups_per_block;
+  const int64_t maxb = (int64_t)ctx->sm_count * 8;
+  const int blocks = (int)(blocks64 < maxb ? blocks64 : maxb);
+#define X(L, V)                                                   \
+  if (lanes == L && nv == V) {                                    \
+    bpr_apply_items<L, V, RBPR_OPT_ADAM><<<blocks, 256, 0, st>>>(p);      \
+    return 0;                                                     \
+  }
+  RBPR_FOR_EACH_GEOMETRY(X)
+#undef X
+  RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
+}
+
+int rbpr_launch_flush_users(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv,
+                            cudaStream_t st) {
+  const int blocks = ctx->sm_count * 8;
+#define X(L, V)                                                                             \
+  if (lanes == L && nv == V) {                                                              \
+    bpr_flush_users<L, V><<<blocks, 256, 0, st>>>(ctx->user_emb, ctx->user_m, ctx->user_v,  \
+                                                  ctx->user_last, ctx->U, ctx->D, step,     \
+                                                  hp->lr, hp->beta1, hp->beta2, hp->eps);   \
+    return 0;                                                                               \
+  }
+  RBPR_FOR_EACH_GEOMETRY(X)
+#undef X
+  RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
+}

@@ -1,0 +1,533 @@
+// Device code of the fused BPR training step (sm_100a).  See train.cu for the step structure.
+//
+// Row geometry: a row of D floats is held by a GROUP of LANES lanes (power of two, D/16 when D is
+// a multiple of 16), each lane keeping NV (<=4, or up to 8 for D>512) float4 vectors; column of
+// vector v on group lane gl is 4*(gl + LANES*v).  A warp therefore works on 32/LANES triples at
+// once (4 for D=128), which amortises the lane-uniform work (Philox, CSR probe, index math) and
+// keeps 32/LANES * 2 * NV 128-bit row loads in flight per warp.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace rbpr_dev {
+
+struct TrainParams {
+  float* __restrict__ user_emb;
+  const float* __restrict__ item_emb;
+  const float* __restrict__ item_bias;
+  float* __restrict__ user_m;
+  float* __restrict__ user_v;
+  int32_t* __restrict__ user_last;
+  float* __restrict__ item_grad;  // (I,D) dense accumulator
+  float* __restrict__ bias_grad;  // (I) or null
+  uint32_t* __restrict__ touched;
+  const int64_t* __restrict__ indptr;
+  const int32_t* __restrict__ indices;
+  const int32_t* __restrict__ coo_user;
+  const uint64_t* __restrict__ keys;  // sorted (step<<32|t) of this step
+  const int32_t* __restrict__ pos;    // original positions (or null)
+  const int64_t* __restrict__ neg_in;
+  int64_t* __restrict__ neg_out;
+  const float* __restrict__ alias_prob;
+  const int32_t* __restrict__ alias_idx;
+  float4* __restrict__ partials;  // one float4 of step statistics per warp
+  int32_t* __restrict__ flag;
+  int n;      // triples in this step
+  int chunk;  // triples per group
+  int D;
+  uint32_t I;
+  uint32_t draw_n;       // I-1 (uniform) or I (alias)
+  uint32_t draw_thresh;  // 2^32 mod draw_n (Lemire rejection threshold)
+  uint32_t seed_lo, seed_hi;
+  uint64_t step;  // global 0-based step -> sampler counter; Adam applies step+1
+  int sampler;
+  float lr, beta1, beta2, eps;
+  float reg_user, reg_item, reg_neg;
+};
+
+struct ApplyParams {
+  float* __restrict__ item_emb;
+  float* __restrict__ item_bias;
+  float* __restrict__ item_m;
+  float* __restrict__ item_v;
+  float* __restrict__ bias_m;
+  float* __restrict__ bias_v;
+  float* __restrict__ item_grad;
+  float* __restrict__ bias_grad;
+  uint32_t* __restrict__ touched;
+  int64_t I;
+  int D;
+  int dense;  // 1: ignore touched flags (multi-GPU / Adam)
+  uint64_t step;
+  float lr, beta1, beta2, eps;
+};
+
+template <int LANES>
+struct Group {
+  int gl;         // lane within group
+  unsigned mask;  // lanes of this group
+  int shift;      // first lane of the group within the warp
+  __device__ __forceinline__ Group() {
+    const int lane = threadIdx.x & 31;
+    gl = lane & (LANES - 1);
+    shift = lane - gl;
+    mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << shift);
+  }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+  }
+};
+
+// Is item j present in the ascending row idx[lo,hi)?  (LANES+1)-ary cooperative search;
+// 32-bit offsets (nnz < 2^32 is enforced at bind time).
+template <int LANES>
+__device__ __forceinline__ bool row_contains(const int32_t* __restrict__ idx, uint32_t lo,
+                                             uint32_t hi, int32_t j, const Group<LANES>& g) {
+  while (true) {
+    if (hi <= lo) return false;
+    const uint32_t n = hi - lo;
+    if (n <= (uint32_t)LANES) {
+      const int32_t v = ((uint32_t)g.gl < n) ? __ldg(idx + lo + g.gl) : -1;
+      return __ballot_sync(g.mask, v == j) != 0u;
+    }
+    // pivots p_l = lo + (l+1)*n/(LANES+1); n < 2^32/(LANES+1) is guaranteed for rows (< num_items)
+    const uint32_t p = lo + ((uint32_t)(g.gl + 1) * n) / (uint32_t)(LANES + 1);
+    const int32_t v = __ldg(idx + p);
+    if (__ballot_sync(g.mask, v == j) != 0u) return true;
+    const unsigned lt = __ballot_sync(g.mask, v < j) >> g.shift;
+    const uint32_t k = (uint32_t)__popc(lt);
+    const uint32_t plo = lo + (k * n) / (uint32_t)(LANES + 1);
+    const uint32_t phi = lo + ((k + 1u) * n) / (uint32_t)(LANES + 1);
+    const uint32_t nlo = (k == 0u) ? lo : plo + 1u;
+    const uint32_t nhi = (k == (uint32_t)LANES) ? hi : phi;
+    lo = nlo;
+    hi = nhi;
+  }
+}
+
+// Counter-based negative draw.  All lanes of the group evaluate the same Philox
+// block, so control flow is group-uniform.  Returns -1 after 256 blocks of failed attempts.
+template <int LANES>
+__device__ __forceinline__ int32_t draw_negative(const TrainParams& p, uint32_t t, uint32_t lo,
+                                                 uint32_t hi, const Group<LANES>& g) {
+  const uint32_t n = p.draw_n, thresh = p.draw_thresh;
+  const uint32_t step_lo = (uint32_t)(p.step << 8), step_hi = (uint32_t)(p.step >> 24);
+  for (uint32_t blk = 0; blk < 256u; ++blk) {
+    const philox4 r = philox4x32_10(step_lo | blk, step_hi, t, 0u, p.seed_lo, p.seed_hi);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    if (p.sampler == RBPR_SAMPLER_UNIFORM) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const uint32_t mlo = w[a] * n, mhi = __umulhi(w[a], n);
+        if (mlo < thresh) continue;  // Lemire rejection: exactly uniform
+        const int32_t j = 1 + (int32_t)mhi;
+        if (!row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
+      }
+    } else {  // Walker alias over [0,I), two words per attempt
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const uint32_t mlo = w[2 * a] * n, mhi = __umulhi(w[2 * a], n);
+        if (mlo < thresh) continue;
+        const int32_t col = (int32_t)mhi;
+        const float uf = (float)(w[2 * a + 1] >> 8) * (1.0f / 16777216.0f);
+        const int32_t j = (uf < __ldg(p.alias_prob + col)) ? col : __ldg(p.alias_idx + col);
+        if (j == 0) continue;
+        if (!row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
+      }
+    }
+  }
+  return -1;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// torch.optim.Adam (no amsgrad, no weight decay) arithmetic for one element:
+// m.lerp_(g, 1-b1); v = b2 v + (1-b2) g²; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float b1, float b2,
+                                      float eps, float step_size, float bc2_sqrt) {
+  m = m + (g - m) * (1.0f - b1);
+  v = v * b2 + (1.0f - b2) * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+__device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, float4 g, float b1,
+                                      float b2, float eps, float step_size, float bc2_sqrt) {
+  adam1(p.x, m.x, v.x, g.x, b1, b2, eps, step_size, bc2_sqrt);
+  adam1(p.y, m.y, v.y, g.y, b1, b2, eps, step_size, bc2_sqrt);
+  adam1(p.z, m.z, v.z, g.z, b1, b2, eps, step_size, bc2_sqrt);
+  adam1(p.w, m.w, v.w, g.w, b1, b2, eps, step_size, bc2_sqrt);
+}
+
+// Replay Adam steps from+1..to with zero gradient (dense-Adam semantics for a row that received
+// no gradient in those steps).
+__device__ __forceinline__ void adam_catchup4(float4& p, float4& m, float4& v, int64_t from,
+                                              int64_t to, float lr, float b1, float b2,
+                                              float eps) {
+  if (to <= from) return;
+  double b1p = pow((double)b1, (double)from), b2p = pow((double)b2, (double)from);
+  for (int64_t s = from + 1; s <= to; ++s) {
+    b1p *= (double)b1;
+    b2p *= (double)b2;
+    const float step_size = (float)((double)lr / (1.0 - b1p));
+    const float bc2_sqrt = (float)sqrt(1.0 - b2p);
+    adam4(p, m, v, f4zero(), b1, b2, eps, step_size, bc2_sqrt);
+  }
+}
+
+constexpr int kPhaseAThreads = 128;
+
+// P1 — negative sampling for EVERY step of a call in one launch.  A group of 8 lanes per sorted
+// slot resolves (user, item), draws the negative with a cooperative 9-ary CSR probe, and emits a
+// 16-byte record {u, i+, i-, head} (head = first triple of a user run inside its step).  The
+// static samplers depend only on (seed, step, triple, CSR), never on the model, so the whole
+// call's dependent-load chains (keys -> coo/indices -> indptr -> probes) run at full occupancy
+// here instead of sitting on the critical path of the row-gather kernel.
+constexpr int kSampleLanes = 8;
+static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __restrict__ records,
+                                                         uint64_t n_slots, uint64_t step0) {
+  const Group<kSampleLanes> g;
+  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSampleLanes;
+  if (k >= n_slots) return;  // whole group leaves together
+  const uint64_t key = __ldg(p.keys + k);
+  const uint32_t t = (uint32_t)key;
+  const int32_t uu = __ldg(p.coo_user + t);
+  const int32_t i = __ldg(p.indices + t);
+  int32_t head = 1;
+  if (k > 0u) {
+    const uint64_t kprev = __ldg(p.keys + k - 1);
+    head = ((kprev >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)kprev) != uu) ? 1 : 0;
+  }
+  int32_t j;
+  if (p.sampler == RBPR_SAMPLER_INJECTED) {
+    j = (int32_t)__ldg(p.neg_in + __ldg(p.pos + k));
+  } else {
+    p.step = step0 + (key >> 32);
+    const uint32_t lo = (uint32_t)__ldg(p.indptr + uu), hi = (uint32_t)__ldg(p.indptr + uu + 1);
+    j = draw_negative<kSampleLanes>(p, t, lo, hi, g);
+    if (j < 0) {
+      if (g.gl == 0) atomicExch(p.flag, 1);
+      j = 1;
+    }
+  }
+  if (g.gl == 0) {
+    if (records != nullptr) records[k] = make_int4(uu, i, j, head);
+    if (p.neg_out != nullptr) p.neg_out[__ldg(p.pos + k)] = (int64_t)j;
+  }
+}
+
+// P2 — row gather / loss / gradients.  A group owns the records [start, start+chunk) and
+// every user run that starts among them; records are read with one coalesced 16-byte load per
+// lane and broadcast with shuffles, so the only dependent global loads are the rows themselves.
+template <int LANES, int NV, int OPT>
+__global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams p,
+                                                              const int4* __restrict__ records) {
+  const Group<LANES> g;
+  const int D = p.D;
+  constexpr int GROUPS_PER_BLOCK = kPhaseAThreads / LANES;
+  const uint32_t gid = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LANES;
+  const uint32_t n = (uint32_t)p.n;
+  const uint32_t start = gid * (uint32_t)p.chunk;  // chunk <= LANES (window = LANES records)
+  const uint32_t end = min(start + (uint32_t)p.chunk, n);
+
+  float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
+
+  bool colok[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
+
+  // window of LANES records, one per lane
+  uint32_t wb = start;
+  int4 rec = (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
+  // first run head inside my chunk (runs that started earlier belong to the previous group)
+  uint32_t k = n;
+  {
+    const unsigned heads =
+        (__ballot_sync(g.mask, rec.w != 0 && rec.x >= 0 && wb + g.gl < end) >> g.shift);
+    if (heads != 0u && start < n) k = start + (uint32_t)(__ffs(heads) - 1);
+  }
+
+  int32_t cur_u = -1;
+  float4 u[NV], gu[NV];
+  float usq = 0.f;
+  int nocc = 0;
+
+  auto flush_user = [&]() {
+    if (cur_u < 0) return;
+    float* urow = p.user_emb + (size_t)cur_u * D;
+    const float rn = p.reg_user * (float)nocc;
+    if (OPT == RBPR_OPT_SGD) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!colok[v]) continue;
+        float4 o;
+        o.x = u[v].x - p.lr * (gu[v].x + rn * u[v].x);
+        o.y = u[v].y - p.lr * (gu[v].y + rn * u[v].y);
+        o.z = u[v].z - p.lr * (gu[v].z + rn * u[v].z);
+        o.w = u[v].w - p.lr * (gu[v].w + rn * u[v].w);
+        st4(urow + 4 * (g.gl + LANES * v), o);
+      }
+    } else {
+      const int64_t s = (int64_t)p.step + 1;  // 1-based optimizer step being applied
+      const double b1p = pow((double)p.beta1, (double)s), b2p = pow((double)p.beta2, (double)s);
+      const float step_size = (float)((double)p.lr / (1.0 - b1p));
+      const float bc2_sqrt = (float)sqrt(1.0 - b2p);
+      float* mrow = p.user_m + (size_t)cur_u * D;
+      float* vrow = p.user_v + (size_t)cur_u * D;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!colok[v]) continue;
+        const int c = 4 * (g.gl + LANES * v);
+        float4 m = ld4(mrow + c), vv = ld4(vrow + c);
+        float4 grad;
+        grad.x = gu[v].x + rn * u[v].x;
+        grad.y = gu[v].y + rn * u[v].y;
+        grad.z = gu[v].z + rn * u[v].z;
+        grad.w = gu[v].w + rn * u[v].w;
+        float4 pp = u[v];  // already caught up to step s-1 at load time
+        adam4(pp, m, vv, grad, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+        st4(urow + c, pp);
+        st4(mrow + c, m);
+        st4(vrow + c, vv);
+      }
+      if (g.gl == 0) p.user_last[cur_u] = (int32_t)s;
+    }
+  };
+
+  while (k < n) {
+    if (k >= wb + (uint32_t)LANES) {
+      wb += (uint32_t)LANES;
+      rec = (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
+    }
+    const int src = g.shift + (int)(k - wb);
+    const int32_t uu = __shfl_sync(g.mask, rec.x, src);
+    const int32_t i = __shfl_sync(g.mask, rec.y, src);
+    const int32_t j = __shfl_sync(g.mask, rec.z, src);
+    const int32_t head = __shfl_sync(g.mask, rec.w, src);
+    if (head) {
+      if (k >= end) break;  // that run belongs to the next group
+      flush_user();
+      cur_u = uu;
+      nocc = 0;
+      const float* urow = p.user_emb + (size_t)uu * D;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        u[v] = colok[v] ? ld4(urow + 4 * (g.gl + LANES * v)) : f4zero();
+        gu[v] = f4zero();
+      }
+      if (OPT == RBPR_OPT_ADAM) {
+        const int64_t last = p.user_last[uu];
+        const int64_t upto = (int64_t)p.step;  // optimizer steps already taken globally
+        if (last > 0 && last < upto) {
+          float* mrow = p.user_m + (size_t)uu * D;
+          float* vrow = p.user_v + (size_t)uu * D;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (!colok[v]) continue;
+            const int c = 4 * (g.gl + LANES * v);
+            float4 m = ld4(mrow + c), vv = ld4(vrow + c);
+            adam_catchup4(u[v], m, vv, last, upto, p.lr, p.beta1, p.beta2, p.eps);
+            st4(mrow + c, m);
+            st4(vrow + c, vv);
+          }
+        }
+      }
+    }
+    const float* irow = p.item_emb + (size_t)i * D;
+    const float* jrow = p.item_emb + (size_t)j * D;
+    float4 vi[NV], vj[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      vi[v] = colok[v] ? ld4(irow + 4 * (g.gl + LANES * v)) : f4zero();
+      vj[v] = colok[v] ? ld4(jrow + 4 * (g.gl + LANES * v)) : f4zero();
+    }
+    if (head) {
+      usq = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) usq += dot4(u[v], u[v]);
+      usq *= p.reg_user;
+    }
+    float part = 0.f, sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      part += dot4(u[v], vi[v]) - dot4(u[v], vj[v]);
+      sq += p.reg_item * dot4(vi[v], vi[v]) + p.reg_neg * dot4(vj[v], vj[v]);
+    }
+    float x = g.sum(part);
+    if (p.item_bias != nullptr) x += __ldg(p.item_bias + i) - __ldg(p.item_bias + j);
+    // softplus(-x) and c = sigmoid(-x), overflow-safe; fast intrinsics: abs err ~1e-7 on a
+    // per-triple loss of O(1), inside the 1e-4 parity budget
+    const float e = __expf(-fabsf(x));
+    const float sp = fmaxf(-x, 0.f) + __logf(1.0f + e);
+    const float inv = __fdividef(1.0f, 1.0f + e);
+    const float c = (x >= 0.f) ? e * inv : inv;
+    l2_acc += 0.5f * (sq + usq);
+    if (g.gl == 0) {
+      loss_acc += sp;
+      absx_acc += fabsf(x);
+      cnt_acc += 1.f;
+      p.touched[i] = 1u;
+      p.touched[j] = 1u;
+      if (p.bias_grad != nullptr) {
+        atomicAdd(p.bias_grad + i, -c);
+        atomicAdd(p.bias_grad + j, c);
+      }
+    }
+    float* gi = p.item_grad + (size_t)i * D;
+    float* gj = p.item_grad + (size_t)j * D;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!colok[v]) continue;
+      const int cidx = 4 * (g.gl + LANES * v);
+      const float4 cu = make_float4(c * u[v].x, c * u[v].y, c * u[v].z, c * u[v].w);
+      float4 a, b;
+      a.x = p.reg_item * vi[v].x - cu.x;
+      a.y = p.reg_item * vi[v].y - cu.y;
+      a.z = p.reg_item * vi[v].z - cu.z;
+      a.w = p.reg_item * vi[v].w - cu.w;
+      b.x = p.reg_neg * vj[v].x + cu.x;
+      b.y = p.reg_neg * vj[v].y + cu.y;
+      b.z = p.reg_neg * vj[v].z + cu.z;
+      b.w = p.reg_neg * vj[v].w + cu.w;
+      red4(gi + cidx, a);
+      red4(gj + cidx, b);
+      gu[v].x -= c * (vi[v].x - vj[v].x);
+      gu[v].y -= c * (vi[v].y - vj[v].y);
+      gu[v].z -= c * (vi[v].z - vj[v].z);
+      gu[v].w -= c * (vi[v].w - vj[v].w);
+    }
+    ++nocc;
+    ++k;
+  }
+  flush_user();
+
+  // per-warp statistics partial (no block barrier: warps retire independently)
+  float a = loss_acc, b = l2_acc, cabs = absx_acc, d = cnt_acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    cabs += __shfl_xor_sync(0xffffffffu, cabs, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if ((threadIdx.x & 31) == 0)
+    p.partials[blockIdx.x * (kPhaseAThreads / 32) + (threadIdx.x >> 5)] = make_float4(a, b, cabs, d);
+}
+
+template <int LANES, int NV, int OPT>
+__global__ void __launch_bounds__(256) bpr_apply_items(const ApplyParams p) {
+  const Group<LANES> g;
+  const int D = p.D;
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  if (OPT == RBPR_OPT_ADAM) {
+    const double s = (double)(p.step + 1);
+    step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, s)));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, s));
+  }
+  for (; r < p.I; r += groups) {
+    if (!p.dense) {
+      if (p.touched[r] == 0u) continue;
+    }
+    float* grow = p.item_grad + r * D;
+    float* prow = p.item_emb + r * D;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (g.gl + LANES * v);
+      if (c >= D) continue;
+      const float4 gr = ld4(grow + c);
+      float4 pp = ld4(prow + c);
+      if (OPT == RBPR_OPT_SGD) {
+        pp.x -= p.lr * gr.x;
+        pp.y -= p.lr * gr.y;
+        pp.z -= p.lr * gr.z;
+        pp.w -= p.lr * gr.w;
+      } else {
+        float4 m = ld4(p.item_m + r * D + c), vv = ld4(p.item_v + r * D + c);
+        adam4(pp, m, vv, gr, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+        st4(p.item_m + r * D + c, m);
+        st4(p.item_v + r * D + c, vv);
+      }
+      st4(prow + c, pp);
+      st4(grow + c, f4zero());
+    }
+    if (g.gl == 0) {
+      p.touched[r] = 0u;
+      if (p.bias_grad != nullptr) {
+        const float gb = p.bias_grad[r];
+        float b = p.item_bias[r];
+        if (OPT == RBPR_OPT_SGD) {
+          b -= p.lr * gb;
+        } else {
+          float m = p.bias_m[r], vv = p.bias_v[r];
+          adam1(b, m, vv, gb, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+          p.bias_m[r] = m;
+          p.bias_v[r] = vv;
+        }
+        p.item_bias[r] = b;
+        p.bias_grad[r] = 0.f;
+      }
+    }
+  }
+}
+
+// Bring all user rows to `step` applied Adam steps (dense semantics), grid-stride over rows.
+template <int LANES, int NV>
+__global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_emb,
+                                                       float* __restrict__ user_m,
+                                                       float* __restrict__ user_v,
+                                                       int32_t* __restrict__ user_last, int64_t U,
+                                                       int D, int64_t step, float lr, float b1,
+                                                       float b2, float eps) {
+  const Group<LANES> g;
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < U; r += groups) {
+    const int64_t last = user_last[r];
+    if (last <= 0 || last >= step) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (g.gl + LANES * v);
+      if (c >= D) continue;
+      float4 pp = ld4(user_emb + r * D + c), m = ld4(user_m + r * D + c),
+             vv = ld4(user_v + r * D + c);
+      adam_catchup4(pp, m, vv, last, step, lr, b1, b2, eps);
+      st4(user_emb + r * D + c, pp);
+      st4(user_m + r * D + c, m);
+      st4(user_v + r * D + c, vv);
+    }
+    __syncwarp(g.mask);
+    if (g.gl == 0) user_last[r] = (int32_t)step;
+  }
+}
+
+}  // namespace rbpr_dev
+
+// Per-optimizer launchers (train_sgd.cu / train_adam.cu), one translation unit each so the
+// template instantiations compile in parallel.
+int rbpr_launch_phase_a_sgd(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,
+                            const int4* records, int* warps_out, cudaStream_t st);
+int rbpr_launch_phase_a_adam(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,
+                             const int4* records, int* warps_out, cudaStream_t st);
+int rbpr_launch_apply_sgd(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,
+                          cudaStream_t st);
+int rbpr_launch_apply_adam(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,
+                           cudaStream_t st);
+int rbpr_launch_flush_users(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv,
+                            cudaStream_t st);
+
+// Instantiate every supported (LANES, NV) pair: NV<=4 for any lane count, NV 5..8 for 32 lanes.
+#define RBPR_FOR_EACH_GEOMETRY(X)                                                            \
+  X(1, 1) X(1, 2) X(1, 3) X(1, 4) X(2, 3) X(2, 4) X(4, 3) X(4, 4) X(8, 3) X(8, 4)    \
+  X(16, 3) X(16, 4) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8)
