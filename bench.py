@@ -15,7 +15,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -47,7 +46,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic matrix (tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=20)
-    ap.add_argument("--e2e-steps-per-call", type=int, default=10,
+    ap.add_argument("--e2e-steps-per-call", type=int, default=25,
                     help="steps handed to one host-buffer API call in the e2e leg")
     return ap.parse_args()
 
@@ -79,40 +78,59 @@ def init_tables(U: int, I: int, D: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    In-process NVML thread (light queries every 5 ms): a polling `nvidia-smi -lms` child process
+    was seen to stall the CUDA driver for hundreds of ms at a time on these boxes."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.rows: list[list[str]] = []
-        self.proc = None
+        self.rows: list[tuple[float, float, int]] = []
+        self.h = None
+        self._stop = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.h = None
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def mark(self):
         return len(self.rows)
 
     def stop(self, start_row: int = 0) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = self.rows[start_row:] or self.rows[-3:]
-        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        self._stop = True
+        self.th.join(timeout=1.0)
+        rows = self.rows[max(0, start_row - 1):] or self.rows[-3:]
+        sm = [r[1] for r in rows]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        reasons = [n for n, b in zip(self.NAMES, self.bits) if mask & b]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm,
                 "reasons": reasons, "samples": len(rows)}
 
 
@@ -261,13 +279,13 @@ def run_ours(args) -> None:
             out.append(st)
         return torch.cat(out)
 
-    # ---- warm-up ----
+    # ---- warm-up (the clock sampler starts first: nvidia-smi's start-up must not overlap the timed region) ----
+    clocks = ClockSampler(local) if rank == 0 else None
     run_steps(perm[:W * B], 0)
     barrier()
     eng.sync_check()
 
     # ---- timed: device-resident ----
-    clocks = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     eng.kernel_timing(True)
     eng.kernel_time_ms()
@@ -339,7 +357,7 @@ def run_ours(args) -> None:
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(D, B),
                          "kernel": "bpr_phase_a", "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_avg": (k_ms / k_n) if k_n else None, "kernel_launches_timed": k_n,
-                         "kernel_share_of_step": (k_ms / ms) if k_n else None, "peak_source": peak_src,
+                         "kernel_share_of_step": (k_ms / k_n * K / ms) if k_n else None, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
             "e2e": {"value": K * B * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": 4 * 8, "ms_per_step": 1e3 * e2e_s / K,

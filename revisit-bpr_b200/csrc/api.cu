@@ -24,6 +24,15 @@ int rbpr_create(int device, rbpr_ctx** out) {
     delete ctx;
     return RBPR_ERR_CUDA;
   }
+  bool ok = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&ctx->ev_ready[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    rbpr_destroy(ctx);
+    return RBPR_ERR_CUDA;
+  }
   *out = ctx;
   return 0;
 }
@@ -40,8 +49,14 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->pos_out);
   cudaFree(ctx->cub_tmp);
   cudaFree(ctx->stats);
-  cudaFree(ctx->partials);
-  cudaFree(ctx->records);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(ctx->partials[b]);
+    cudaFree(ctx->records[b]);
+    if (ctx->ev_ready[b]) cudaEventDestroy(ctx->ev_ready[b]);
+    if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+  }
+  if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   cudaFree(ctx->flag);
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);
@@ -80,6 +95,7 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
   ctx->U = num_users;
   ctx->I = num_items;
   ctx->D = dim;
+  ctx->phase_a_blocks_per_sm[0] = ctx->phase_a_blocks_per_sm[1] = 0;
   return 0;
 }
 

@@ -2,11 +2,11 @@
 # Build librbpr.so for sm_100a (in-tree; the .so is git-ignored but travels with gpurun).
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-out="$here/../librbpr.so"
-obj="$here/../build"
+out="${RBPR_OUT:-$here/../librbpr.so}"
+obj="${RBPR_OBJ:-$here/../build}"
 mkdir -p "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xptxas -v -Xcompiler -fPIC,-O3)
+FLAGS=(${RBPR_DEFS:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xptxas -v -Xcompiler -fPIC,-O3)
 pids=()
 for f in api train train_sgd train_adam score; do
   ( "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$obj/$f.o" > "$obj/$f.log" 2>&1 || { cat "$obj/$f.log"; exit 1; } ) &

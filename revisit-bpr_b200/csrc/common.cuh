@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -41,10 +42,15 @@ struct rbpr_ctx {
   int64_t cap = 0;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  void* records = nullptr;  // (records_cap) int4 {u, i+, i-, head} of the current step
+  // per-wave scratch, double-buffered: wave w+1 is sorted/sampled on `aux` while wave w trains
+  void* records[2] = {nullptr, nullptr};  // (records_cap) int4 {u, i+, i-, head}
   int64_t records_cap = 0;
-  float* partials = nullptr;  // per-warp step statistics (float4 each)
+  float* partials[2] = {nullptr, nullptr};  // per-warp step statistics (float4 each)
   int64_t partials_cap = 0;
+  cudaStream_t aux = nullptr;            // preparation stream (sort + negative sampling)
+  cudaEvent_t ev_inputs = nullptr;       // caller's stream -> aux: inputs of the call are ready
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr};  // aux -> main: records[b] are ready
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};   // main -> aux: records[b] may be overwritten
   double* stats = nullptr;  // (stats_cap steps, 4)
   int64_t stats_cap = 0;
   int32_t* flag = nullptr;  // device error flag
@@ -63,6 +69,7 @@ struct rbpr_ctx {
   double timed_ms = 0.0;
   int64_t timed_launches = 0;
   int sm_count = 148;
+  int phase_a_blocks_per_sm[2] = {0, 0};  // per optimizer, for the bound dim (0 = not prepared)
 };
 
 #define RBPR_FAIL(ctx, code, ...)                     \
@@ -81,14 +88,15 @@ struct rbpr_ctx {
                 __FILE__, __LINE__);                                                    \
   } while (0)
 
-// Group geometry for a row of D floats: LANES lanes (power of two, <=32) each holding NV
-// float4 vectors; column of vector v on lane gl is 4*(gl + LANES*v).
+// Group geometry for a row of D floats: LANES lanes (power of two, <=32) each holding NV float4
+// vectors; column of vector v on lane gl is 4*(gl + LANES*v).  Two float4 per lane up to D=256
+// (16 lanes at D=128: two triples per warp), more vectors per lane beyond.  Measured on B200 at
+// D=128 (profiles/r01h_matrix.txt): 8x4, 16x2 and 32x1 are within 5% of each other, 16x2 best.
 static inline void rbpr_geometry(int D, int* lanes, int* nv) {
   const int vecs = (D + 3) / 4;
-  const int want = (vecs + 3) / 4;  // aim for 4 float4 per lane: 32/LANES triples per warp
+  const int want = (vecs + 1) / 2;
   int l = 1;
   while (l < want && l < 32) l <<= 1;
   *lanes = l;
   *nv = (vecs + l - 1) / l;
 }
-

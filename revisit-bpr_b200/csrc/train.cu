@@ -22,6 +22,9 @@ using namespace rbpr_dev;
 
 namespace {
 
+constexpr int64_t kWaveTriples = 1ll << 19;       // triples sorted + sampled per preparation wave
+constexpr int64_t kFirstWaveTriples = 1ll << 17;  // ... of the first wave of a call
+
 // One block per step: sums the per-warp float4 partials of that step in double.
 __global__ void reduce_stats(const float4* __restrict__ partials, int stride, double* __restrict__ out) {
   __shared__ double red[4][8];
@@ -150,8 +153,9 @@ int ensure_capacity(rbpr_ctx* ctx, int64_t n, int64_t steps) {
     cudaFree(ctx->stats);
     ctx->stats = nullptr;
     ctx->stats_cap = 0;
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->stats, steps * RBPR_STATS_PER_STEP * sizeof(double)));
-    ctx->stats_cap = steps;
+    const int64_t cap = steps > 4096 ? steps : 4096;
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->stats, cap * RBPR_STATS_PER_STEP * sizeof(double)));
+    ctx->stats_cap = cap;
   }
   return 0;
 }
@@ -241,53 +245,64 @@ int sort_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t ba
   return 0;
 }
 
-int pick_chunk(rbpr_ctx* ctx, int64_t n, int lanes) {
-  const char* e = getenv("RBPR_CHUNK");  // tuning override
-  int64_t c = lanes;
-  if (e && atoi(e) > 0) {
-    c = atoi(e);
-  } else {
-    // small steps: trade window efficiency for parallelism (aim for >= 1 group per resident slot)
-    const int64_t resident_groups = (int64_t)ctx->sm_count * 16 * (32 / lanes);
-    c = n / resident_groups;
+// Lane groups per launch: the grid is ONE resident wave (every CTA co-resident, the same number
+// of CTAs on every SM, no tail wave); group g walks records [g*n/G, (g+1)*n/G) with kStages
+// triples of rows in flight.  Returns G (a multiple of the groups per CTA).
+int pick_groups(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t n, int lanes, int nv, int* groups) {
+  const int o = hp->optimizer == RBPR_OPT_ADAM ? 1 : 0;
+  if (ctx->phase_a_blocks_per_sm[o] == 0) {
+    int bps = 0;
+    int rc = o ? rbpr_phase_a_prepare_adam(ctx, ctx->D, lanes, nv, &bps)
+               : rbpr_phase_a_prepare_sgd(ctx, ctx->D, lanes, nv, &bps);
+    if (rc) return rc;
+    if (bps < 1) RBPR_FAIL(ctx, RBPR_ERR_CUDA, "phase-A kernel does not fit on an SM (dim=%d)", ctx->D);
+    ctx->phase_a_blocks_per_sm[o] = bps;
   }
-  if (c < 1) c = 1;
-  if (c > lanes) c = lanes;
-  return (int)c;
-}
-
-int warps_for(int64_t n, int chunk, int lanes) {
   const int gpb = kPhaseAThreads / lanes;
-  const int64_t groups = (n + chunk - 1) / chunk;
-  return (int)(((groups + gpb - 1) / gpb) * (kPhaseAThreads / 32));
+  const int64_t resident_blocks = (int64_t)ctx->sm_count * ctx->phase_a_blocks_per_sm[o];
+  int64_t blocks = (n + gpb - 1) / gpb;  // one triple per group
+  if (blocks > resident_blocks) blocks = resident_blocks;
+  const char* e = getenv("RBPR_CHUNK");  // tuning override: triples per group
+  if (e && atoi(e) > 0) blocks = ((n + atoi(e) - 1) / atoi(e) + gpb - 1) / gpb;
+  if (blocks < 1) blocks = 1;
+  *groups = (int)(blocks * gpb);
+  return 0;
 }
 
-// Scratch for one call: 16-byte record per triple, `steps` x `stride` float4 statistics partials.
-int ensure_step_scratch(rbpr_ctx* ctx, int64_t n, int64_t steps, int stride, cudaStream_t st) {
+int warps_for(int groups, int lanes) { return groups / (kPhaseAThreads / lanes) * (kPhaseAThreads / 32); }
+
+// Scratch for one wave (both buffers): 16-byte record per triple, `steps` x `stride` float4
+// statistics partials.
+int ensure_step_scratch(rbpr_ctx* ctx, int64_t n, int64_t steps, int stride) {
   if (n > ctx->records_cap) {
-    cudaFree(ctx->records);
-    ctx->records = nullptr;
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(ctx->records[b]);
+      ctx->records[b] = nullptr;
+    }
     ctx->records_cap = 0;
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->records, (size_t)n * 16));
+    for (int b = 0; b < 2; ++b) RBPR_CUDA(ctx, cudaMalloc(&ctx->records[b], (size_t)n * 16));
     ctx->records_cap = n;
   }
   const int64_t need = steps * stride;
   if (need > ctx->partials_cap) {
-    cudaFree(ctx->partials);
-    ctx->partials = nullptr;
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(ctx->partials[b]);
+      ctx->partials[b] = nullptr;
+    }
     ctx->partials_cap = 0;
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->partials, need * 4 * sizeof(float)));
+    for (int b = 0; b < 2; ++b)
+      RBPR_CUDA(ctx, cudaMalloc(&ctx->partials[b], need * 4 * sizeof(float)));
     ctx->partials_cap = need;
   }
-  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials, 0, need * 4 * sizeof(float), st));
   return 0;
 }
 
-// P1 over all sorted slots of the call.
-int run_sample(rbpr_ctx* ctx, const TrainParams& p, int64_t n, uint64_t step0, cudaStream_t st) {
+// P1 over all sorted slots of a wave.
+int run_sample(rbpr_ctx* ctx, const TrainParams& p, void* records, int64_t n, uint64_t step0,
+               cudaStream_t st) {
   const int64_t threads = n * kSampleLanes;
   bpr_sample<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-      p, reinterpret_cast<int4*>(ctx->records), (uint64_t)n, step0);
+      p, reinterpret_cast<int4*>(records), (uint64_t)n, step0);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -443,38 +458,93 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool need_pos = (neg_in != nullptr && hp->sampler == RBPR_SAMPLER_INJECTED) || neg_out;
-  rc = sort_batches(ctx, triple_idx, n, batch, need_pos, st);
-  if (rc) return rc;
   const int64_t steps = (n + batch - 1) / batch;
+  // A call is processed in WAVES of whole steps (<= kWaveTriples triples): wave w+1 is sorted and
+  // sampled on the context's auxiliary stream while wave w trains on the caller's stream (the
+  // static samplers depend on (seed, step, triple, CSR) only, never on the model).
+  int64_t spw = kWaveTriples / batch;
+  if (spw < 1) spw = 1;
+  if (spw > steps) spw = steps;
+  // the first wave is short (its preparation is the only one that is not overlapped)
+  int64_t first = kFirstWaveTriples / batch;
+  if (first < 1) first = 1;
+  if (first > spw) first = spw;
+  const int64_t nwaves = 1 + (steps - first + spw - 1) / spw;
+  auto wave_step0 = [&](int64_t w) { return w == 0 ? (int64_t)0 : first + (w - 1) * spw; };
+  auto wave_steps = [&](int64_t w) {
+    const int64_t a0 = wave_step0(w), a1 = (w == 0) ? first : a0 + spw;
+    return (a1 < steps ? a1 : steps) - a0;
+  };
+  const int64_t wave_cap = (spw * batch < n) ? spw * batch : n;
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  const int chunk = pick_chunk(ctx, batch < n ? batch : n, lanes);
-  const int stride = warps_for(batch < n ? batch : n, chunk, lanes);
-  rc = ensure_step_scratch(ctx, n, steps, stride, st);
+  int groups = 1;
+  rc = pick_groups(ctx, hp, batch < n ? batch : n, lanes, nv, &groups);
+  if (rc) return rc;
+  const int stride = warps_for(groups, lanes);
+  // scratch is sized for a full wave from the first call on, so later (longer) calls never allocate
+  const int64_t alloc_cap = wave_cap > kWaveTriples ? wave_cap : kWaveTriples;
+  const int64_t alloc_spw = (kWaveTriples / batch) > spw ? (kWaveTriples / batch) : spw;
+  rc = ensure_capacity(ctx, alloc_cap, steps);
+  if (rc) return rc;
+  rc = ensure_step_scratch(ctx, alloc_cap, alloc_spw, stride);
   if (rc) return rc;
   TrainParams p;
   fill_train_params(ctx, p, seed, hp);
-  p.keys = ctx->keys_out;
-  p.pos = need_pos ? ctx->pos_out : nullptr;
-  p.neg_in = neg_in;  // positions stored are global (0..n): neg_in/neg_out are indexed globally
-  p.neg_out = neg_out;
-  rc = run_sample(ctx, p, n, step0, st);
-  if (rc) return rc;
-  p.chunk = chunk;
-  for (int64_t s = 0; s < steps; ++s) {
-    const int64_t off = s * batch;
-    p.n = (int)((n - off) < batch ? (n - off) : batch);
-    p.step = step0 + (uint64_t)s;
-    rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records) + off,
-                     reinterpret_cast<float4*>(ctx->partials) + s * stride, st);
-    if (rc) return rc;
-    rc = run_apply(ctx, p.step, hp, 0, st);
-    if (rc) return rc;
+  p.groups = groups;
+  const bool piped = nwaves > 1;
+  cudaStream_t prep_st = piped ? ctx->aux : st;
+  if (piped) {
+    RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, st));
+    RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_inputs, 0));
   }
-  reduce_stats<<<(unsigned)steps, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials),
-                                                stride, ctx->stats);
-  ctx->launches++;
-  RBPR_CUDA(ctx, cudaGetLastError());
+  auto prepare = [&](int64_t w) -> int {
+    const int b = (int)(w & 1);
+    const int64_t off = wave_step0(w) * batch;
+    const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
+    if (piped && w >= 2) RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_free[b], 0));
+    int r = sort_batches(ctx, triple_idx + off, nw, batch, need_pos, prep_st);
+    if (r) return r;
+    TrainParams q = p;
+    q.keys = ctx->keys_out;
+    q.pos = need_pos ? ctx->pos_out : nullptr;  // positions are local to the wave
+    q.neg_in = neg_in ? neg_in + off : nullptr;
+    q.neg_out = neg_out ? neg_out + off : nullptr;
+    r = run_sample(ctx, q, ctx->records[b], nw, step0 + (uint64_t)wave_step0(w), prep_st);
+    if (r) return r;
+    if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_ready[b], ctx->aux));
+    return 0;
+  };
+  rc = prepare(0);
+  if (rc) return rc;
+  for (int64_t w = 0; w < nwaves; ++w) {
+    const int b = (int)(w & 1);
+    if (w + 1 < nwaves) {
+      rc = prepare(w + 1);
+      if (rc) return rc;
+    }
+    const int64_t off = wave_step0(w) * batch;
+    const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
+    const int64_t wsteps = wave_steps(w);
+    if (piped) RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[b], 0, (size_t)wsteps * stride * 16, st));
+    for (int64_t s = 0; s < wsteps; ++s) {
+      const int64_t soff = s * batch;
+      p.n = (int)((nw - soff) < batch ? (nw - soff) : batch);
+      p.step = step0 + (uint64_t)(wave_step0(w) + s);
+      rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records[b]) + soff,
+                       reinterpret_cast<float4*>(ctx->partials[b]) + s * stride, st);
+      if (rc) return rc;
+      rc = run_apply(ctx, p.step, hp, 0, st);
+      if (rc) return rc;
+    }
+    reduce_stats<<<(unsigned)wsteps, 256, 0, st>>>(
+        reinterpret_cast<const float4*>(ctx->partials[b]), stride,
+        ctx->stats + wave_step0(w) * RBPR_STATS_PER_STEP);
+    ctx->launches++;
+    RBPR_CUDA(ctx, cudaGetLastError());
+    if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
+  }
   if (stats_out)
     RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats,
                                    steps * RBPR_STATS_PER_STEP * sizeof(double),
@@ -546,25 +616,28 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     if (rc) return rc;
     int lanes, nv;
     rbpr_geometry(ctx->D, &lanes, &nv);
-    const int chunk = pick_chunk(ctx, n, lanes);
-    const int stride = warps_for(n, chunk, lanes);
-    rc = ensure_step_scratch(ctx, n, 1, stride, st);
+    int groups = 1;
+    rc = pick_groups(ctx, hp, n, lanes, nv, &groups);
     if (rc) return rc;
+    const int stride = warps_for(groups, lanes);
+    rc = ensure_step_scratch(ctx, n, 1, stride);
+    if (rc) return rc;
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
     TrainParams p;
     fill_train_params(ctx, p, seed, hp);
     p.keys = ctx->keys_out;
     p.pos = need_pos ? ctx->pos_out : nullptr;
     p.neg_in = neg_in;
     p.neg_out = neg_out;
-    rc = run_sample(ctx, p, n, step, st);
+    rc = run_sample(ctx, p, ctx->records[0], n, step, st);
     if (rc) return rc;
-    p.chunk = chunk;
+    p.groups = groups;
     p.n = (int)n;
     p.step = step;
-    rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records),
-                     reinterpret_cast<float4*>(ctx->partials), st);
+    rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records[0]),
+                     reinterpret_cast<float4*>(ctx->partials[0]), st);
     if (rc) return rc;
-    reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials), stride,
+    reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials[0]), stride,
                                     ctx->stats);
     ctx->launches++;
     RBPR_CUDA(ctx, cudaGetLastError());

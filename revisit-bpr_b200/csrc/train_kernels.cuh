@@ -31,9 +31,11 @@ struct TrainParams {
   const float* __restrict__ alias_prob;
   const int32_t* __restrict__ alias_idx;
   float4* __restrict__ partials;  // one float4 of step statistics per warp
+  float2* __restrict__ logit_out;     // (logits_pos, logits_neg) per original position, or null
+  const int32_t* __restrict__ step_pos;  // original position of each sorted slot of this step
   int32_t* __restrict__ flag;
   int n;      // triples in this step
-  int chunk;  // triples per group
+  int groups;  // lane groups in the launch; group g owns records [g*n/groups, (g+1)*n/groups)
   int D;
   uint32_t I;
   uint32_t draw_n;       // I-1 (uniform) or I (alias)
@@ -227,19 +229,102 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
   }
 }
 
-// P2 — row gather / loss / gradients.  A group owns the records [start, start+chunk) and
-// every user run that starts among them; records are read with one coalesced 16-byte load per
-// lane and broadcast with shuffles, so the only dependent global loads are the rows themselves.
+// ---- TMA / mbarrier primitives (sm_100a PTX; UBLKCP + SYNCS in SASS) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  // relaxed: the default .release would make the arrive wait for every outstanding red.global
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk asynchronous copy global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// 1-D bulk asynchronous reduction shared -> global (fp32 add), tracked by bulk async-groups.
+__device__ __forceinline__ void bulk_red_add_f32(float* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+               "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Shared-memory bytes of one phase-A CTA: per group kStages x {16-byte record, user row, i+ row,
+// i- row} plus one mbarrier per stage.
+#ifndef RBPR_STAGES
+#define RBPR_STAGES 3
+#endif
+constexpr int kStages = RBPR_STAGES;
+static inline size_t phase_a_smem_bytes(int D, int lanes) {
+  const size_t groups = kPhaseAThreads / lanes;
+  return groups * kStages * (16 + 3 * (size_t)D * 4) + groups * kStages * 8;
+}
+
+// P2 — row gather / loss / gradients.  A group of LANES lanes owns the records
+// [start, start+chunk) and every user run that starts among them.  The rows of the next kStages
+// triples of the group are always in flight: one lane issues 1-D bulk asynchronous copies (TMA)
+// of the user / positive / negative rows into the group's shared-memory ring, each stage
+// completing on its own mbarrier, so the bytes in flight per SM are bounded by shared memory
+// (~216 KB) instead of by the register file.  The user row of a run lives in registers from the
+// head triple until the run ends and is written back once (single owner, no atomics); the two
+// item-row gradients go to the dense accumulator with 128-bit vector reductions.
 template <int LANES, int NV, int OPT>
 __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams p,
                                                               const int4* __restrict__ records) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const Group<LANES> g;
   const int D = p.D;
-  constexpr int GROUPS_PER_BLOCK = kPhaseAThreads / LANES;
-  const uint32_t gid = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LANES;
+  constexpr int GPB = kPhaseAThreads / LANES;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  const uint32_t stage_bytes = 16u + 3u * row_bytes;
+  const int gin = threadIdx.x / LANES;
+  unsigned char* gsm = smem_raw + (size_t)gin * kStages * stage_bytes;
+  const uint32_t gsm_u32 = smem_u32(gsm);
+  const uint32_t bar0 =
+      smem_u32(smem_raw + (size_t)GPB * kStages * stage_bytes) + (uint32_t)gin * kStages * 8u;
+  if (g.gl == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1u);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t gid = blockIdx.x * GPB + gin;
   const uint32_t n = (uint32_t)p.n;
-  const uint32_t start = gid * (uint32_t)p.chunk;  // chunk <= LANES (window = LANES records)
-  const uint32_t end = min(start + (uint32_t)p.chunk, n);
+  const uint32_t ngroups = (uint32_t)p.groups;
+  const uint32_t start = gid < ngroups ? (uint32_t)(((uint64_t)gid * n) / ngroups) : n;
+  const uint32_t end = gid < ngroups ? (uint32_t)(((uint64_t)(gid + 1u) * n) / ngroups) : n;
 
   float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
 
@@ -247,16 +332,57 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
 #pragma unroll
   for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
 
-  // window of LANES records, one per lane
-  uint32_t wb = start;
-  int4 rec = (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
-  // first run head inside my chunk (runs that started earlier belong to the previous group)
-  uint32_t k = n;
-  {
+  auto load_window = [&](uint32_t wb) -> int4 {
+    return (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
+  };
+
+  // ---- fetch cursor: first run head inside my chunk (earlier runs belong to the previous group)
+  uint32_t kf = n, wbf = start;
+  bool fdone = true;
+  int4 rec_f = make_int4(-1, 0, 0, 0), rec_nx = rec_f;
+  while (wbf < end) {
+    rec_f = load_window(wbf);
     const unsigned heads =
-        (__ballot_sync(g.mask, rec.w != 0 && rec.x >= 0 && wb + g.gl < end) >> g.shift);
-    if (heads != 0u && start < n) k = start + (uint32_t)(__ffs(heads) - 1);
+        __ballot_sync(g.mask, rec_f.w != 0 && rec_f.x >= 0 && wbf + g.gl < end) >> g.shift;
+    if (heads != 0u) {
+      kf = wbf + (uint32_t)(__ffs(heads) - 1);
+      fdone = false;
+      break;
+    }
+    wbf += (uint32_t)LANES;
   }
+  if (!fdone) rec_nx = load_window(wbf + (uint32_t)LANES);
+  const uint32_t kfirst = kf;
+
+  uint32_t fseq = 0, cseq = 0;
+  auto fetch_one = [&]() {
+    if (kf >= wbf + (uint32_t)LANES) {
+      wbf += (uint32_t)LANES;
+      rec_f = rec_nx;
+      rec_nx = load_window(wbf + (uint32_t)LANES);
+    }
+    const int src = g.shift + (int)(kf - wbf);
+    const int32_t uu = __shfl_sync(g.mask, rec_f.x, src);
+    const int32_t i = __shfl_sync(g.mask, rec_f.y, src);
+    const int32_t j = __shfl_sync(g.mask, rec_f.z, src);
+    const int32_t head = __shfl_sync(g.mask, rec_f.w, src);
+    if (kf >= n || (head != 0 && kf >= end)) {  // end of data, or that run belongs to the next group
+      fdone = true;
+      return;
+    }
+    if (g.gl == 0) {
+      const uint32_t stage = fseq % kStages;
+      const uint32_t sbase = gsm_u32 + stage * stage_bytes;
+      const uint32_t bar = bar0 + 8u * stage;
+      *reinterpret_cast<int4*>(gsm + (size_t)stage * stage_bytes) = make_int4(uu, i, j, head);
+      mbar_arrive_expect_tx(bar, (head != 0 ? 3u : 2u) * row_bytes);
+      if (head != 0) bulk_g2s(sbase + 16u, p.user_emb + (size_t)uu * D, row_bytes, bar);
+      bulk_g2s(sbase + 16u + row_bytes, p.item_emb + (size_t)i * D, row_bytes, bar);
+      bulk_g2s(sbase + 16u + 2u * row_bytes, p.item_emb + (size_t)j * D, row_bytes, bar);
+    }
+    ++fseq;
+    ++kf;
+  };
 
   int32_t cur_u = -1;
   float4 u[NV], gu[NV];
@@ -264,7 +390,7 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
   int nocc = 0;
 
   auto flush_user = [&]() {
-    if (cur_u < 0) return;
+    if (cur_u <= 0) return;  // nothing staged, or the padding row (its gradient is blocked)
     float* urow = p.user_emb + (size_t)cur_u * D;
     const float rn = p.reg_user * (float)nocc;
     if (OPT == RBPR_OPT_SGD) {
@@ -305,25 +431,28 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
     }
   };
 
-  while (k < n) {
-    if (k >= wb + (uint32_t)LANES) {
-      wb += (uint32_t)LANES;
-      rec = (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
-    }
-    const int src = g.shift + (int)(k - wb);
-    const int32_t uu = __shfl_sync(g.mask, rec.x, src);
-    const int32_t i = __shfl_sync(g.mask, rec.y, src);
-    const int32_t j = __shfl_sync(g.mask, rec.z, src);
-    const int32_t head = __shfl_sync(g.mask, rec.w, src);
+  // prologue: fill the ring
+#pragma unroll
+  for (int s = 0; s < kStages; ++s)
+    if (!fdone) fetch_one();
+  __syncwarp(g.mask);  // stage records (plain shared stores by lane 0) are visible to the group
+
+  while (cseq < fseq) {
+    const uint32_t stage = cseq % kStages;
+    mbar_wait(bar0 + 8u * stage, (cseq / kStages) & 1u);
+    const unsigned char* sp = gsm + (size_t)stage * stage_bytes;
+    const int4 rec = *reinterpret_cast<const int4*>(sp);
+    const int32_t uu = rec.x, i = rec.y, j = rec.z, head = rec.w;
+    const float* su = reinterpret_cast<const float*>(sp + 16);
+    const float* si = su + D;
+    const float* sj = si + D;
     if (head) {
-      if (k >= end) break;  // that run belongs to the next group
       flush_user();
       cur_u = uu;
       nocc = 0;
-      const float* urow = p.user_emb + (size_t)uu * D;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        u[v] = colok[v] ? ld4(urow + 4 * (g.gl + LANES * v)) : f4zero();
+        u[v] = colok[v] ? ld4(su + 4 * (g.gl + LANES * v)) : f4zero();
         gu[v] = f4zero();
       }
       if (OPT == RBPR_OPT_ADAM) {
@@ -343,38 +472,50 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
           }
         }
       }
-    }
-    const float* irow = p.item_emb + (size_t)i * D;
-    const float* jrow = p.item_emb + (size_t)j * D;
-    float4 vi[NV], vj[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      vi[v] = colok[v] ? ld4(irow + 4 * (g.gl + LANES * v)) : f4zero();
-      vj[v] = colok[v] ? ld4(jrow + 4 * (g.gl + LANES * v)) : f4zero();
-    }
-    if (head) {
       usq = 0.f;
 #pragma unroll
       for (int v = 0; v < NV; ++v) usq += dot4(u[v], u[v]);
       usq *= p.reg_user;
     }
-    float part = 0.f, sq = 0.f;
+    float4 vi[NV], vj[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      part += dot4(u[v], vi[v]) - dot4(u[v], vj[v]);
+      vi[v] = colok[v] ? ld4(si + 4 * (g.gl + LANES * v)) : f4zero();
+      vj[v] = colok[v] ? ld4(sj + 4 * (g.gl + LANES * v)) : f4zero();
+    }
+    float pp = 0.f, pn = 0.f, sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      pp += dot4(u[v], vi[v]);
+      pn += dot4(u[v], vj[v]);
       sq += p.reg_item * dot4(vi[v], vi[v]) + p.reg_neg * dot4(vj[v], vj[v]);
     }
-    float x = g.sum(part);
-    if (p.item_bias != nullptr) x += __ldg(p.item_bias + i) - __ldg(p.item_bias + j);
+    float x;
+    if (p.logit_out != nullptr) {  // drop-in Model.forward output: logits_pos / logits_neg
+      float xp = g.sum(pp), xn = g.sum(pn);
+      if (p.item_bias != nullptr) {
+        xp += __ldg(p.item_bias + i);
+        xn += __ldg(p.item_bias + j);
+      }
+      x = xp - xn;
+      if (g.gl == 0) {
+        const uint32_t kc = kfirst + cseq;
+        p.logit_out[p.step_pos != nullptr ? __ldg(p.step_pos + kc) : (int32_t)kc] =
+            make_float2(xp, xn);
+      }
+    } else {
+      x = g.sum(pp - pn);
+      if (p.item_bias != nullptr) x += __ldg(p.item_bias + i) - __ldg(p.item_bias + j);
+    }
     // softplus(-x) and c = sigmoid(-x), overflow-safe; fast intrinsics: abs err ~1e-7 on a
     // per-triple loss of O(1), inside the 1e-4 parity budget
     const float e = __expf(-fabsf(x));
-    const float sp = fmaxf(-x, 0.f) + __logf(1.0f + e);
+    const float sp_ = fmaxf(-x, 0.f) + __logf(1.0f + e);
     const float inv = __fdividef(1.0f, 1.0f + e);
     const float c = (x >= 0.f) ? e * inv : inv;
     l2_acc += 0.5f * (sq + usq);
     if (g.gl == 0) {
-      loss_acc += sp;
+      loss_acc += sp_;
       absx_acc += fabsf(x);
       cnt_acc += 1.f;
       p.touched[i] = 1u;
@@ -384,8 +525,11 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
         atomicAdd(p.bias_grad + j, c);
       }
     }
-    float* gi = p.item_grad + (size_t)i * D;
-    float* gj = p.item_grad + (size_t)j * D;
+    // The two item-row gradients overwrite the rows they were computed from (each lane rewrites
+    // exactly the words it read) and leave for the dense accumulator as ONE bulk asynchronous
+    // reduction per row (TMA, fp32 add at L2) instead of LANES*NV vector atomics per row.
+    float* smi = const_cast<float*>(si);
+    float* smj = const_cast<float*>(sj);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       if (!colok[v]) continue;
@@ -400,17 +544,29 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
       b.y = p.reg_neg * vj[v].y + cu.y;
       b.z = p.reg_neg * vj[v].z + cu.z;
       b.w = p.reg_neg * vj[v].w + cu.w;
-      red4(gi + cidx, a);
-      red4(gj + cidx, b);
+      st4(smi + cidx, a);
+      st4(smj + cidx, b);
       gu[v].x -= c * (vi[v].x - vj[v].x);
       gu[v].y -= c * (vi[v].y - vj[v].y);
       gu[v].z -= c * (vi[v].z - vj[v].z);
       gu[v].w -= c * (vi[v].w - vj[v].w);
     }
+    fence_proxy_async_smem();  // generic-proxy stores above -> visible to the async proxy
+    __syncwarp(g.mask);
+    if (g.gl == 0) {
+      // row 0 of the item table is the padding row: nn.Embedding(padding_idx=0) blocks its gradient
+      if (i != 0) bulk_red_add_f32(p.item_grad + (size_t)i * D, smem_u32(smi), row_bytes);
+      if (j != 0) bulk_red_add_f32(p.item_grad + (size_t)j * D, smem_u32(smj), row_bytes);
+      bulk_commit();
+      bulk_wait_read<1>();  // the previous triple's reduction has read its stage: it can be refilled
+    }
+    __syncwarp(g.mask);
+    ++cseq;
+    if (cseq >= 2u && !fdone) fetch_one();  // refills stage (cseq-2) % kStages == fseq % kStages
     ++nocc;
-    ++k;
   }
   flush_user();
+  if (g.gl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem outlives its readers
 
   // per-warp statistics partial (no block barrier: warps retire independently)
   float a = loss_acc, b = l2_acc, cabs = absx_acc, d = cnt_acc;
@@ -520,6 +676,8 @@ int rbpr_launch_phase_a_sgd(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int l
                             const int4* records, int* warps_out, cudaStream_t st);
 int rbpr_launch_phase_a_adam(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,
                              const int4* records, int* warps_out, cudaStream_t st);
+int rbpr_phase_a_prepare_sgd(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm);
+int rbpr_phase_a_prepare_adam(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm);
 int rbpr_launch_apply_sgd(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,
                           cudaStream_t st);
 int rbpr_launch_apply_adam(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,
@@ -527,7 +685,6 @@ int rbpr_launch_apply_adam(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int la
 int rbpr_launch_flush_users(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv,
                             cudaStream_t st);
 
-// Instantiate every supported (LANES, NV) pair: NV<=4 for any lane count, NV 5..8 for 32 lanes.
-#define RBPR_FOR_EACH_GEOMETRY(X)                                                            \
-  X(1, 1) X(1, 2) X(1, 3) X(1, 4) X(2, 3) X(2, 4) X(4, 3) X(4, 4) X(8, 3) X(8, 4)    \
-  X(16, 3) X(16, 4) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8)
+// Instantiate every (LANES, NV) pair rbpr_geometry can return for D in [4,1024], D % 4 == 0.
+#define RBPR_FOR_EACH_GEOMETRY(X) \
+  X(1, 1) X(1, 2) X(2, 2) X(4, 2) X(8, 2) X(16, 2) X(32, 2) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8)

@@ -6,13 +6,30 @@ using namespace rbpr_dev;
 int rbpr_launch_phase_a_sgd(rbpr_ctx* ctx, const TrainParams& p, int lanes, int nv,
                               const int4* records, int* warps_out, cudaStream_t st) {
   const int groups_per_block = kPhaseAThreads / lanes;
-  const int64_t groups = ((int64_t)p.n + p.chunk - 1) / p.chunk;
-  const int blocks = (int)((groups + groups_per_block - 1) / groups_per_block);
+  const int blocks = (p.groups + groups_per_block - 1) / groups_per_block;
+  const size_t smem = phase_a_smem_bytes(p.D, lanes);
   *warps_out = blocks * (kPhaseAThreads / 32);
-#define X(L, V)                                                       \
-  if (lanes == L && nv == V) {                                        \
-    bpr_phase_a<L, V, RBPR_OPT_SGD><<<blocks, kPhaseAThreads, 0, st>>>(p, records);  \
-    return 0;                                                         \
+#define X(L, V)                                                                                \
+  if (lanes == L && nv == V) {                                                                 \
+    bpr_phase_a<L, V, RBPR_OPT_SGD><<<blocks, kPhaseAThreads, smem, st>>>(p, records);          \
+    return 0;                                                                                  \
+  }
+  RBPR_FOR_EACH_GEOMETRY(X)
+#undef X
+  RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
+}
+
+// Opt the instantiation for `dim` into its dynamic shared-memory size and report how many CTAs
+// of it fit on one SM (used to size the grid as one resident wave).
+int rbpr_phase_a_prepare_sgd(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm) {
+  const size_t smem = phase_a_smem_bytes(dim, lanes);
+#define X(L, V)                                                                                \
+  if (lanes == L && nv == V) {                                                                 \
+    RBPR_CUDA(ctx, cudaFuncSetAttribute(bpr_phase_a<L, V, RBPR_OPT_SGD>,                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RBPR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(                              \
+                       blocks_per_sm, bpr_phase_a<L, V, RBPR_OPT_SGD>, kPhaseAThreads, smem));  \
+    return 0;                                                                                  \
   }
   RBPR_FOR_EACH_GEOMETRY(X)
 #undef X
