@@ -42,6 +42,7 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->coo_user);
   cudaFree(ctx->item_grad);
+  cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
   cudaFree(ctx->keys_in);
   cudaFree(ctx->keys_out);
@@ -81,12 +82,17 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: tables must be 16-byte aligned");
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaFree(ctx->item_grad);
+  cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
   ctx->item_grad = nullptr;
+  ctx->user_grad = nullptr;
   ctx->touched = nullptr;
   const size_t gbytes = ((size_t)num_items * dim + (size_t)num_items) * sizeof(float);
   RBPR_CUDA(ctx, cudaMalloc(&ctx->item_grad, gbytes));
   RBPR_CUDA(ctx, cudaMemset(ctx->item_grad, 0, gbytes));
+  const size_t ubytes = (size_t)num_users * dim * sizeof(float);
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->user_grad, ubytes));
+  RBPR_CUDA(ctx, cudaMemset(ctx->user_grad, 0, ubytes));
   RBPR_CUDA(ctx, cudaMalloc(&ctx->touched, num_items * sizeof(uint32_t)));
   RBPR_CUDA(ctx, cudaMemset(ctx->touched, 0, num_items * sizeof(uint32_t)));
   ctx->user_emb = user_emb;

@@ -34,6 +34,7 @@ struct rbpr_ctx {
   // owned scratch
   int32_t* coo_user = nullptr;  // (nnz) triple -> user
   float* item_grad = nullptr;   // (I*D + I) dense item (+bias) gradient accumulator
+  float* user_grad = nullptr;   // (U*D) dense user gradient accumulator (multi-occurrence users)
   uint32_t* touched = nullptr;  // (I) item touched in this step
   uint64_t* keys_in = nullptr;  // (cap) (step<<32 | triple)
   uint64_t* keys_out = nullptr;

@@ -1,18 +1,19 @@
-// Fused BPR training step for sm_100a: on-device negative sampling, (u, i+, i-) row gather,
-// dot, log-sigmoid loss + L2, exact synchronous-minibatch gradients, in-place update.
+// BPR training step for sm_100a: on-device negative sampling, (u, i+, i-) row gather, dot,
+// log-sigmoid loss + L2, exact synchronous-minibatch gradients, in-place update.
 //
-// One step = two phases on one stream (kernels in train_kernels.cuh):
-//   phase A  bpr_phase_a   — the batch is sorted by triple id (== grouped by user, because
-//            triples are the COO flattening of the CSR).  A lane group owns every user run
-//            that STARTS inside its chunk: the user row is staged once in registers, each
-//            triple of the run samples its negative, gathers the two item rows with 128-bit
-//            loads, reduces the dot with shuffles, and pushes the two item-row gradients
-//            into the dense item-gradient accumulator with vector red.global.add.v4.f32.
-//            The user row is updated in place when the run ends (no atomics: one owner).
-//            Item rows are only READ in this phase, so every triple sees pre-step values.
-//   phase B  bpr_apply_items — applies the accumulated item gradient (SGD: touched rows
-//            only; Adam: every row, which is torch.optim.Adam's dense semantics) and
-//            clears the accumulator.
+// A call is cut into WAVES of whole steps.  Per wave, on the context's auxiliary stream:
+//   P1  make_keys + cub radix sort + bpr_sample — the wave's triples are sorted by (step, triple
+//       id) == grouped by user inside every step (triples are the COO flattening of the CSR);
+//       a group of 8 lanes per slot draws the negative (Philox4x32-10, CSR rejection) and emits
+//       a 16-byte record {u, i+, i-, run flags}.  The static samplers depend on (seed, step,
+//       triple, CSR) only, so wave w+1 is prepared while wave w trains.
+// Per step, on the caller's stream (kernels in train_kernels.cuh):
+//   P2  bpr_phase_a — one lane group per triple, 128-bit row loads, shuffle-reduced dot, the two
+//       item-row gradients into the dense accumulator (vector red), single-occurrence users
+//       updated in place, multi-occurrence users into the dense user-gradient accumulator.
+//       Tables are only READ for rows that other triples of the step may read: exact minibatch.
+//   P3  bpr_apply — accumulated item gradient (SGD: touched rows; Adam: every row, which is
+//       torch.optim.Adam's dense semantics) and multi-occurrence users; clears the accumulators.
 // Reference call sites replaced: see include/rbpr.h (rbpr_train_steps).
 #include <cub/device/device_radix_sort.cuh>
 
@@ -148,6 +149,20 @@ int ensure_capacity(rbpr_ctx* ctx, int64_t n, int64_t steps) {
     RBPR_CUDA(ctx, cudaMalloc(&ctx->pos_in, n * sizeof(int32_t)));
     RBPR_CUDA(ctx, cudaMalloc(&ctx->pos_out, n * sizeof(int32_t)));
     ctx->cap = n;
+    // size the radix-sort temporary for the full capacity now (keys-only and pairs, widest bit
+    // range) so that no later call allocates or frees inside a training loop
+    size_t need_k = 0, need_p = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need_k, ctx->keys_in, ctx->keys_out, n, 0, 64);
+    cub::DeviceRadixSort::SortPairs(nullptr, need_p, ctx->keys_in, ctx->keys_out, ctx->pos_in,
+                                    ctx->pos_out, n, 0, 64);
+    const size_t need = need_k > need_p ? need_k : need_p;
+    if (need > ctx->cub_tmp_bytes) {
+      cudaFree(ctx->cub_tmp);
+      ctx->cub_tmp = nullptr;
+      ctx->cub_tmp_bytes = 0;
+      RBPR_CUDA(ctx, cudaMalloc(&ctx->cub_tmp, need));
+      ctx->cub_tmp_bytes = need;
+    }
   }
   if (steps > ctx->stats_cap) {
     cudaFree(ctx->stats);
@@ -169,6 +184,7 @@ void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_
   p.user_v = ctx->user_v;
   p.user_last = ctx->user_last;
   p.item_grad = ctx->item_grad;
+  p.user_grad = ctx->user_grad;
   p.bias_grad = ctx->item_bias ? ctx->item_grad + ctx->I * ctx->D : nullptr;
   p.touched = ctx->touched;
   p.indptr = ctx->indptr;
@@ -245,10 +261,9 @@ int sort_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t ba
   return 0;
 }
 
-// Lane groups per launch: the grid is ONE resident wave (every CTA co-resident, the same number
-// of CTAs on every SM, no tail wave); group g walks records [g*n/G, (g+1)*n/G) with kStages
-// triples of rows in flight.  Returns G (a multiple of the groups per CTA).
-int pick_groups(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t n, int lanes, int nv, int* groups) {
+// CTAs of phase A: one lane group per triple, capped at ONE resident wave (the same number of
+// CTAs on every SM; groups then stride over the step's records).
+int pick_blocks(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t n, int lanes, int nv, int* blocks_out) {
   const int o = hp->optimizer == RBPR_OPT_ADAM ? 1 : 0;
   if (ctx->phase_a_blocks_per_sm[o] == 0) {
     int bps = 0;
@@ -256,20 +271,18 @@ int pick_groups(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t n, int lanes, int
                : rbpr_phase_a_prepare_sgd(ctx, ctx->D, lanes, nv, &bps);
     if (rc) return rc;
     if (bps < 1) RBPR_FAIL(ctx, RBPR_ERR_CUDA, "phase-A kernel does not fit on an SM (dim=%d)", ctx->D);
+    const char* e = getenv("RBPR_BLOCKS_PER_SM");  // tuning override
+    if (e && atoi(e) > 0 && atoi(e) < bps) bps = atoi(e);
     ctx->phase_a_blocks_per_sm[o] = bps;
   }
   const int gpb = kPhaseAThreads / lanes;
   const int64_t resident_blocks = (int64_t)ctx->sm_count * ctx->phase_a_blocks_per_sm[o];
-  int64_t blocks = (n + gpb - 1) / gpb;  // one triple per group
+  int64_t blocks = (n + gpb - 1) / gpb;
   if (blocks > resident_blocks) blocks = resident_blocks;
-  const char* e = getenv("RBPR_CHUNK");  // tuning override: triples per group
-  if (e && atoi(e) > 0) blocks = ((n + atoi(e) - 1) / atoi(e) + gpb - 1) / gpb;
   if (blocks < 1) blocks = 1;
-  *groups = (int)(blocks * gpb);
+  *blocks_out = (int)blocks;
   return 0;
 }
-
-int warps_for(int groups, int lanes) { return groups / (kPhaseAThreads / lanes) * (kPhaseAThreads / 32); }
 
 // Scratch for one wave (both buffers): 16-byte record per triple, `steps` x `stride` float4
 // statistics partials.
@@ -310,7 +323,7 @@ int run_sample(rbpr_ctx* ctx, const TrainParams& p, void* records, int64_t n, ui
 
 // P2 for one step: p.n / p.step / p.chunk set by the caller; records and partials of that step.
 int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int4* records,
-                float4* partials, cudaStream_t st) {
+                float4* partials, int blocks, cudaStream_t st) {
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
   p.partials = partials;
@@ -322,10 +335,12 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
     e1 = next_event(ctx);
     cudaEventRecord(e0, st);
   }
-  int nwarps = 0;
+  // the last (short) step of a call may need fewer CTAs; never more than `blocks` (partials stride)
+  const int64_t need = ((int64_t)p.n + (kPhaseAThreads / lanes) - 1) / (kPhaseAThreads / lanes);
+  const int nb = (int)(need < blocks ? (need > 0 ? need : 1) : blocks);
   int rc = (hp->optimizer == RBPR_OPT_SGD)
-               ? rbpr_launch_phase_a_sgd(ctx, p, lanes, nv, records, &nwarps, st)
-               : rbpr_launch_phase_a_adam(ctx, p, lanes, nv, records, &nwarps, st);
+               ? rbpr_launch_phase_a_sgd(ctx, p, lanes, nv, records, nb, st)
+               : rbpr_launch_phase_a_adam(ctx, p, lanes, nv, records, nb, st);
   if (rc) return rc;
   if (timed) cudaEventRecord(e1, st);
   ctx->launches++;
@@ -333,9 +348,21 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
   return 0;
 }
 
-int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, cudaStream_t st) {
+// do_items / do_users select the halves of bpr_apply; records/n are the step's records (users).
+int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
+              const int4* records, int n, cudaStream_t st) {
   ApplyParams a;
   memset(&a, 0, sizeof(a));
+  a.do_items = do_items;
+  a.do_users = (records != nullptr && n > 0) ? 1 : 0;
+  if (!a.do_items && !a.do_users) return 0;
+  a.records = records;
+  a.n = n;
+  a.user_emb = ctx->user_emb;
+  a.user_grad = ctx->user_grad;
+  a.user_m = ctx->user_m;
+  a.user_v = ctx->user_v;
+  a.user_last = ctx->user_last;
   a.item_emb = ctx->item_emb;
   a.item_bias = ctx->item_bias;
   a.item_m = ctx->item_m;
@@ -478,10 +505,10 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
   const int64_t wave_cap = (spw * batch < n) ? spw * batch : n;
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  int groups = 1;
-  rc = pick_groups(ctx, hp, batch < n ? batch : n, lanes, nv, &groups);
+  int blocks = 1;
+  rc = pick_blocks(ctx, hp, batch < n ? batch : n, lanes, nv, &blocks);
   if (rc) return rc;
-  const int stride = warps_for(groups, lanes);
+  const int stride = blocks * (kPhaseAThreads / 32);
   // scratch is sized for a full wave from the first call on, so later (longer) calls never allocate
   const int64_t alloc_cap = wave_cap > kWaveTriples ? wave_cap : kWaveTriples;
   const int64_t alloc_spw = (kWaveTriples / batch) > spw ? (kWaveTriples / batch) : spw;
@@ -491,7 +518,6 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
   if (rc) return rc;
   TrainParams p;
   fill_train_params(ctx, p, seed, hp);
-  p.groups = groups;
   const bool piped = nwaves > 1;
   cudaStream_t prep_st = piped ? ctx->aux : st;
   if (piped) {
@@ -532,10 +558,11 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
       const int64_t soff = s * batch;
       p.n = (int)((nw - soff) < batch ? (nw - soff) : batch);
       p.step = step0 + (uint64_t)(wave_step0(w) + s);
-      rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records[b]) + soff,
-                       reinterpret_cast<float4*>(ctx->partials[b]) + s * stride, st);
+      const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
+      rc = run_phase_a(ctx, p, hp, recs, reinterpret_cast<float4*>(ctx->partials[b]) + s * stride,
+                       blocks, st);
       if (rc) return rc;
-      rc = run_apply(ctx, p.step, hp, 0, st);
+      rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st);
       if (rc) return rc;
     }
     reduce_stats<<<(unsigned)wsteps, 256, 0, st>>>(
@@ -616,10 +643,10 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     if (rc) return rc;
     int lanes, nv;
     rbpr_geometry(ctx->D, &lanes, &nv);
-    int groups = 1;
-    rc = pick_groups(ctx, hp, n, lanes, nv, &groups);
+    int blocks = 1;
+    rc = pick_blocks(ctx, hp, n, lanes, nv, &blocks);
     if (rc) return rc;
-    const int stride = warps_for(groups, lanes);
+    const int stride = blocks * (kPhaseAThreads / 32);
     rc = ensure_step_scratch(ctx, n, 1, stride);
     if (rc) return rc;
     RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
@@ -631,11 +658,14 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     p.neg_out = neg_out;
     rc = run_sample(ctx, p, ctx->records[0], n, step, st);
     if (rc) return rc;
-    p.groups = groups;
-    p.n = (int)n;
+      p.n = (int)n;
     p.step = step;
     rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records[0]),
-                     reinterpret_cast<float4*>(ctx->partials[0]), st);
+                     reinterpret_cast<float4*>(ctx->partials[0]), blocks, st);
+    if (rc) return rc;
+    // users are owned by this rank: finish the multi-occurrence ones now (items wait for the
+    // all-reduce, rbpr_apply_item_grads)
+    rc = run_apply(ctx, step, hp, 0, 0, reinterpret_cast<const int4*>(ctx->records[0]), (int)n, st);
     if (rc) return rc;
     reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials[0]), stride,
                                     ctx->stats);
@@ -660,7 +690,7 @@ int rbpr_apply_item_grads(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, 
   int rc = check_ready(ctx, hp);
   if (rc) return rc;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
-  return run_apply(ctx, step, hp, 1, (cudaStream_t)stream);
+  return run_apply(ctx, step, hp, 1, 1, nullptr, 0, (cudaStream_t)stream);
 }
 
 int rbpr_sync_check(rbpr_ctx* ctx, void* stream) {

@@ -19,6 +19,8 @@ struct TrainParams {
   float* __restrict__ user_v;
   int32_t* __restrict__ user_last;
   float* __restrict__ item_grad;  // (I,D) dense accumulator
+  float* __restrict__ user_grad;  // (U,D) dense accumulator, used only by users that occur more
+                                  // than once in a step
   float* __restrict__ bias_grad;  // (I) or null
   uint32_t* __restrict__ touched;
   const int64_t* __restrict__ indptr;
@@ -35,7 +37,6 @@ struct TrainParams {
   const int32_t* __restrict__ step_pos;  // original position of each sorted slot of this step
   int32_t* __restrict__ flag;
   int n;      // triples in this step
-  int groups;  // lane groups in the launch; group g owns records [g*n/groups, (g+1)*n/groups)
   int D;
   uint32_t I;
   uint32_t draw_n;       // I-1 (uniform) or I (alias)
@@ -62,7 +63,21 @@ struct ApplyParams {
   int dense;  // 1: ignore touched flags (multi-GPU / Adam)
   uint64_t step;
   float lr, beta1, beta2, eps;
+  // user part: users occurring more than once in the step (records flagged kRecMultiHead)
+  int do_items, do_users;
+  const int4* __restrict__ records;
+  int n;
+  float* __restrict__ user_emb;
+  float* __restrict__ user_grad;
+  float* __restrict__ user_m;
+  float* __restrict__ user_v;
+  int32_t* __restrict__ user_last;
 };
+
+// record.w flags
+constexpr int kRecHead = 1;       // first triple of a user run inside its step
+constexpr int kRecSingle = 2;     // the user occurs exactly once in the step
+constexpr int kRecMultiHead = 4;  // head of a run of length >= 2
 
 template <int LANES>
 struct Group {
@@ -192,7 +207,7 @@ constexpr int kPhaseAThreads = 128;
 
 // P1 — negative sampling for EVERY step of a call in one launch.  A group of 8 lanes per sorted
 // slot resolves (user, item), draws the negative with a cooperative 9-ary CSR probe, and emits a
-// 16-byte record {u, i+, i-, head} (head = first triple of a user run inside its step).  The
+// 16-byte record {u, i+, i-, flags} (kRecHead / kRecSingle / kRecMultiHead of the user run).  The
 // static samplers depend only on (seed, step, triple, CSR), never on the model, so the whole
 // call's dependent-load chains (keys -> coo/indices -> indptr -> probes) run at full occupancy
 // here instead of sitting on the critical path of the row-gather kernel.
@@ -206,11 +221,16 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
   const uint32_t t = (uint32_t)key;
   const int32_t uu = __ldg(p.coo_user + t);
   const int32_t i = __ldg(p.indices + t);
-  int32_t head = 1;
+  bool head = true, last = true;
   if (k > 0u) {
     const uint64_t kprev = __ldg(p.keys + k - 1);
-    head = ((kprev >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)kprev) != uu) ? 1 : 0;
+    head = (kprev >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)kprev) != uu;
   }
+  if (k + 1u < n_slots) {
+    const uint64_t knext = __ldg(p.keys + k + 1);
+    last = (knext >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)knext) != uu;
+  }
+  const int32_t flags = head ? (last ? (kRecHead | kRecSingle) : (kRecHead | kRecMultiHead)) : 0;
   int32_t j;
   if (p.sampler == RBPR_SAMPLER_INJECTED) {
     j = (int32_t)__ldg(p.neg_in + __ldg(p.pos + k));
@@ -224,271 +244,86 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
     }
   }
   if (g.gl == 0) {
-    if (records != nullptr) records[k] = make_int4(uu, i, j, head);
+    if (records != nullptr) records[k] = make_int4(uu, i, j, flags);
     if (p.neg_out != nullptr) p.neg_out[__ldg(p.pos + k)] = (int64_t)j;
   }
 }
 
-// ---- TMA / mbarrier primitives (sm_100a PTX; UBLKCP + SYNCS in SASS) -------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  // relaxed: the default .release would make the arrive wait for every outstanding red.global
-  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 1-D bulk asynchronous copy global -> shared, completion counted in bytes on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-
-// 1-D bulk asynchronous reduction shared -> global (fp32 add), tracked by bulk async-groups.
-__device__ __forceinline__ void bulk_red_add_f32(float* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-               "r"(src), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// Shared-memory bytes of one phase-A CTA: per group kStages x {16-byte record, user row, i+ row,
-// i- row} plus one mbarrier per stage.
-#ifndef RBPR_STAGES
-#define RBPR_STAGES 3
-#endif
-constexpr int kStages = RBPR_STAGES;
-static inline size_t phase_a_smem_bytes(int D, int lanes) {
-  const size_t groups = kPhaseAThreads / lanes;
-  return groups * kStages * (16 + 3 * (size_t)D * 4) + groups * kStages * 8;
-}
-
-// P2 — row gather / loss / gradients.  A group of LANES lanes owns the records
-// [start, start+chunk) and every user run that starts among them.  The rows of the next kStages
-// triples of the group are always in flight: one lane issues 1-D bulk asynchronous copies (TMA)
-// of the user / positive / negative rows into the group's shared-memory ring, each stage
-// completing on its own mbarrier, so the bytes in flight per SM are bounded by shared memory
-// (~216 KB) instead of by the register file.  The user row of a run lives in registers from the
-// head triple until the run ends and is written back once (single owner, no atomics); the two
-// item-row gradients go to the dense accumulator with 128-bit vector reductions.
+// P2 — row gather / loss / gradients, one lane group per triple, every triple independent.
+// Measured on B200 (profiles/r01i_gather_floor.txt): for 512-byte rows the
+// memory system serves this pattern fastest from plain 128-bit row loads at high occupancy
+// (one LDG.128 per lane fetches a whole D=128 row per warp instruction); the TMA/mbarrier-staged
+// variants of this kernel (git history, profiles/r01[cfgh]_*) were 2x slower because of their
+// per-triple bookkeeping.  So the kernel is deliberately minimal:
+//   * the three rows are read with 128-bit loads, the dot is reduced with shuffles;
+//   * the two item-row gradients go to the dense accumulator with red.global.add.v4.f32
+//     (item rows are only READ here, so every triple sees pre-step values: exact minibatch);
+//   * a user that occurs once in the step (kRecSingle, the common case) is updated in place
+//     by its only triple; a user with several triples accumulates into the dense user-gradient
+//     buffer and is updated by bpr_apply (its row is not written here, so its other triples
+//     still read the pre-step value).
 template <int LANES, int NV, int OPT>
 __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams p,
                                                               const int4* __restrict__ records) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   const Group<LANES> g;
   const int D = p.D;
-  constexpr int GPB = kPhaseAThreads / LANES;
-  const uint32_t row_bytes = (uint32_t)D * 4u;
-  const uint32_t stage_bytes = 16u + 3u * row_bytes;
-  const int gin = threadIdx.x / LANES;
-  unsigned char* gsm = smem_raw + (size_t)gin * kStages * stage_bytes;
-  const uint32_t gsm_u32 = smem_u32(gsm);
-  const uint32_t bar0 =
-      smem_u32(smem_raw + (size_t)GPB * kStages * stage_bytes) + (uint32_t)gin * kStages * 8u;
-  if (g.gl == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8u * s, 1u);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-
-  const uint32_t gid = blockIdx.x * GPB + gin;
   const uint32_t n = (uint32_t)p.n;
-  const uint32_t ngroups = (uint32_t)p.groups;
-  const uint32_t start = gid < ngroups ? (uint32_t)(((uint64_t)gid * n) / ngroups) : n;
-  const uint32_t end = gid < ngroups ? (uint32_t)(((uint64_t)(gid + 1u) * n) / ngroups) : n;
-
+  const uint32_t ngroups = (gridDim.x * kPhaseAThreads) / LANES;
   float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
 
   bool colok[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
 
-  auto load_window = [&](uint32_t wb) -> int4 {
-    return (wb + g.gl < n) ? __ldg(records + wb + g.gl) : make_int4(-1, 0, 0, 0);
-  };
-
-  // ---- fetch cursor: first run head inside my chunk (earlier runs belong to the previous group)
-  uint32_t kf = n, wbf = start;
-  bool fdone = true;
-  int4 rec_f = make_int4(-1, 0, 0, 0), rec_nx = rec_f;
-  while (wbf < end) {
-    rec_f = load_window(wbf);
-    const unsigned heads =
-        __ballot_sync(g.mask, rec_f.w != 0 && rec_f.x >= 0 && wbf + g.gl < end) >> g.shift;
-    if (heads != 0u) {
-      kf = wbf + (uint32_t)(__ffs(heads) - 1);
-      fdone = false;
-      break;
-    }
-    wbf += (uint32_t)LANES;
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  if (OPT == RBPR_OPT_ADAM) {
+    const double s = (double)(p.step + 1);  // 1-based optimizer step being applied
+    step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, s)));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, s));
   }
-  if (!fdone) rec_nx = load_window(wbf + (uint32_t)LANES);
-  const uint32_t kfirst = kf;
 
-  uint32_t fseq = 0, cseq = 0;
-  auto fetch_one = [&]() {
-    if (kf >= wbf + (uint32_t)LANES) {
-      wbf += (uint32_t)LANES;
-      rec_f = rec_nx;
-      rec_nx = load_window(wbf + (uint32_t)LANES);
-    }
-    const int src = g.shift + (int)(kf - wbf);
-    const int32_t uu = __shfl_sync(g.mask, rec_f.x, src);
-    const int32_t i = __shfl_sync(g.mask, rec_f.y, src);
-    const int32_t j = __shfl_sync(g.mask, rec_f.z, src);
-    const int32_t head = __shfl_sync(g.mask, rec_f.w, src);
-    if (kf >= n || (head != 0 && kf >= end)) {  // end of data, or that run belongs to the next group
-      fdone = true;
-      return;
-    }
-    if (g.gl == 0) {
-      const uint32_t stage = fseq % kStages;
-      const uint32_t sbase = gsm_u32 + stage * stage_bytes;
-      const uint32_t bar = bar0 + 8u * stage;
-      *reinterpret_cast<int4*>(gsm + (size_t)stage * stage_bytes) = make_int4(uu, i, j, head);
-      mbar_arrive_expect_tx(bar, (head != 0 ? 3u : 2u) * row_bytes);
-      if (head != 0) bulk_g2s(sbase + 16u, p.user_emb + (size_t)uu * D, row_bytes, bar);
-      bulk_g2s(sbase + 16u + row_bytes, p.item_emb + (size_t)i * D, row_bytes, bar);
-      bulk_g2s(sbase + 16u + 2u * row_bytes, p.item_emb + (size_t)j * D, row_bytes, bar);
-    }
-    ++fseq;
-    ++kf;
-  };
-
-  int32_t cur_u = -1;
-  float4 u[NV], gu[NV];
-  float usq = 0.f;
-  int nocc = 0;
-
-  auto flush_user = [&]() {
-    if (cur_u <= 0) return;  // nothing staged, or the padding row (its gradient is blocked)
-    float* urow = p.user_emb + (size_t)cur_u * D;
-    const float rn = p.reg_user * (float)nocc;
-    if (OPT == RBPR_OPT_SGD) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        if (!colok[v]) continue;
-        float4 o;
-        o.x = u[v].x - p.lr * (gu[v].x + rn * u[v].x);
-        o.y = u[v].y - p.lr * (gu[v].y + rn * u[v].y);
-        o.z = u[v].z - p.lr * (gu[v].z + rn * u[v].z);
-        o.w = u[v].w - p.lr * (gu[v].w + rn * u[v].w);
-        st4(urow + 4 * (g.gl + LANES * v), o);
-      }
-    } else {
-      const int64_t s = (int64_t)p.step + 1;  // 1-based optimizer step being applied
-      const double b1p = pow((double)p.beta1, (double)s), b2p = pow((double)p.beta2, (double)s);
-      const float step_size = (float)((double)p.lr / (1.0 - b1p));
-      const float bc2_sqrt = (float)sqrt(1.0 - b2p);
-      float* mrow = p.user_m + (size_t)cur_u * D;
-      float* vrow = p.user_v + (size_t)cur_u * D;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        if (!colok[v]) continue;
-        const int c = 4 * (g.gl + LANES * v);
-        float4 m = ld4(mrow + c), vv = ld4(vrow + c);
-        float4 grad;
-        grad.x = gu[v].x + rn * u[v].x;
-        grad.y = gu[v].y + rn * u[v].y;
-        grad.z = gu[v].z + rn * u[v].z;
-        grad.w = gu[v].w + rn * u[v].w;
-        float4 pp = u[v];  // already caught up to step s-1 at load time
-        adam4(pp, m, vv, grad, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
-        st4(urow + c, pp);
-        st4(mrow + c, m);
-        st4(vrow + c, vv);
-      }
-      if (g.gl == 0) p.user_last[cur_u] = (int32_t)s;
-    }
-  };
-
-  // prologue: fill the ring
-#pragma unroll
-  for (int s = 0; s < kStages; ++s)
-    if (!fdone) fetch_one();
-  __syncwarp(g.mask);  // stage records (plain shared stores by lane 0) are visible to the group
-
-  while (cseq < fseq) {
-    const uint32_t stage = cseq % kStages;
-    mbar_wait(bar0 + 8u * stage, (cseq / kStages) & 1u);
-    const unsigned char* sp = gsm + (size_t)stage * stage_bytes;
-    const int4 rec = *reinterpret_cast<const int4*>(sp);
-    const int32_t uu = rec.x, i = rec.y, j = rec.z, head = rec.w;
-    const float* su = reinterpret_cast<const float*>(sp + 16);
-    const float* si = su + D;
-    const float* sj = si + D;
-    if (head) {
-      flush_user();
-      cur_u = uu;
-      nocc = 0;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        u[v] = colok[v] ? ld4(su + 4 * (g.gl + LANES * v)) : f4zero();
-        gu[v] = f4zero();
-      }
-      if (OPT == RBPR_OPT_ADAM) {
-        const int64_t last = p.user_last[uu];
-        const int64_t upto = (int64_t)p.step;  // optimizer steps already taken globally
-        if (last > 0 && last < upto) {
-          float* mrow = p.user_m + (size_t)uu * D;
-          float* vrow = p.user_v + (size_t)uu * D;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            if (!colok[v]) continue;
-            const int c = 4 * (g.gl + LANES * v);
-            float4 m = ld4(mrow + c), vv = ld4(vrow + c);
-            adam_catchup4(u[v], m, vv, last, upto, p.lr, p.beta1, p.beta2, p.eps);
-            st4(mrow + c, m);
-            st4(vrow + c, vv);
-          }
-        }
-      }
-      usq = 0.f;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) usq += dot4(u[v], u[v]);
-      usq *= p.reg_user;
-    }
-    float4 vi[NV], vj[NV];
+  for (uint32_t k = (blockIdx.x * kPhaseAThreads + threadIdx.x) / LANES; k < n; k += ngroups) {
+    const int4 rec = __ldg(records + k);
+    const int32_t uu = rec.x, i = rec.y, j = rec.z;
+    const bool single = (rec.w & kRecSingle) != 0;
+    const float* urow = p.user_emb + (size_t)uu * D;
+    const float* irow = p.item_emb + (size_t)i * D;
+    const float* jrow = p.item_emb + (size_t)j * D;
+    float4 u[NV], vi[NV], vj[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      vi[v] = colok[v] ? ld4(si + 4 * (g.gl + LANES * v)) : f4zero();
-      vj[v] = colok[v] ? ld4(sj + 4 * (g.gl + LANES * v)) : f4zero();
+      const int c = 4 * (g.gl + LANES * v);
+      u[v] = colok[v] ? ld4(urow + c) : f4zero();
+      vi[v] = colok[v] ? ld4(irow + c) : f4zero();
+      vj[v] = colok[v] ? ld4(jrow + c) : f4zero();
     }
-    float pp = 0.f, pn = 0.f, sq = 0.f;
+    float4 m[NV], vv[NV];  // Adam moments of the user row (ADAM instantiation only)
+    if (OPT == RBPR_OPT_ADAM) {
+      // Lazy dense-Adam catch-up of the user row to the optimizer steps already taken globally:
+      // the caught-up row is what every triple of the user must see.  (bpr_apply redoes it for
+      // users with several triples, whose row and moments are not written here.)
+      const int64_t last = p.user_last[uu];
+      const int64_t upto = (int64_t)p.step;
+      const bool behind = last > 0 && last < upto;
+      if (single || behind) {
+        const float* mrow = p.user_m + (size_t)uu * D;
+        const float* vrow = p.user_v + (size_t)uu * D;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = 4 * (g.gl + LANES * v);
+          m[v] = colok[v] ? ld4(mrow + c) : f4zero();
+          vv[v] = colok[v] ? ld4(vrow + c) : f4zero();
+          if (behind) adam_catchup4(u[v], m[v], vv[v], last, upto, p.lr, p.beta1, p.beta2, p.eps);
+        }
+      }
+    }
+    float pp = 0.f, pn = 0.f, sq = 0.f, usq = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       pp += dot4(u[v], vi[v]);
       pn += dot4(u[v], vj[v]);
       sq += p.reg_item * dot4(vi[v], vi[v]) + p.reg_neg * dot4(vj[v], vj[v]);
+      usq += dot4(u[v], u[v]);
     }
     float x;
     if (p.logit_out != nullptr) {  // drop-in Model.forward output: logits_pos / logits_neg
@@ -498,11 +333,8 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
         xn += __ldg(p.item_bias + j);
       }
       x = xp - xn;
-      if (g.gl == 0) {
-        const uint32_t kc = kfirst + cseq;
-        p.logit_out[p.step_pos != nullptr ? __ldg(p.step_pos + kc) : (int32_t)kc] =
-            make_float2(xp, xn);
-      }
+      if (g.gl == 0)
+        p.logit_out[p.step_pos != nullptr ? __ldg(p.step_pos + k) : (int32_t)k] = make_float2(xp, xn);
     } else {
       x = g.sum(pp - pn);
       if (p.item_bias != nullptr) x += __ldg(p.item_bias + i) - __ldg(p.item_bias + j);
@@ -510,12 +342,12 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
     // softplus(-x) and c = sigmoid(-x), overflow-safe; fast intrinsics: abs err ~1e-7 on a
     // per-triple loss of O(1), inside the 1e-4 parity budget
     const float e = __expf(-fabsf(x));
-    const float sp_ = fmaxf(-x, 0.f) + __logf(1.0f + e);
+    const float sp = fmaxf(-x, 0.f) + __logf(1.0f + e);
     const float inv = __fdividef(1.0f, 1.0f + e);
     const float c = (x >= 0.f) ? e * inv : inv;
-    l2_acc += 0.5f * (sq + usq);
+    l2_acc += 0.5f * (sq + p.reg_user * usq);
     if (g.gl == 0) {
-      loss_acc += sp_;
+      loss_acc += sp;
       absx_acc += fabsf(x);
       cnt_acc += 1.f;
       p.touched[i] = 1u;
@@ -525,17 +357,17 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
         atomicAdd(p.bias_grad + j, c);
       }
     }
-    // The two item-row gradients overwrite the rows they were computed from (each lane rewrites
-    // exactly the words it read) and leave for the dense accumulator as ONE bulk asynchronous
-    // reduction per row (TMA, fp32 add at L2) instead of LANES*NV vector atomics per row.
-    float* smi = const_cast<float*>(si);
-    float* smj = const_cast<float*>(sj);
+    // row 0 of either table is the padding row: nn.Embedding(padding_idx=0) blocks its gradient
+    float* gi = (i != 0) ? p.item_grad + (size_t)i * D : nullptr;
+    float* gj = (j != 0) ? p.item_grad + (size_t)j * D : nullptr;
+    float* gurow = p.user_grad + (size_t)uu * D;
+    float* uout = p.user_emb + (size_t)uu * D;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       if (!colok[v]) continue;
       const int cidx = 4 * (g.gl + LANES * v);
       const float4 cu = make_float4(c * u[v].x, c * u[v].y, c * u[v].z, c * u[v].w);
-      float4 a, b;
+      float4 a, b, gu;
       a.x = p.reg_item * vi[v].x - cu.x;
       a.y = p.reg_item * vi[v].y - cu.y;
       a.z = p.reg_item * vi[v].z - cu.z;
@@ -544,29 +376,35 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
       b.y = p.reg_neg * vj[v].y + cu.y;
       b.z = p.reg_neg * vj[v].z + cu.z;
       b.w = p.reg_neg * vj[v].w + cu.w;
-      st4(smi + cidx, a);
-      st4(smj + cidx, b);
-      gu[v].x -= c * (vi[v].x - vj[v].x);
-      gu[v].y -= c * (vi[v].y - vj[v].y);
-      gu[v].z -= c * (vi[v].z - vj[v].z);
-      gu[v].w -= c * (vi[v].w - vj[v].w);
+      if (gi != nullptr) red4(gi + cidx, a);
+      if (gj != nullptr) red4(gj + cidx, b);
+      gu.x = p.reg_user * u[v].x - c * (vi[v].x - vj[v].x);
+      gu.y = p.reg_user * u[v].y - c * (vi[v].y - vj[v].y);
+      gu.z = p.reg_user * u[v].z - c * (vi[v].z - vj[v].z);
+      gu.w = p.reg_user * u[v].w - c * (vi[v].w - vj[v].w);
+      if (uu == 0) continue;
+      if (!single) {
+        red4(gurow + cidx, gu);
+      } else if (OPT == RBPR_OPT_SGD) {
+        float4 o;
+        o.x = u[v].x - p.lr * gu.x;
+        o.y = u[v].y - p.lr * gu.y;
+        o.z = u[v].z - p.lr * gu.z;
+        o.w = u[v].w - p.lr * gu.w;
+        st4(uout + cidx, o);
+      } else {
+        float4 pp4 = u[v];
+        adam4(pp4, m[v], vv[v], gu, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+        st4(uout + cidx, pp4);
+        st4(p.user_m + (size_t)uu * D + cidx, m[v]);
+        st4(p.user_v + (size_t)uu * D + cidx, vv[v]);
+      }
     }
-    fence_proxy_async_smem();  // generic-proxy stores above -> visible to the async proxy
-    __syncwarp(g.mask);
-    if (g.gl == 0) {
-      // row 0 of the item table is the padding row: nn.Embedding(padding_idx=0) blocks its gradient
-      if (i != 0) bulk_red_add_f32(p.item_grad + (size_t)i * D, smem_u32(smi), row_bytes);
-      if (j != 0) bulk_red_add_f32(p.item_grad + (size_t)j * D, smem_u32(smj), row_bytes);
-      bulk_commit();
-      bulk_wait_read<1>();  // the previous triple's reduction has read its stage: it can be refilled
+    if (OPT == RBPR_OPT_ADAM && single && uu != 0) {
+      __syncwarp(g.mask);  // every lane has read user_last before it moves
+      if (g.gl == 0) p.user_last[uu] = (int32_t)(p.step + 1);
     }
-    __syncwarp(g.mask);
-    ++cseq;
-    if (cseq >= 2u && !fdone) fetch_one();  // refills stage (cseq-2) % kStages == fseq % kStages
-    ++nocc;
   }
-  flush_user();
-  if (g.gl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem outlives its readers
 
   // per-warp statistics partial (no block barrier: warps retire independently)
   float a = loss_acc, b = l2_acc, cabs = absx_acc, d = cnt_acc;
@@ -581,19 +419,63 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
     p.partials[blockIdx.x * (kPhaseAThreads / 32) + (threadIdx.x >> 5)] = make_float4(a, b, cabs, d);
 }
 
+// Phase B — apply the accumulated gradients and clear the accumulators.
+//   items: SGD touches only the rows flagged by phase A; Adam (and the multi-GPU path, where the
+//          accumulator holds the all-reduced gradient) sweeps every row, which is torch.optim's
+//          dense semantics for the replicated item table.
+//   users: rows of users with several triples in the step (records flagged kRecMultiHead): their
+//          summed gradient sits in user_grad; single-occurrence users were finished by phase A.
 template <int LANES, int NV, int OPT>
-__global__ void __launch_bounds__(256) bpr_apply_items(const ApplyParams p) {
+__global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
   const Group<LANES> g;
   const int D = p.D;
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   float step_size = 0.f, bc2_sqrt = 1.f;
   if (OPT == RBPR_OPT_ADAM) {
     const double s = (double)(p.step + 1);
     step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, s)));
     bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, s));
   }
-  for (; r < p.I; r += groups) {
+  if (p.do_users) {
+    for (int64_t k = gid; k < p.n; k += groups) {
+      const int4 rec = __ldg(p.records + k);
+      if ((rec.w & kRecMultiHead) == 0 || rec.x == 0) continue;
+      const int64_t r = rec.x;
+      float* grow = p.user_grad + r * D;
+      float* prow = p.user_emb + r * D;
+      int64_t last = 0;
+      if (OPT == RBPR_OPT_ADAM) last = p.user_last[r];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = 4 * (g.gl + LANES * v);
+        if (c >= D) continue;
+        const float4 gr = ld4(grow + c);
+        float4 pp = ld4(prow + c);
+        if (OPT == RBPR_OPT_SGD) {
+          pp.x -= p.lr * gr.x;
+          pp.y -= p.lr * gr.y;
+          pp.z -= p.lr * gr.z;
+          pp.w -= p.lr * gr.w;
+        } else {
+          float4 m = ld4(p.user_m + r * D + c), vv = ld4(p.user_v + r * D + c);
+          if (last > 0 && last < (int64_t)p.step)
+            adam_catchup4(pp, m, vv, last, (int64_t)p.step, p.lr, p.beta1, p.beta2, p.eps);
+          adam4(pp, m, vv, gr, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+          st4(p.user_m + r * D + c, m);
+          st4(p.user_v + r * D + c, vv);
+        }
+        st4(prow + c, pp);
+        st4(grow + c, f4zero());
+      }
+      if (OPT == RBPR_OPT_ADAM) {
+        __syncwarp(g.mask);
+        if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
+      }
+    }
+  }
+  if (!p.do_items) return;
+  for (int64_t r = gid; r < p.I; r += groups) {
     if (!p.dense) {
       if (p.touched[r] == 0u) continue;
     }
@@ -673,9 +555,9 @@ __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_
 // Per-optimizer launchers (train_sgd.cu / train_adam.cu), one translation unit each so the
 // template instantiations compile in parallel.
 int rbpr_launch_phase_a_sgd(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,
-                            const int4* records, int* warps_out, cudaStream_t st);
+                            const int4* records, int blocks, cudaStream_t st);
 int rbpr_launch_phase_a_adam(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,
-                             const int4* records, int* warps_out, cudaStream_t st);
+                             const int4* records, int blocks, cudaStream_t st);
 int rbpr_phase_a_prepare_sgd(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm);
 int rbpr_phase_a_prepare_adam(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm);
 int rbpr_launch_apply_sgd(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,

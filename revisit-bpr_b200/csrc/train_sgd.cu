@@ -4,31 +4,24 @@
 using namespace rbpr_dev;
 
 int rbpr_launch_phase_a_sgd(rbpr_ctx* ctx, const TrainParams& p, int lanes, int nv,
-                              const int4* records, int* warps_out, cudaStream_t st) {
-  const int groups_per_block = kPhaseAThreads / lanes;
-  const int blocks = (p.groups + groups_per_block - 1) / groups_per_block;
-  const size_t smem = phase_a_smem_bytes(p.D, lanes);
-  *warps_out = blocks * (kPhaseAThreads / 32);
-#define X(L, V)                                                                                \
-  if (lanes == L && nv == V) {                                                                 \
-    bpr_phase_a<L, V, RBPR_OPT_SGD><<<blocks, kPhaseAThreads, smem, st>>>(p, records);          \
-    return 0;                                                                                  \
+                              const int4* records, int blocks, cudaStream_t st) {
+#define X(L, V)                                                                       \
+  if (lanes == L && nv == V) {                                                        \
+    bpr_phase_a<L, V, RBPR_OPT_SGD><<<blocks, kPhaseAThreads, 0, st>>>(p, records);    \
+    return 0;                                                                         \
   }
   RBPR_FOR_EACH_GEOMETRY(X)
 #undef X
   RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
 }
 
-// Opt the instantiation for `dim` into its dynamic shared-memory size and report how many CTAs
-// of it fit on one SM (used to size the grid as one resident wave).
+// How many CTAs of the instantiation fit on one SM (the grid is sized as one resident wave).
 int rbpr_phase_a_prepare_sgd(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm) {
-  const size_t smem = phase_a_smem_bytes(dim, lanes);
+  (void)dim;
 #define X(L, V)                                                                                \
   if (lanes == L && nv == V) {                                                                 \
-    RBPR_CUDA(ctx, cudaFuncSetAttribute(bpr_phase_a<L, V, RBPR_OPT_SGD>,                        \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     RBPR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(                              \
-                       blocks_per_sm, bpr_phase_a<L, V, RBPR_OPT_SGD>, kPhaseAThreads, smem));  \
+                       blocks_per_sm, bpr_phase_a<L, V, RBPR_OPT_SGD>, kPhaseAThreads, 0));     \
     return 0;                                                                                  \
   }
   RBPR_FOR_EACH_GEOMETRY(X)
@@ -39,12 +32,13 @@ int rbpr_phase_a_prepare_sgd(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blo
 int rbpr_launch_apply_sgd(rbpr_ctx* ctx, const ApplyParams& p, int lanes, int nv,
                             cudaStream_t st) {
   const int groups_per_block = 256 / lanes;
-  const int64_t blocks64 = (p.I + groups_per_block - 1) / groups_per_block;
+  const int64_t work = (p.do_items ? p.I : 0) > (p.do_users ? (int64_t)p.n : 0) ? (p.do_items ? p.I : 0) : (p.do_users ? (int64_t)p.n : 0);
+  const int64_t blocks64 = (work + groups_per_block - 1) / groups_per_block > 0 ? (work + groups_per_block - 1) / groups_per_block : 1;
   const int64_t maxb = (int64_t)ctx->sm_count * 8;
   const int blocks = (int)(blocks64 < maxb ? blocks64 : maxb);
 #define X(L, V)                                                   \
   if (lanes == L && nv == V) {                                    \
-    bpr_apply_items<L, V, RBPR_OPT_SGD><<<blocks, 256, 0, st>>>(p);      \
+    bpr_apply<L, V, RBPR_OPT_SGD><<<blocks, 256, 0, st>>>(p);      \
     return 0;                                                     \
   }
   RBPR_FOR_EACH_GEOMETRY(X)

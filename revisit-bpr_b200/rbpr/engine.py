@@ -69,6 +69,7 @@ class Engine:
         self.indptr = self.indices = None
         self.nnz = 0
         self._alias = None
+        self._pin_stats = self._pin_neg = None
 
     def __del__(self) -> None:
         try:
@@ -160,8 +161,16 @@ class Engine:
         assert not triple_idx.is_cuda and triple_idx.dtype == torch.int64
         n = triple_idx.numel()
         steps = (n + batch - 1) // batch
-        stats = torch.empty((steps, native.STATS_PER_STEP), dtype=torch.float64).pin_memory()
-        neg_out = torch.empty(n, dtype=torch.int64).pin_memory() if want_neg else None
+        # pinned result buffers are kept across calls (page-locking per call costs milliseconds)
+        if self._pin_stats is None or self._pin_stats.size(0) < steps:
+            self._pin_stats = torch.empty((max(steps, 256), native.STATS_PER_STEP),
+                                          dtype=torch.float64).pin_memory()
+        stats = self._pin_stats[:steps]
+        neg_out = None
+        if want_neg:
+            if self._pin_neg is None or self._pin_neg.numel() < n:
+                self._pin_neg = torch.empty(n, dtype=torch.int64).pin_memory()
+            neg_out = self._pin_neg[:n]
         self._check(self.lib.rbpr_train_steps_host(self.ctx, _ptr(triple_idx), n, batch, seed, step0,
                                                    C.byref(self.hp), _ptr(neg_in), _ptr(neg_out),
                                                    _ptr(stats), _stream()))

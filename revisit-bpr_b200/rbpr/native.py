@@ -5,6 +5,11 @@ import ctypes as C
 import os
 from pathlib import Path
 
+# Load every kernel of librbpr.so when the CUDA context is created instead of at first launch:
+# lazy loading otherwise pages cubins in from disk in the middle of a training loop (seen as
+# 10-400 ms stalls on fresh boxes).  Only effective if set before the process initialises CUDA.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 LIB_PATH = Path(__file__).resolve().parent.parent / "librbpr.so"
 
 OPT_SGD, OPT_ADAM = 0, 1
