@@ -154,6 +154,41 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
 int rbpr_item_grad_buffer(rbpr_ctx* ctx, float** ptr, int64_t* numel);
 int rbpr_apply_item_grads(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* stream);
 
+/* ---- entry points shaped like the reference's Python call sites (explicit id batches) ---------- */
+
+/* One training step on an explicit batch of (user, positive, negative) ids, as a DataLoader of the
+ * reference delivers them (device int64, length n): forward + backward + optimizer update, exact
+ * minibatch semantics, the three rows of every triple updated in place.  Row 0 of either table is
+ * the padding row: it contributes to the logits but receives no embedding gradient
+ * (nn.Embedding(padding_idx=0), example.py:311-321).
+ * Replaces Model.forward train branch + Loss + regularization (model.py:48-93, loss.py:19-21),
+ * accelerator.backward and optimizer.step/zero_grad (experiments/trainer.py:72-81,
+ * example.py:175-178) for one batch.
+ *   logits_out : device float (n,2) or NULL — (logits_pos, logits_neg) per triple, input order
+ *   stats_out  : device double (RBPR_STATS_PER_STEP) or NULL
+ *   step       : optimizer steps taken so far (Adam bias correction / lazy catch-up)            */
+int rbpr_train_step_triples(rbpr_ctx* ctx, const int64_t* users, const int64_t* items,
+                            const int64_t* negs, int64_t n, uint64_t step, const rbpr_hparams* hp,
+                            float* logits_out, double* stats_out, void* stream);
+
+/* logits[b,k] = <U[users[b]], V[items[b,k]]> + item_bias[items[b,k]] + user_bias[users[b]] for an
+ * arbitrary (n_users, per_user) block of item ids; entries with mask == 0 become -1e13.
+ * Replaces MF.forward (model.py:131-145) in eval mode and Model.forward's eval branch
+ * (model.py:43-47) for any collator (AllItemsCollator, OnePosCollator, ManyPosCollator:
+ * experiments/bpr/dataset.py:193-296).  mask, user_bias may be NULL.  Device pointers. */
+int rbpr_pair_logits(rbpr_ctx* ctx, const int64_t* users, const int64_t* items, const float* mask,
+                     int64_t n_users, int64_t per_user, const float* user_bias, float* out,
+                     void* stream);
+
+/* Negative sampling from the reference's batch layout: seen (batch,width) int64, 0-padded rows in
+ * any order (batch["seen_items"], experiments/bpr/dataset.py:175-181).  neg_out (batch,num) int64.
+ * Same counter-based draw as rbpr_sample_negatives with the slot (row*num + s) as subsequence;
+ * draws of one row are independent.  Replaces _sampling_weights + torch.multinomial
+ * (revisit_bpr/modules/neg_samplers.py:31-37,135-141; experiments/bpr/exp.py:282-293). */
+int rbpr_sample_negatives_padded(rbpr_ctx* ctx, const int64_t* seen, int64_t batch, int64_t width,
+                                 int64_t num_items, int64_t num, uint64_t seed, uint64_t step,
+                                 int32_t sampler, int64_t* neg_out, void* stream);
+
 /* Bring every lazily-updated user row up to `step` optimizer steps (dense-Adam semantics
  * of torch.optim.Adam: rows with zero gradient still move).  Call before reading the user
  * table (eval, checkpoint).  No-op for SGD. */
@@ -185,6 +220,20 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
 int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
                      const int64_t* seen_indptr, const int32_t* seen_indices, float* out,
                      void* stream);
+
+/* Ranking metrics from DENSE tensors, the calling convention of revisit_bpr.metrics
+ * (Metric.__call__/compute(output (B,I), target (B,I) multi-hot)): per row, top-k_max of `scores`
+ * (ties -> lower column first), hits against `target`, NDCG@k / Recall@k / Precision@k for every
+ * cut-off.  Replaces prepare_target (revisit_bpr/metrics/metric.py:110-113: a full argsort per
+ * metric), NDCG.compute (metrics/ndcg.py:8-24,69-78; linear_gain selects gain_function="linear"),
+ * Recall.compute (metrics/recall.py:44-51), Precision.compute (metrics/precision.py:44-51).
+ * A target value outside {0,1} raises RBPR_ERR_DATA at the next rbpr_sync_check
+ * (validate_metric_inputs, metric.py:100-107).  Outputs (n_rows, n_ks) float or NULL;
+ * topk_items (n_rows,k_max) int32 or NULL.  Device pointers, contiguous rows. */
+int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
+                            int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,
+                            int32_t linear_gain, float* ndcg_out, float* recall_out,
+                            float* precision_out, int32_t* topk_items, void* stream);
 
 /* Instrumentation: number of kernels this context has launched so far, and the device time
  * (ms, CUDA events on the launch stream) spent in the dominant training kernel since the

@@ -105,3 +105,50 @@ def sample_negatives(indptr, indices, coo_user, triple_idx, seed, step, num_item
     if pending.size:
         raise RuntimeError("negative sampler exhausted its attempts")
     return out
+
+
+def sample_negatives_padded(seen, num_items, num, seed, step, alias=None):
+    """Padded-seen variant (rbpr_sample_negatives_padded): seen (B,S) int64 0-padded, any order;
+    slot = row*num + s is the Philox subsequence.  Returns (B,num) int64."""
+    seen = np.asarray(seen, dtype=np.int64)
+    B = seen.shape[0]
+    out = np.zeros((B, num), dtype=np.int64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    n = num_items - 1 if alias is None else num_items
+    thresh = (1 << 32) % n
+    for row in range(B):
+        banned = set(int(x) for x in seen[row])
+        for s in range(num):
+            slot = row * num + s
+            res = -1
+            for blk in range(256):
+                off = (int(step) << 8) | blk
+                w = [int(x) for x in philox4x32_10(np.uint32(off & 0xFFFFFFFF), np.uint32((off >> 32) & 0xFFFFFFFF),
+                                                   np.uint32(slot & 0xFFFFFFFF), np.uint32(slot >> 32), k0, k1)]
+                if alias is None:
+                    for a in range(4):
+                        m = w[a] * n
+                        if (m & 0xFFFFFFFF) < thresh:
+                            continue
+                        j = 1 + (m >> 32)
+                        if j not in banned:
+                            res = j
+                            break
+                else:
+                    for a in range(2):
+                        m = w[2 * a] * n
+                        if (m & 0xFFFFFFFF) < thresh:
+                            continue
+                        col = m >> 32
+                        uf = np.float32(w[2 * a + 1] >> 8) * np.float32(1.0 / 16777216.0)
+                        j = col if uf < alias[0][col] else int(alias[1][col])
+                        if j == 0 or j in banned:
+                            continue
+                        res = j
+                        break
+                if res >= 0:
+                    break
+            if res < 0:
+                raise RuntimeError("negative sampler exhausted its attempts")
+            out[row, s] = res
+    return out

@@ -148,6 +148,12 @@ struct TopkParams {
   float* __restrict__ topk_scores;
   float* __restrict__ ndcg_out;
   float* __restrict__ recall_out;
+  float* __restrict__ precision_out;
+  // dense-target mode (revisit_bpr.metrics on (B,I) tensors): positives = target[row, item] > 0
+  const float* __restrict__ target;
+  int64_t target_ld;
+  int linear_gain;  // NDCG gain_function="linear": discount 1/(rank+1) instead of 1/log2(rank+2)
+  int32_t* __restrict__ flag;
 };
 
 __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
@@ -259,25 +265,46 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
     hlo = p.held_indptr[orow];
     hhi = p.held_indptr[orow + 1];
   }
-  const int n_pos = (int)(hhi - hlo);
+  int n_pos = (int)(hhi - hlo);
+  if (p.target != nullptr) {  // count positives of the dense target row (and check it is binary)
+    __shared__ int s_npos;
+    if (tid == 0) s_npos = 0;
+    __syncthreads();
+    const float* trow = p.target + orow * p.target_ld;
+    int local = 0;
+    bool bad = false;
+    for (int i = tid; i < I; i += 256) {
+      const float t = trow[i];
+      local += (t == 1.0f);
+      bad |= !(t == 0.0f || t == 1.0f);
+    }
+    if (bad) atomicExch(p.flag, 9);
+    atomicAdd(&s_npos, local);
+    __syncthreads();
+    n_pos = s_npos;
+  }
   if (tid < KCAP) {
     if (tid < k) {
       const unsigned long long c = sel[tid];
       item = (int32_t)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull));
       if (p.topk_items) p.topk_items[orow * p.k_max + tid] = item;
       if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = row[item];
-      int64_t lo = hlo, hi = hhi;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const int32_t v = p.held_indices[mid];
-        if (v < item) lo = mid + 1; else hi = mid;
+      if (p.target != nullptr) {
+        hit = (p.target[orow * p.target_ld + item] == 1.0f) ? 1.f : 0.f;
+      } else {
+        int64_t lo = hlo, hi = hhi;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          const int32_t v = p.held_indices[mid];
+          if (v < item) lo = mid + 1; else hi = mid;
+        }
+        if (lo < hhi && p.held_indices[lo] == item) hit = 1.f;
       }
-      if (lo < hhi && p.held_indices[lo] == item) hit = 1.f;
     } else if (tid < p.k_max) {
       if (p.topk_items) p.topk_items[orow * p.k_max + tid] = -1;
       if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = kMasked;
     }
-    const float disc = 1.0f / log2f((float)tid + 2.0f);
+    const float disc = p.linear_gain ? 1.0f / ((float)tid + 1.0f) : 1.0f / log2f((float)tid + 2.0f);
     disc_scan[tid] = disc;
     hit_scan[tid] = hit * disc;
   }
@@ -299,7 +326,7 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   __syncthreads();
   if (tid < p.n_ks) {
     const int kk = min(min(p.ks[tid], k), KCAP);
-    float ndcg = 0.f, recall = 0.f;
+    float ndcg = 0.f, recall = 0.f, precision = 0.f;
     if (kk > 0 && n_pos > 0) {
       const float dcg = hit_scan[kk - 1];
       const float idcg = disc_scan[min(kk, n_pos) - 1];
@@ -313,9 +340,11 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
         hits += __popc(hitbits[w] & m);
       }
       recall = (float)hits / (float)n_pos;
+      precision = (float)hits / (float)kk;
     }
     if (p.ndcg_out) p.ndcg_out[orow * p.n_ks + tid] = ndcg;
     if (p.recall_out) p.recall_out[orow * p.n_ks + tid] = recall;
+    if (p.precision_out) p.precision_out[orow * p.n_ks + tid] = precision;
   }
 }
 
@@ -417,6 +446,48 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
     ctx->launches++;
     RBPR_CUDA(ctx, cudaGetLastError());
   }
+  return 0;
+}
+
+int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
+                            int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,
+                            int32_t linear_gain, float* ndcg_out, float* recall_out,
+                            float* precision_out, int32_t* topk_items, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (n_rows == 0) return 0;
+  if (!scores || !target || n_rows < 0 || n_cols < 1 || n_cols >= (1ll << 31))
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "topk_metrics_dense: bad arguments");
+  if (k_max < 1 || k_max > RBPR_MAX_TOPK)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "topk_metrics_dense: k_max=%d outside [1,%d]", k_max, RBPR_MAX_TOPK);
+  if (n_ks < 1 || n_ks > 16 || !ks) RBPR_FAIL(ctx, RBPR_ERR_ARG, "topk_metrics_dense: 1..16 cut-offs");
+  for (int q = 0; q < n_ks; ++q)
+    if (ks[q] < 1 || ks[q] > k_max)
+      RBPR_FAIL(ctx, RBPR_ERR_ARG, "topk_metrics_dense: cut-off %d outside [1,k_max=%d]", ks[q], k_max);
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  TopkParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.S = scores;
+  tp.ld = n_cols;
+  tp.I = (int)n_cols;
+  tp.k_max = k_max;
+  tp.n_ks = n_ks;
+  for (int q = 0; q < n_ks; ++q) tp.ks[q] = ks[q];
+  tp.topk_items = topk_items;
+  tp.ndcg_out = ndcg_out;
+  tp.recall_out = recall_out;
+  tp.precision_out = precision_out;
+  tp.target = target;
+  tp.target_ld = n_cols;
+  tp.linear_gain = linear_gain;
+  tp.flag = ctx->flag;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += 32768) {  // grid.x limit is not the issue; keep launches modest
+    const int nb = (int)((n_rows - r0) < 32768 ? (n_rows - r0) : 32768);
+    tp.S = scores + r0 * n_cols;
+    tp.row0 = r0;
+    topk_metrics<<<nb, 256, 0, (cudaStream_t)stream>>>(tp);
+    ctx->launches++;
+  }
+  RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
 }
 

@@ -112,14 +112,10 @@ __global__ void sample_only(const TrainParams p, const int64_t* __restrict__ tri
   if (g.gl == 0) out[k] = (int64_t)j;
 }
 
-int check_ready(rbpr_ctx* ctx, const rbpr_hparams* hp) {
+int check_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!hp) RBPR_FAIL(ctx, RBPR_ERR_ARG, "hparams is NULL");
   if (!ctx->user_emb || !ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
-  if (!ctx->indptr || !ctx->indices) RBPR_FAIL(ctx, RBPR_ERR_STATE, "CSR not bound");
-  if (ctx->csr_users != ctx->U)
-    RBPR_FAIL(ctx, RBPR_ERR_ARG, "CSR has %lld rows but the user table has %lld",
-              (long long)ctx->csr_users, (long long)ctx->U);
   if (hp->optimizer != RBPR_OPT_SGD && hp->optimizer != RBPR_OPT_ADAM)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "unknown optimizer %d", hp->optimizer);
   if (hp->optimizer == RBPR_OPT_ADAM) {
@@ -128,6 +124,16 @@ int check_ready(rbpr_ctx* ctx, const rbpr_hparams* hp) {
     if (ctx->item_bias && (!ctx->bias_m || !ctx->bias_v))
       RBPR_FAIL(ctx, RBPR_ERR_STATE, "Adam requested with item bias but bias state not bound");
   }
+  return 0;
+}
+
+int check_ready(rbpr_ctx* ctx, const rbpr_hparams* hp) {
+  int rc = check_tables(ctx, hp);
+  if (rc) return rc;
+  if (!ctx->indptr || !ctx->indices) RBPR_FAIL(ctx, RBPR_ERR_STATE, "CSR not bound");
+  if (ctx->csr_users != ctx->U)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "CSR has %lld rows but the user table has %lld",
+              (long long)ctx->csr_users, (long long)ctx->U);
   if (hp->sampler < RBPR_SAMPLER_UNIFORM || hp->sampler > RBPR_SAMPLER_INJECTED)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "unknown sampler %d", hp->sampler);
   if (hp->sampler == RBPR_SAMPLER_WEIGHTED && (!ctx->alias_prob || !ctx->alias_idx))
@@ -403,6 +409,9 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
       case 4: RBPR_FAIL(ctx, RBPR_ERR_DATA, "a user has seen every non-padding item: no negative exists");
       case 5: RBPR_FAIL(ctx, RBPR_ERR_DATA, "CSR item id outside [1,num_items)");
       case 6: RBPR_FAIL(ctx, RBPR_ERR_DATA, "CSR row is not strictly ascending");
+      case 7: RBPR_FAIL(ctx, RBPR_ERR_ARG, "user id outside [0,num_users)");
+      case 8: RBPR_FAIL(ctx, RBPR_ERR_ARG, "item id outside [0,num_items)");
+      case 9: RBPR_FAIL(ctx, RBPR_ERR_DATA, "metric target contains values outside of 0 and 1");
       default: RBPR_FAIL(ctx, RBPR_ERR_DATA, "device error flag %d", f);
     }
   }
@@ -410,6 +419,52 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
 }
 
 }  // namespace
+
+// ---- helpers shared with dropin.cu ---------------------------------------------------------------
+int rbpr_internal_check_ready_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
+  return check_tables(ctx, hp);
+}
+
+int rbpr_internal_reserve_sort(rbpr_ctx* ctx, int64_t n) {
+  int rc = ensure_capacity(ctx, n, 1);
+  if (rc) return rc;
+  return ensure_step_scratch(ctx, n, 1, 4 * ctx->sm_count * 16);
+}
+
+// One step over prepared records on the caller's stream: phase A, apply (items + users), stats.
+int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int4* records, int n,
+                                uint64_t step, float2* logit_out, const int32_t* step_pos,
+                                double* stats_out, cudaStream_t st) {
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, RBPR_STATS_PER_STEP * sizeof(double), st));
+  if (n > 0) {
+    int lanes, nv, blocks = 1;
+    rbpr_geometry(ctx->D, &lanes, &nv);
+    int rc = pick_blocks(ctx, hp, n, lanes, nv, &blocks);
+    if (rc) return rc;
+    const int stride = blocks * (kPhaseAThreads / 32);
+    rc = ensure_step_scratch(ctx, n, 1, stride);
+    if (rc) return rc;
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
+    TrainParams p;
+    fill_train_params(ctx, p, 0, hp);
+    p.n = n;
+    p.step = step;
+    p.logit_out = logit_out;
+    p.step_pos = step_pos;
+    rc = run_phase_a(ctx, p, hp, records, reinterpret_cast<float4*>(ctx->partials[0]), blocks, st);
+    if (rc) return rc;
+    rc = run_apply(ctx, step, hp, 0, 1, records, n, st);
+    if (rc) return rc;
+    reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials[0]), stride,
+                                    ctx->stats);
+    ctx->launches++;
+    RBPR_CUDA(ctx, cudaGetLastError());
+  }
+  if (stats_out)
+    RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats, RBPR_STATS_PER_STEP * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
 
 extern "C" {
 

@@ -38,7 +38,83 @@ def resolve_reg(reg_alphas: dict | None) -> tuple[float, float, float]:
     return float(user), float(item), float(neg)
 
 
-class Engine:
+class Context:
+    """A bare native context on one device: what the table-less entry points need (negative
+    sampling from padded seen matrices, ranking metrics from dense tensors)."""
+
+    def __init__(self, device: torch.device) -> None:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise native.NativeError("the BPR hot path runs on a B200 only: no CPU fallback exists")
+        self.lib = native.load()
+        self.device = device
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = C.c_void_p()
+        rc = self.lib.rbpr_create(dev_index, C.byref(self.ctx))
+        if rc != 0:
+            raise native.NativeError(f"rbpr_create failed ({rc}): needs a compute-capability 10.x device")
+        self._alias = None
+
+    def __del__(self) -> None:
+        try:
+            if getattr(self, "ctx", None) is not None and self.ctx.value:
+                self.lib.rbpr_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        native.check(self.lib, self.ctx, rc)
+
+    def sync_check(self) -> None:
+        self._check(self.lib.rbpr_sync_check(self.ctx, _stream()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.rbpr_launch_count(self.ctx))
+
+    def bind_item_weights(self, weights: torch.Tensor) -> None:
+        """Popularity weights (I,) -> Walker alias table (weights[0] is forced to 0)."""
+        w = weights.detach().double().cpu().numpy().copy()
+        w[0] = 0.0
+        prob, alias = build_alias(w)
+        self._alias = (torch.from_numpy(prob).to(self.device), torch.from_numpy(alias).to(self.device))
+        self._check(self.lib.rbpr_bind_item_alias(self.ctx, _ptr(self._alias[0]), _ptr(self._alias[1])))
+
+    def sample_padded(self, seen: torch.Tensor, num_items: int, num: int, seed: int, step: int,
+                      sampler: int = native.SAMPLER_UNIFORM) -> torch.Tensor:
+        """Negatives (B,num) int64 for a 0-padded seen matrix (B,S) int64 on this device."""
+        if seen.dim() != 2:
+            raise ValueError("seen_items must be (batch, width)")
+        seen = seen.to(self.device, torch.int64).contiguous()
+        out = torch.empty((seen.size(0), num), dtype=torch.int64, device=self.device)
+        self._check(self.lib.rbpr_sample_negatives_padded(
+            self.ctx, _ptr(seen), seen.size(0), seen.size(1), num_items, num, seed & (2**64 - 1), step,
+            sampler, _ptr(out), _stream()))
+        return out
+
+    def topk_metrics_dense(self, output: torch.Tensor, target: torch.Tensor, ks: Sequence[int],
+                           linear_gain: bool = False, want_items: bool = False) -> dict[str, torch.Tensor]:
+        """NDCG / Recall / Precision at every cut-off of `ks` from dense (B,I) scores and targets."""
+        output = output.to(self.device, torch.float32).contiguous()
+        target = target.to(self.device, torch.float32).contiguous()
+        n, cols = output.shape
+        ks = [min(int(k), cols) for k in ks]
+        k_max = max(ks)
+        if k_max > native.MAX_TOPK:
+            raise ValueError(f"topk={k_max} exceeds the kernel limit {native.MAX_TOPK}")
+        out = {name: torch.empty((n, len(ks)), dtype=torch.float32, device=self.device)
+               for name in ("ndcg", "recall", "precision")}
+        items = torch.empty((n, k_max), dtype=torch.int32, device=self.device) if want_items else None
+        ks_arr = (C.c_int32 * len(ks))(*ks)
+        self._check(self.lib.rbpr_topk_metrics_dense(
+            self.ctx, _ptr(output), _ptr(target), n, cols, k_max, ks_arr, len(ks), int(linear_gain),
+            _ptr(out["ndcg"]), _ptr(out["recall"]), _ptr(out["precision"]), _ptr(items), _stream()))
+        if want_items:
+            out["items"] = items
+        return out
+
+
+class Engine(Context):
     def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor,
                  item_bias: torch.Tensor | None = None) -> None:
         if not user_emb.is_cuda:
@@ -48,13 +124,7 @@ class Engine:
                 raise ValueError("tables must be contiguous float32")
         if user_emb.size(1) != item_emb.size(1):
             raise ValueError("user and item tables must share the embedding dim")
-        self.lib = native.load()
-        self.device = user_emb.device
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.ctx = C.c_void_p()
-        rc = self.lib.rbpr_create(dev_index, C.byref(self.ctx))
-        if rc != 0:
-            raise native.NativeError(f"rbpr_create failed ({rc}): needs a compute-capability 10.x device")
+        super().__init__(user_emb.device)
         self.user_emb, self.item_emb, self.item_bias = user_emb, item_emb, item_bias
         self.U, self.D = user_emb.shape
         self.I = item_emb.size(0)
@@ -68,19 +138,7 @@ class Engine:
         self.adam_state: dict[str, torch.Tensor] | None = None
         self.indptr = self.indices = None
         self.nnz = 0
-        self._alias = None
         self._pin_stats = self._pin_neg = None
-
-    def __del__(self) -> None:
-        try:
-            if getattr(self, "ctx", None) is not None and self.ctx.value:
-                self.lib.rbpr_destroy(self.ctx)
-                self.ctx = C.c_void_p()
-        except Exception:
-            pass
-
-    def _check(self, rc: int) -> None:
-        native.check(self.lib, self.ctx, rc)
 
     # ---- configuration -------------------------------------------------------------------
     def set_reg(self, reg_alphas: dict | None) -> None:
@@ -123,14 +181,6 @@ class Engine:
         self.indptr, self.indices, self.nnz = indptr, indices, indices.numel()
         self._check(self.lib.rbpr_bind_csr(self.ctx, _ptr(indptr), _ptr(indices), self.U, self.nnz,
                                            _stream()))
-
-    def bind_item_weights(self, weights: torch.Tensor) -> None:
-        """Popularity weights (I,) -> Walker alias table (weights[0] is forced to 0)."""
-        w = weights.detach().double().cpu().numpy().copy()
-        w[0] = 0.0
-        prob, alias = build_alias(w)
-        self._alias = (torch.from_numpy(prob).to(self.device), torch.from_numpy(alias).to(self.device))
-        self._check(self.lib.rbpr_bind_item_alias(self.ctx, _ptr(self._alias[0]), _ptr(self._alias[1])))
 
     # ---- hot path --------------------------------------------------------------------------
     def sample(self, triple_idx: torch.Tensor, seed: int, step: int, sampler: int | None = None) -> torch.Tensor:
@@ -176,8 +226,39 @@ class Engine:
                                                    _ptr(stats), _stream()))
         return stats, neg_out
 
-    def sync_check(self) -> None:
-        self._check(self.lib.rbpr_sync_check(self.ctx, _stream()))
+    # ---- reference-shaped calls (explicit id batches) ---------------------------------------
+    def train_step_triples(self, users: torch.Tensor, items: torch.Tensor, negs: torch.Tensor,
+                           step: int, want_logits: bool = True):
+        """One fused step on explicit (user, positive, negative) ids. Returns (logits (n,2) | None,
+        stats (4,) float64 device tensor)."""
+        dev = self.device
+        users = users.to(dev, torch.int64).contiguous()
+        items = items.to(dev, torch.int64).contiguous()
+        negs = negs.to(dev, torch.int64).contiguous()
+        n = users.numel()
+        if items.numel() != n or negs.numel() != n:
+            raise ValueError("user, item and neg must hold the same number of ids")
+        logits = torch.empty((n, 2), dtype=torch.float32, device=dev) if want_logits else None
+        stats = torch.empty(native.STATS_PER_STEP, dtype=torch.float64, device=dev)
+        self._check(self.lib.rbpr_train_step_triples(self.ctx, _ptr(users), _ptr(items), _ptr(negs), n,
+                                                     step, C.byref(self.hp), _ptr(logits), _ptr(stats),
+                                                     _stream()))
+        return logits, stats
+
+    def pair_logits(self, users: torch.Tensor, items: torch.Tensor, mask: torch.Tensor | None = None,
+                    user_bias: torch.Tensor | None = None) -> torch.Tensor:
+        """logits (B, K) for users (B,) and items (B, K) [+ biases]; mask==0 entries -> -1e13."""
+        dev = self.device
+        users = users.to(dev, torch.int64).contiguous()
+        items = items.to(dev, torch.int64).contiguous()
+        per_user = items.numel() // max(users.numel(), 1)
+        out = torch.empty(items.shape, dtype=torch.float32, device=dev)
+        if mask is not None:
+            mask = mask.to(dev, torch.float32).contiguous()
+        self._check(self.lib.rbpr_pair_logits(self.ctx, _ptr(users), _ptr(items), _ptr(mask),
+                                              users.numel(), per_user, _ptr(user_bias), _ptr(out),
+                                              _stream()))
+        return out
 
     # ---- data-parallel split ---------------------------------------------------------------
     def grad_step(self, triple_idx: torch.Tensor, seed: int, step: int,
@@ -245,9 +326,6 @@ class Engine:
         return out
 
     # ---- instrumentation -------------------------------------------------------------------
-    def launch_count(self) -> int:
-        return int(self.lib.rbpr_launch_count(self.ctx))
-
     def kernel_timing(self, enable: bool) -> None:
         self._check(self.lib.rbpr_kernel_timing(self.ctx, int(enable)))
 

@@ -24,7 +24,9 @@ SYMBOLS = (
     "rbpr_bind_adam_state", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_sample_negatives",
     "rbpr_train_steps", "rbpr_sync_check", "rbpr_train_steps_host", "rbpr_grad_step",
     "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
-    "rbpr_score_dense", "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
+    "rbpr_score_dense", "rbpr_train_step_triples", "rbpr_pair_logits", "rbpr_sample_negatives_padded",
+    "rbpr_topk_metrics_dense",
+    "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
 )
 
 
@@ -78,6 +80,11 @@ def load() -> C.CDLL:
         "rbpr_score_topk": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
                                       vp, vp, vp, vp, vp]),
         "rbpr_score_dense": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "rbpr_train_step_triples": (C.c_int, [vp, vp, vp, vp, i64, u64, hp, vp, vp, vp]),
+        "rbpr_pair_logits": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+        "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),
+        "rbpr_topk_metrics_dense": (C.c_int, [vp, vp, vp, i64, i64, i32, C.POINTER(i32), i32, i32,
+                                              vp, vp, vp, vp, vp]),
         "rbpr_launch_count": (i64, [vp]),
         "rbpr_kernel_timing": (C.c_int, [vp, i32]),
         "rbpr_kernel_time_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]),

@@ -1,0 +1,6 @@
+from revisit_bpr.metrics.metric import MaskedMetric, Metric
+from revisit_bpr.metrics.ndcg import NDCG
+from revisit_bpr.metrics.precision import Precision
+from revisit_bpr.metrics.recall import Recall
+
+__all__ = ["Metric", "MaskedMetric", "NDCG", "Recall", "Precision"]

@@ -1,0 +1,262 @@
+"""`Model` (exported as `revisit_bpr.models.BPR`) and `MF` with the reference's constructor
+signatures, parameter names, output keys and error types (reference:
+revisit_bpr/models/bpr/model.py:13-153), executed by librbpr.so.
+
+What changes underneath, and nothing else:
+
+* train-mode `Model.forward(batch)` runs the WHOLE step — logits, loss, L2, exact minibatch
+  gradients and the optimizer update of the touched rows — in the fused CUDA path
+  (rbpr_train_step_triples).  The returned dict has the reference's keys (`logits_pos`,
+  `logits_neg`, `logits`, `bpr_loss`, `l2_reg`, `loss`); `loss.backward()`, `optimizer.step()` and
+  `optimizer.zero_grad()` stay legal and become no-ops (no `.grad` is ever materialised), so loops
+  written like the reference's example.py:172-180 / experiments/trainer.py:64-83 run unchanged
+  once `model.bind_optimizer(optimizer)` has been called (our Trainer does it).
+* eval-mode `Model.forward(batch)` returns `{"logits": ...}` from the pair-logits kernel.
+* `MF` keeps `nn.Embedding` tables and `nn.Parameter` biases, so `state_dict()`, `parameters()`,
+  `get_features()` and checkpoints are interchangeable with the reference's.
+
+There is no CPU path: calling forward with CPU tensors raises.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+
+from rbpr import native
+from rbpr.engine import Engine
+from revisit_bpr.models.bpr.loss import Loss
+
+
+class BaseLogitModel(torch.nn.Module):
+    def get_features(self) -> dict[str, torch.Tensor]:
+        return {}
+
+
+class MF(BaseLogitModel):
+    """Matrix-factorisation logits: <user row, item row> (+ item bias) (+ user bias)."""
+
+    def __init__(self, user_emb: torch.nn.Embedding, item_emb: torch.nn.Embedding,
+                 item_bias: bool = False, user_bias: bool = False) -> None:
+        super().__init__()
+        if user_emb.embedding_dim != item_emb.embedding_dim:
+            raise ValueError("user and item embeddings must share embedding_dim")
+        self._user_emb = user_emb
+        self._item_emb = item_emb
+        if item_bias:
+            self._item_bias = torch.nn.Parameter(torch.empty(item_emb.num_embeddings))
+        else:
+            self.register_parameter("_item_bias", None)
+        if user_bias:
+            self._user_bias = torch.nn.Parameter(torch.empty(user_emb.num_embeddings))
+        else:
+            self.register_parameter("_user_bias", None)
+        self._engine: Engine | None = None
+        self._engine_key: tuple | None = None
+        self.reset_parameters()
+
+    @torch.no_grad()
+    def reset_parameters(self) -> None:
+        # U(-0.5, 0.5) / dim for both tables, padding row zeroed, biases zero
+        # (reference model.py:117-129; same RNG consumption order: user table first)
+        for emb in (self._user_emb, self._item_emb):
+            emb.weight.uniform_().sub_(0.5).div_(emb.embedding_dim)
+            if emb.padding_idx is not None:
+                emb.weight[emb.padding_idx].zero_()
+        for bias in (self._item_bias, self._user_bias):
+            if bias is not None:
+                bias.zero_()
+
+    def get_features(self) -> dict[str, torch.Tensor]:
+        return {"user": self._user_emb.weight, "item": self._item_emb.weight,
+                "user_bias": self._user_bias, "item_bias": self._item_bias}
+
+    # ---- native context bound to the parameter storages --------------------------------------
+    def engine(self) -> Engine:
+        uw, iw, ib = self._user_emb.weight, self._item_emb.weight, self._item_bias
+        if not uw.is_cuda:
+            raise native.NativeError(
+                "revisit_bpr.models.bpr.MF runs on a B200 only (librbpr.so, sm_100a): move the model "
+                "to CUDA; there is no CPU fallback")
+        for emb in (self._user_emb, self._item_emb):
+            if emb.padding_idx not in (None, 0):
+                raise NotImplementedError("only padding_idx in (None, 0) is supported")
+        key = (uw.data_ptr(), iw.data_ptr(), None if ib is None else ib.data_ptr(), tuple(uw.shape),
+               tuple(iw.shape))
+        if self._engine is None or self._engine_key != key:
+            self._engine = Engine(uw.data, iw.data, None if ib is None else ib.data)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, user: torch.Tensor, item: torch.Tensor, _: dict[str, torch.Tensor] | None = None,
+                mask: torch.Tensor | None = None) -> torch.Tensor:
+        # user (B,), item (B, ...) -> logits (B, ...)
+        if user.dim() != 1 or item.size(0) != user.size(0):
+            raise IndexError(f"user must be (batch,), item (batch, ...): got {tuple(user.shape)}, {tuple(item.shape)}")
+        eng = self.engine()
+        ub = None if self._user_bias is None else self._user_bias.data
+        return eng.pair_logits(user, item, mask, ub)
+
+
+class _AppliedStep(torch.autograd.Function):
+    """Gives the already-applied loss a grad_fn so that `loss.backward()` stays legal."""
+
+    @staticmethod
+    def forward(ctx: Any, anchor: torch.Tensor, value: torch.Tensor) -> torch.Tensor:  # noqa: ARG004
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx: Any, grad: torch.Tensor):  # noqa: ARG004
+        return None, None
+
+
+class Model(torch.nn.Module):
+    """The BPR model: `Model(logits_model, reg_alphas=None, fuse_forward=False)`.
+
+    reg_alphas keys: user, item, neg, all (`all` overrides; `neg` defaults to `item`) — reference
+    model.py:70-86.  `fuse_forward` is accepted for signature compatibility: the CUDA path always
+    evaluates both logits of a triple in one pass.
+    """
+
+    def __init__(self, logits_model: BaseLogitModel, reg_alphas: dict[str, float] | None = None,
+                 fuse_forward: bool = False) -> None:
+        super().__init__()
+        self.logits_model = logits_model
+        self._reg_alphas = reg_alphas or {}
+        self._fuse_forward = fuse_forward
+        self._loss = Loss(size_average=False)
+        self._optimizer: torch.optim.Optimizer | None = None
+        self._opt_kind: int | None = None
+        self._opt_step = 0
+        self._adam_last: torch.Tensor | None = None
+        self._anchor = torch.zeros((), requires_grad=True)
+
+    # ---- optimizer binding ---------------------------------------------------------------------
+    def bind_optimizer(self, optimizer: torch.optim.Optimizer) -> None:
+        """Tell the fused step which torch optimizer it stands in for (hyper-parameters are read
+        from its param_groups at every step, so LR schedulers keep working; Adam moments live in
+        `optimizer.state`, so `optimizer.state_dict()` stays meaningful)."""
+        opt = getattr(optimizer, "optimizer", optimizer)  # accelerate's AcceleratedOptimizer wrapper
+        if len(opt.param_groups) != 1:
+            raise NotImplementedError("the fused BPR step supports a single param group")
+        g = opt.param_groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("maximize", False):
+            raise NotImplementedError("weight_decay / maximize are not supported by the fused BPR step")
+        if isinstance(opt, torch.optim.SGD):
+            if g.get("momentum", 0) != 0 or g.get("dampening", 0) != 0 or g.get("nesterov", False):
+                raise NotImplementedError("SGD momentum is not implemented in the fused BPR step yet")
+            self._opt_kind = native.OPT_SGD
+        elif isinstance(opt, torch.optim.Adam) and not isinstance(opt, torch.optim.AdamW):
+            if g.get("amsgrad", False):
+                raise NotImplementedError("amsgrad is not supported by the fused BPR step")
+            self._opt_kind = native.OPT_ADAM
+        else:
+            raise NotImplementedError(f"{type(opt).__name__} is not implemented in the fused BPR step "
+                                      "(supported: torch.optim.SGD without momentum, torch.optim.Adam)")
+        self._optimizer = opt
+        self._adam_last = None
+        steps = [int(s["step"]) for s in opt.state.values() if "step" in s]
+        self._opt_step = max(steps) if steps else 0
+        if hasattr(opt, "register_state_dict_pre_hook"):
+            opt.register_state_dict_pre_hook(lambda _opt: self.flush())
+
+    def _adam_state(self, eng: Engine) -> dict[str, torch.Tensor]:
+        opt = self._optimizer
+        feats = self.logits_model.get_features()
+
+        def moments(p: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+            st = opt.state[p]
+            if "exp_avg" not in st:
+                st["step"] = torch.tensor(float(self._opt_step))
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            return st["exp_avg"], st["exp_avg_sq"]
+
+        um, uv = moments(feats["user"])
+        im, iv = moments(feats["item"])
+        state = {"user_m": um, "user_v": uv, "item_m": im, "item_v": iv}
+        if feats["item_bias"] is not None:
+            state["bias_m"], state["bias_v"] = moments(feats["item_bias"])
+        if self._adam_last is None or self._adam_last.device != eng.device:
+            # every row is consistent with `_opt_step` dense steps when binding (fresh or resumed)
+            self._adam_last = torch.full((eng.U,), self._opt_step, dtype=torch.int32, device=eng.device)
+        state["user_last"] = self._adam_last
+        return state
+
+    def _configure(self, eng: Engine) -> None:
+        if self._optimizer is None:
+            raise RuntimeError(
+                "train-mode forward of the CUDA BPR model applies the optimizer update inside the fused "
+                "kernel: call model.bind_optimizer(optimizer) once after creating the optimizer "
+                "(experiments.trainer.Trainer does this for you)")
+        g = self._optimizer.param_groups[0]
+        eng.set_reg(self._reg_alphas)
+        if self._opt_kind == native.OPT_SGD:
+            eng.set_sgd(float(g["lr"]))
+        else:
+            eng.set_adam(float(g["lr"]), tuple(g["betas"]), float(g["eps"]), state=self._adam_state(eng))
+
+    @torch.no_grad()
+    def flush(self) -> None:
+        """Materialise lazily-deferred optimizer work (dense-Adam catch-up of user rows) and mirror
+        the step counter into `optimizer.state`.  Called before eval, state_dict and checkpoints."""
+        lm = self.logits_model
+        if self._optimizer is None or self._opt_kind != native.OPT_ADAM or not isinstance(lm, MF):
+            return
+        if lm._engine is None or self._adam_last is None:
+            return
+        eng = lm.engine()
+        self._configure(eng)
+        eng.flush_lazy(self._opt_step)
+        for st in self._optimizer.state.values():
+            if "step" in st:
+                st["step"].fill_(float(self._opt_step))
+
+    def state_dict(self, *args: Any, **kwargs: Any):  # noqa: ANN201
+        self.flush()
+        return super().state_dict(*args, **kwargs)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        lm = self.logits_model
+        if not isinstance(lm, MF):
+            raise NotImplementedError("the CUDA BPR path implements the MF logits model only")
+        if not self.training:
+            self.flush()
+            return {"logits": lm(inputs["user"], inputs["item"], inputs, mask=inputs.get("mask"))}
+        user, item, neg = inputs["user"], inputs["item"], inputs["neg"]
+        if item.dim() < 2:
+            item = item.unsqueeze(-1)
+        if neg.dim() < 2:
+            neg = neg.unsqueeze(-1)
+        if item.size(-1) != 1 or neg.size(-1) != 1:
+            raise NotImplementedError("the fused BPR step takes one positive and one negative per row")
+        if not (user.size(0) == item.size(0) == neg.size(0)):
+            raise IndexError("user, item and neg must share the batch dimension")
+        eng = lm.engine()
+        self._configure(eng)
+        logits, stats = eng.train_step_triples(user, item.reshape(-1), neg.reshape(-1), self._opt_step)
+        self._opt_step += 1
+        stats32 = stats.to(torch.float32)
+        pos, ng = logits[:, 0:1], logits[:, 1:2]
+        if self._anchor.device != stats32.device:
+            self._anchor = torch.zeros((), requires_grad=True, device=stats32.device)
+        bpr_loss, l2_reg = stats32[0], stats32[1]
+        return {"logits_pos": pos, "logits_neg": ng, "logits": pos - ng, "bpr_loss": bpr_loss,
+                "l2_reg": l2_reg, "loss": _AppliedStep.apply(self._anchor, bpr_loss + l2_reg)}
+
+    @torch.no_grad()
+    def regularization(self, inputs: dict[str, torch.Tensor]) -> torch.Tensor:
+        """Per-row L2 term (B,) of the reference (model.py:70-93) for callers that want it on its
+        own; the training path computes it inside the fused kernel."""
+        from rbpr.engine import resolve_reg
+        feats = self.logits_model.get_features()
+        if not feats or all(self._reg_alphas.get(k) is None for k in ("all", "user", "item", "neg")):
+            return torch.tensor(0)
+        ru, ri, rn = resolve_reg(self._reg_alphas)
+        term = (ri * feats["item"][inputs["item"]].pow(2).flatten(1).sum(1)
+                + rn * feats["item"][inputs["neg"]].pow(2).flatten(1).sum(1))
+        if feats.get("user") is not None:
+            term = term + ru * feats["user"][inputs["user"]].pow(2).flatten(1).sum(1)
+        return term / 2
