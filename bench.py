@@ -20,8 +20,6 @@ import threading
 import time
 from pathlib import Path
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # no lazy cubin loads inside the timed region
-
 import numpy as np
 import torch
 
@@ -39,12 +37,13 @@ SEED = 13
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="ml-20m")
     ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--batch", type=int, default=262144,
+                    help="triples per step and per GPU (train_batch_size is a free jinja variable of the reference configs)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic matrix (tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period-ms", type=float, default=5.0, help="NVML sampling period (0 = off)")
@@ -221,14 +220,6 @@ def run_reference(args) -> None:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def shard_users(inter, world: int, rank: int):
-    """Contiguous user blocks balanced by interaction count; returns the triple-id range owned."""
-    cuts = np.searchsorted(inter.indptr, np.linspace(0, inter.nnz, world + 1), side="left")
-    cuts[0], cuts[-1] = 0, inter.num_users
-    lo, hi = int(inter.indptr[cuts[rank]]), int(inter.indptr[cuts[rank + 1]])
-    return lo, hi
-
-
 def run_ours(args) -> None:
     import torch.distributed as dist
     from rbpr import native
@@ -256,7 +247,8 @@ def run_ours(args) -> None:
     eng.set_sgd(LR)
     eng.set_sampler(native.SAMPLER_UNIFORM)
 
-    lo, hi = shard_users(inter, world, rank)
+    from rbpr.parallel import DataParallelTrainer, owned_triples
+    lo, hi = owned_triples(inter.indptr, world, rank)
     n_local = hi - lo
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     need = (W + K) * B
@@ -271,19 +263,14 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    grad = eng.item_grad_tensor() if world > 1 else None
+    if world > 1:  # the library joins its own NCCL communicator and runs the exchange itself
+        eng.init_comm()
+    del DataParallelTrainer
 
     def run_steps(t_dev: torch.Tensor, step0: int):
-        """Device-resident steps. N=1: one library call; N>1: per-step grad / all-reduce / apply."""
-        if world == 1:
-            return eng.train_steps(t_dev, B, SEED, step0)[0]
-        out = []
-        for s in range(t_dev.numel() // B):
-            st, _ = eng.grad_step(t_dev[s * B:(s + 1) * B], SEED, step0 + s)
-            dist.all_reduce(grad)
-            eng.apply_item_grads(step0 + s)
-            out.append(st)
-        return torch.cat(out)
+        """Device-resident steps in ONE library call; with N>1 every step all-reduces the dense
+        item gradient once (NCCL, inside the library) before the replicated item update."""
+        return eng.train_steps(t_dev, B, SEED, step0)[0]
 
     # ---- warm-up (the clock sampler starts first: nvidia-smi's start-up must not overlap the timed region) ----
     clocks = ClockSampler(local, args.clock_period_ms) if rank == 0 else None
@@ -296,6 +283,7 @@ def run_ours(args) -> None:
     eng.kernel_timing(True)
     eng.kernel_time_ms()
     l0 = eng.launch_count()
+    c0 = eng.collective_count()
     mark = clocks.mark() if clocks else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -305,6 +293,7 @@ def run_ours(args) -> None:
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    collectives = eng.collective_count() - c0
     k_ms, k_n = eng.kernel_time_ms()
     eng.kernel_timing(False)
     eng.sync_check()
@@ -315,23 +304,16 @@ def run_ours(args) -> None:
     loss_last = stats[-1, 0].item() / max(stats[-1, 3].item(), 1.0)
 
     # ---- timed: end to end with host buffers (H2D of the step's triple ids, D2H of its stats) ----
-    spc = max(1, min(args.e2e_steps_per_call, K)) if world == 1 else 1
-    if world == 1:  # untimed: first use of the host-buffer entry point (staging + pinned result buffers)
-        eng.train_steps_host(perm_host[:spc * B], B, SEED, W + K)
+    spc = max(1, min(args.e2e_steps_per_call, K))
+    # untimed: first use of the host-buffer entry point (staging + pinned result buffers)
+    eng.train_steps_host(perm_host[:spc * B], B, SEED, W + K)
     barrier()
     t0 = time.perf_counter()
     e2e_loss = 0.0
     for s in range(0, K, spc):
         th = perm_host[(W + s) * B:(W + min(s + spc, K)) * B]
-        if world == 1:
-            st, _ = eng.train_steps_host(th, B, SEED, W + K + spc + s)
-            e2e_loss = st[-1, 0].item()
-        else:
-            td = th.to(dev, non_blocking=True)
-            st, _ = eng.grad_step(td, SEED, W + K + s)
-            dist.all_reduce(grad)
-            eng.apply_item_grads(W + K + s)
-            e2e_loss = st.cpu()[0, 0].item()
+        st, _ = eng.train_steps_host(th, B, SEED, W + K + spc + s)
+        e2e_loss = st[-1, 0].item()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -369,9 +351,8 @@ def run_ours(args) -> None:
                          "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
             "e2e": {"value": K * B * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": 4 * 8, "ms_per_step": 1e3 * e2e_s / K,
-                    "api": f"rbpr_train_steps_host (C ABI, pinned host buffers), {spc} steps per call" if world == 1 else
-                           "Engine.grad_step + all_reduce + apply_item_grads, pinned host batch"},
-            "gpu_launches": launches, "clocks": clk,
+                    "api": f"rbpr_train_steps_host (C ABI, pinned host buffers), {spc} steps per call"},
+            "gpu_launches": launches, "nccl_allreduces": collectives, "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
             r = cpu_reference_run(inter, D, 256, args.cpu_steps, 2)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 1
+#define RBPR_ABI_VERSION 2
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -37,7 +37,8 @@ typedef enum {
   RBPR_ERR_ARG = -1,   /* bad argument / shape mismatch / not bound */
   RBPR_ERR_CUDA = -2,  /* CUDA runtime error */
   RBPR_ERR_STATE = -3, /* call order violated */
-  RBPR_ERR_DATA = -4   /* invalid data (e.g. a user who has seen every item) */
+  RBPR_ERR_DATA = -4,  /* invalid data (e.g. a user who has seen every item) */
+  RBPR_ERR_COMM = -5   /* NCCL error / libnccl not loadable */
 } rbpr_status;
 
 typedef enum { RBPR_OPT_SGD = 0, RBPR_OPT_ADAM = 1 } rbpr_optimizer;
@@ -45,7 +46,9 @@ typedef enum { RBPR_OPT_SGD = 0, RBPR_OPT_ADAM = 1 } rbpr_optimizer;
 typedef enum {
   RBPR_SAMPLER_UNIFORM = 0,  /* uniform over {1..I-1} \ seen(u)                */
   RBPR_SAMPLER_WEIGHTED = 1, /* ∝ item_weight over {1..I-1} \ seen(u) (alias)  */
-  RBPR_SAMPLER_INJECTED = 2  /* negatives supplied by the caller (neg_in)      */
+  RBPR_SAMPLER_INJECTED = 2, /* negatives supplied by the caller (neg_in)      */
+  RBPR_SAMPLER_ADAPTIVE = 3  /* factor/rank adaptive (needs the current user rows: sampled
+                                step by step, never ahead of the model)        */
 } rbpr_sampler;
 
 /* Hyper-parameters of one training call.
@@ -59,7 +62,9 @@ typedef struct {
   float lr;
   float beta1, beta2, eps; /* Adam */
   float reg_user, reg_item, reg_neg;
-  float reserved0;
+  float adaptive_prob;    /* Geometric success probability (AdaptiveSampler sampling_prob)      */
+  int32_t adaptive_every; /* refresh the item snapshot after every N-th sampled step (0: never) */
+  int32_t reserved0;
 } rbpr_hparams;
 
 /* Per-step statistics written by the training entry points (doubles). */
@@ -104,6 +109,25 @@ int rbpr_bind_csr(rbpr_ctx* ctx, const int64_t* indptr, const int32_t* indices, 
  * (experiments/bpr/exp.py:85-91,282-293: weights = count^alpha).  prob (I,) float in [0,1],
  * alias (I,) int32; entry 0 (padding) must have prob 0 and a non-zero alias. Device ptrs. */
 int rbpr_bind_item_alias(rbpr_ctx* ctx, const float* prob, const int32_t* alias);
+
+/* Adaptive sampler state (owned by the context): snapshot the item table, per-factor unbiased std
+ * over items 1..I-1, every factor column sorted once (descending, ties by item id) + inverse.
+ * Replaces AdaptiveSampler.update_stats (revisit_bpr/modules/neg_samplers.py:126-132) and
+ * BPRExperiment._update_adaptive_stats (experiments/bpr/exp.py:344-354). */
+int rbpr_adaptive_update_stats(rbpr_ctx* ctx, void* stream);
+/* Borrow the state for inspection (device pointers: std (D), order (D,I), pos (D,I)). */
+int rbpr_adaptive_stats(rbpr_ctx* ctx, const float** factor_std, const int32_t** order,
+                        const int32_t** pos);
+
+/* Adaptive negatives for a batch in the reference's layout: users (batch,) int64, seen
+ * (batch,width) int64 0-padded; neg_out (batch,num) int64.  factor ~ |u_f|*std_f of the CURRENT
+ * user row, rank ~ Geometric(sampling_prob) clamped to the number of unseen items, item = that
+ * rank among the user's unseen items in the snapshot's factor order (top if u_f > 0 else bottom).
+ * Replaces AdaptiveSampler.sample (neg_samplers.py:74-124) / _adaptive_sampling (exp.py:295-342):
+ * no (B,I) scatter, no per-row argsort over I.  Counter-based draw of DESIGN.md §3.3. */
+int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64_t* seen,
+                                int64_t batch, int64_t width, int64_t num, double sampling_prob,
+                                uint64_t seed, uint64_t step, int64_t* neg_out, void* stream);
 
 /* Negative sampler alone: for each triple id t = triple_idx[k] draw
  * neg_out[k] = f(seed, step, t, CSR) — the counter-based specification in DESIGN.md §3
@@ -188,6 +212,20 @@ int rbpr_pair_logits(rbpr_ctx* ctx, const int64_t* users, const int64_t* items, 
 int rbpr_sample_negatives_padded(rbpr_ctx* ctx, const int64_t* seen, int64_t batch, int64_t width,
                                  int64_t num_items, int64_t num, uint64_t seed, uint64_t step,
                                  int32_t sampler, int64_t* neg_out, void* stream);
+
+/* Data-parallel communicator, one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id and
+ * hands it to the other ranks through any host channel (the shipped host code broadcasts it with
+ * torch.distributed); every rank then joins.  Once a communicator with world > 1 exists,
+ * rbpr_train_steps runs the data-parallel step by itself: phase A on the rank's own triples (users
+ * sharded by owner), ONE ncclAllReduce(sum, fp32) of the dense item-gradient buffer on the
+ * caller's stream, then the dense item update, identical on every rank — preparation waves still
+ * overlap.  Replaces mp.spawn + init_process_group("nccl") + DDP (experiments/launcher.py:35-73,
+ * experiments/bpr/exp.py:102, experiments/trainer.py:76). */
+int rbpr_comm_unique_id(rbpr_ctx* ctx, void* out128);
+int rbpr_comm_init(rbpr_ctx* ctx, int32_t world, int32_t rank, const void* id128);
+/* The all-reduce alone, for callers driving rbpr_grad_step / rbpr_apply_item_grads themselves. */
+int rbpr_comm_allreduce_item_grads(rbpr_ctx* ctx, void* stream);
+int64_t rbpr_collective_count(const rbpr_ctx* ctx);
 
 /* Bring every lazily-updated user row up to `step` optimizer steps (dense-Adam semantics
  * of torch.optim.Adam: rows with zero gradient still move).  Call before reading the user

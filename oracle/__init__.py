@@ -15,6 +15,8 @@ it is only a type annotation) and committed as tests/golden/*.npz.
   oracle.ref_bpr  torch-CPU restatement of the reference op sequence: MF logits, BPR loss, L2,
                   autograd backward, dense torch.optim step, multinomial samplers, all-item
                   eval + seen masking + NDCG/Recall   [pinned against the reference]
-  oracle.closed   numpy closed-form gradients of one minibatch (second, independent check)
-  oracle/csrc     plain-C restatement of the sampler + SGD step (fast checker for full sizes)
+  oracle.adaptive numpy restatement of the adaptive sampler; its deterministic part restates the
+                  reference's formula and is pinned by tests/golden/adaptive.npz
+  oracle.closed   numpy closed-form minibatch SGD step (independent of autograd; vectorised, so it
+                  also checks BASELINE-size steps in seconds)
 """

@@ -1,0 +1,340 @@
+// Adaptive (factor / rank) negative sampling for sm_100a — DESIGN.md §3.3.
+// Reference: AdaptiveSampler.sample / update_stats (revisit_bpr/modules/neg_samplers.py:74-132),
+// BPRExperiment._adaptive_sampling / _update_adaptive_stats (experiments/bpr/exp.py:295-354).
+//
+//   adaptive_update_stats : snapshot the item table transposed (D,I), unbiased per-factor std over
+//                           items 1..I-1, sort every factor column once (descending value, ties by
+//                           ascending item id) -> order[f][q], and its inverse pos[f][item].
+//   sample_adaptive       : per slot: factor ~ Categorical(|u_f| * std_f), rank ~ Geometric(p)
+//                           clamped to the number of unseen items, item = rank-th unseen item in
+//                           the factor's order (from the top if u_f > 0, else from the bottom).
+//                           The rank-th UNSEEN position is the fixed point of
+//                           q <- r + #{masked positions <= q} (masked = seen items and item 0).
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include "train_kernels.cuh"
+
+using namespace rbpr_dev;
+
+namespace {
+
+// snapshot[f][i] = item_emb[i][f]; ids[f][i] = i   (tile transpose through shared memory)
+__global__ void snapshot_transpose(const float* __restrict__ item_emb, int64_t I, int D,
+                                   float* __restrict__ snap, int32_t* __restrict__ ids) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int f0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r;
+    const int f = f0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < I && f < D) ? item_emb[i * D + f] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int f = f0 + r;
+    const int64_t i = i0 + threadIdx.x;
+    if (f < D && i < I) {
+      snap[(int64_t)f * I + i] = tile[threadIdx.x][r];
+      ids[(int64_t)f * I + i] = (int32_t)i;
+    }
+  }
+}
+
+// unbiased std of snapshot[f][1..I-1], one block per factor, two passes in double
+__global__ void factor_std(const float* __restrict__ snap, int64_t I, float* __restrict__ out) {
+  __shared__ double red[256];
+  __shared__ double s_mean;
+  const float* row = snap + (int64_t)blockIdx.x * I;
+  const int64_t n = I - 1;
+  double acc = 0.0;
+  for (int64_t i = 1 + threadIdx.x; i < I; i += blockDim.x) acc += (double)row[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_mean = red[0] / (double)n;
+  __syncthreads();
+  const double mean = s_mean;
+  acc = 0.0;
+  for (int64_t i = 1 + threadIdx.x; i < I; i += blockDim.x) {
+    const double d = (double)row[i] - mean;
+    acc += d * d;
+  }
+  __syncthreads();
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)sqrt(red[0] / (double)(n - 1));
+}
+
+__global__ void invert_order(const int32_t* __restrict__ order, int64_t I, int D,
+                             int32_t* __restrict__ pos) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= I * D) return;
+  const int64_t f = k / I, q = k % I;
+  pos[f * I + order[k]] = (int32_t)q;
+}
+
+struct AdaptiveParams {
+  const float* __restrict__ user_emb;
+  const float* __restrict__ fstd;      // (D)
+  const int32_t* __restrict__ order;   // (D,I)
+  const int32_t* __restrict__ pos;     // (D,I)
+  int64_t I;
+  int D;
+  double log1m_p;  // log1p(-p)
+  uint32_t seed_lo, seed_hi;
+  uint64_t step;
+  int32_t* __restrict__ flag;
+};
+
+// One group of 8 lanes per slot.  `masked(c)` enumerates the masked items of the slot's user:
+// c in [0, n_mask) -> item id (0 = padding entries are ignored; item 0 itself is always masked).
+template <typename RowFn>
+__device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const Group<8>& g,
+                                                 int64_t user, uint32_t sub_lo, uint32_t sub_hi,
+                                                 int64_t n_entries, RowFn entry) {
+  const int D = p.D;
+  const float* urow = p.user_emb + user * D;
+  // number of unseen, non-padding items
+  int64_t n_seen = 0;
+  for (int64_t c = g.gl; c < n_entries; c += 8) n_seen += (entry(c) != 0);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) n_seen += __shfl_xor_sync(g.mask, n_seen, o);
+  const int64_t n_unseen = (p.I - 1) - n_seen;
+  if (n_unseen <= 0) {
+    if (g.gl == 0) atomicExch(p.flag, 4);
+    return 1;
+  }
+  const uint32_t step_lo = (uint32_t)(p.step << 8), step_hi = (uint32_t)(p.step >> 24);
+  const philox4 r4 = philox4x32_10(step_lo, step_hi, sub_lo, sub_hi, p.seed_lo, p.seed_hi);
+  // factor ~ Categorical(|u_f| * std_f): sequential fp32 inverse CDF (every lane, same order)
+  float total = 0.f;
+  for (int f = 0; f < D; ++f) total = __fadd_rn(total, __fmul_rn(fabsf(urow[f]), p.fstd[f]));
+  if (!(total > 0.f)) {
+    if (g.gl == 0) atomicExch(p.flag, 10);
+    return 1;
+  }
+  const float target = __fmul_rn((float)(r4.x >> 8) * (1.0f / 16777216.0f), total);
+  int factor = -1, last_pos = 0;
+  float cum = 0.f;
+  for (int f = 0; f < D; ++f) {
+    const float w = __fmul_rn(fabsf(urow[f]), p.fstd[f]);
+    cum = __fadd_rn(cum, w);
+    if (w > 0.f) last_pos = f;
+    if (factor < 0 && cum > target) factor = f;
+  }
+  if (factor < 0) factor = last_pos;
+  // rank ~ Geometric(p) on {1,2,...}, clamped to the number of unseen items
+  const double u2 = ((double)(r4.y >> 8) + 1.0) * (1.0 / 16777216.0);
+  double gq = ceil(log(u2) / p.log1m_p);
+  if (!(gq >= 1.0)) gq = 1.0;
+  const int64_t rank = gq > (double)n_unseen ? n_unseen : (int64_t)gq;
+  const int64_t r = (urow[factor] > 0.f) ? rank - 1 : n_unseen - rank;
+  // r-th unmasked position of the factor's order: fixed point of q <- r + #{masked pos <= q}
+  const int32_t* prow = p.pos + (int64_t)factor * p.I;
+  const int32_t pos0 = prow[0];
+  int64_t q = r;
+  while (true) {
+    int64_t c = 0;
+    for (int64_t e = g.gl; e < n_entries; e += 8) {
+      const int64_t it = entry(e);
+      c += (it != 0 && (int64_t)prow[it] <= q);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
+    c += (pos0 <= q);
+    const int64_t nq = r + c;
+    if (nq == q) break;
+    q = nq;
+  }
+  return p.order[(int64_t)factor * p.I + q];
+}
+
+__global__ void __launch_bounds__(256)
+sample_adaptive_padded(const AdaptiveParams p, const int64_t* __restrict__ users,
+                       const int64_t* __restrict__ seen, int64_t B, int64_t S, int64_t num,
+                       int64_t U, int64_t* __restrict__ out) {
+  const Group<8> g;
+  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  if (slot >= B * num) return;
+  const int64_t row = slot / num;
+  int64_t user = users[row];
+  if (user < 0 || user >= U) {
+    if (g.gl == 0) atomicExch(p.flag, 7);
+    user = 0;
+  }
+  const int64_t* srow = seen + row * S;
+  const int64_t I = p.I;
+  auto entry = [&](int64_t c) -> int64_t {
+    const int64_t v = srow[c];
+    return (v > 0 && v < I) ? v : 0;
+  };
+  const int32_t j = adaptive_draw(p, g, user, (uint32_t)slot, (uint32_t)((uint64_t)slot >> 32), S, entry);
+  if (g.gl == 0) out[slot] = (int64_t)j;
+}
+
+}  // namespace
+
+// CSR variant used by bpr_sample-style preparation (train.cu): records for one step (tp.batch >= n).
+__global__ void __launch_bounds__(256)
+rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t* order,
+                         const int32_t* pos, double log1m_p, int4* __restrict__ records,
+                         uint64_t n_slots, uint64_t step) {
+  const Group<8> g;
+  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  if (k >= n_slots) return;
+  int64_t t64 = __ldg(tp.triple_idx + k);
+  if (t64 < 0 || t64 >= tp.nnz) t64 = 0;  // flagged by count_users
+  const uint32_t t = (uint32_t)t64;
+  const int32_t uu = __ldg(tp.coo_user + t);
+  const int32_t i = __ldg(tp.indices + t);
+  const int32_t flags = slot_flags(tp, k, uu);
+  AdaptiveParams p;
+  p.user_emb = tp.user_emb;
+  p.fstd = fstd;
+  p.order = order;
+  p.pos = pos;
+  p.I = tp.I;
+  p.D = tp.D;
+  p.log1m_p = log1m_p;
+  p.seed_lo = tp.seed_lo;
+  p.seed_hi = tp.seed_hi;
+  p.step = step;
+  p.flag = tp.flag;
+  const int64_t lo = tp.indptr[uu], hi = tp.indptr[uu + 1];
+  const int32_t* idx = tp.indices;
+  auto entry = [&](int64_t c) -> int64_t { return (int64_t)__ldg(idx + lo + c); };
+  const int32_t j = adaptive_draw(p, g, (int64_t)uu, t, 0u, hi - lo, entry);
+  if (g.gl == 0) {
+    records[k] = make_int4(uu, i, j, flags);
+    if (tp.neg_out != nullptr) tp.neg_out[k] = (int64_t)j;
+  }
+}
+
+int rbpr_internal_adaptive_ready(rbpr_ctx* ctx);
+
+// Records of ONE step from sorted keys, negatives drawn adaptively from the current user rows.
+int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void* records, int64_t n,
+                                      uint64_t step, double sampling_prob, cudaStream_t st) {
+  int rc = rbpr_internal_adaptive_ready(ctx);
+  if (rc) return rc;
+  if (!(sampling_prob > 0.0 && sampling_prob < 1.0))
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "adaptive sampler: adaptive_prob must be in (0,1)");
+  const int64_t threads = n * 8;
+  rbpr_sample_adaptive_csr<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+      tp, ctx->ad_std, ctx->ad_order, ctx->ad_pos, log1p(-sampling_prob),
+      reinterpret_cast<int4*>(records), (uint64_t)n, step);
+  ctx->launches++;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int rbpr_internal_adaptive_ready(rbpr_ctx* ctx) {
+  if (!ctx->ad_order || !ctx->ad_pos || !ctx->ad_std)
+    RBPR_FAIL(ctx, RBPR_ERR_STATE, "adaptive sampler: call rbpr_adaptive_update_stats first");
+  return 0;
+}
+
+extern "C" {
+
+int rbpr_adaptive_update_stats(rbpr_ctx* ctx, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t I = ctx->I;
+  const int D = ctx->D;
+  const size_t cells = (size_t)I * D;
+  if (ctx->ad_cells != cells) {
+    cudaFree(ctx->ad_snap); cudaFree(ctx->ad_snap_sorted); cudaFree(ctx->ad_ids);
+    cudaFree(ctx->ad_order); cudaFree(ctx->ad_pos); cudaFree(ctx->ad_std); cudaFree(ctx->ad_offsets);
+    cudaFree(ctx->ad_tmp);
+    ctx->ad_snap = ctx->ad_snap_sorted = ctx->ad_std = nullptr;
+    ctx->ad_ids = ctx->ad_order = ctx->ad_pos = nullptr;
+    ctx->ad_offsets = nullptr;
+    ctx->ad_tmp = nullptr;
+    ctx->ad_tmp_bytes = 0;
+    ctx->ad_cells = 0;
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_snap, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_snap_sorted, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_ids, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_order, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_pos, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_std, (size_t)D * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_offsets, (size_t)(D + 1) * 8));
+    std::vector<int64_t> off(D + 1);
+    for (int f = 0; f <= D; ++f) off[f] = (int64_t)f * I;
+    RBPR_CUDA(ctx, cudaMemcpy(ctx->ad_offsets, off.data(), (size_t)(D + 1) * 8, cudaMemcpyHostToDevice));
+    size_t need = 0;
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(
+        nullptr, need, ctx->ad_snap, ctx->ad_snap_sorted, ctx->ad_ids, ctx->ad_order, (int64_t)cells, D,
+        ctx->ad_offsets, ctx->ad_offsets + 1, 0, 32, st);
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_tmp, need > 0 ? need : 16));
+    ctx->ad_tmp_bytes = need;
+    ctx->ad_cells = cells;
+  }
+  dim3 grid((unsigned)((I + 31) / 32), (unsigned)((D + 31) / 32));
+  snapshot_transpose<<<grid, dim3(32, 8), 0, st>>>(ctx->item_emb, I, D, ctx->ad_snap, ctx->ad_ids);
+  factor_std<<<D, 256, 0, st>>>(ctx->ad_snap, I, ctx->ad_std);
+  size_t tb = ctx->ad_tmp_bytes;
+  RBPR_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairsDescending(
+                     ctx->ad_tmp, tb, ctx->ad_snap, ctx->ad_snap_sorted, ctx->ad_ids, ctx->ad_order,
+                     (int64_t)cells, D, ctx->ad_offsets, ctx->ad_offsets + 1, 0, 32, st));
+  invert_order<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ctx->ad_order, I, D, ctx->ad_pos);
+  ctx->launches += 4;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int rbpr_adaptive_stats(rbpr_ctx* ctx, const float** factor_std_out, const int32_t** order_out,
+                        const int32_t** pos_out) {
+  if (!ctx) return RBPR_ERR_ARG;
+  int rc = rbpr_internal_adaptive_ready(ctx);
+  if (rc) return rc;
+  if (factor_std_out) *factor_std_out = ctx->ad_std;
+  if (order_out) *order_out = ctx->ad_order;
+  if (pos_out) *pos_out = ctx->ad_pos;
+  return 0;
+}
+
+int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64_t* seen,
+                                int64_t batch, int64_t width, int64_t num, double sampling_prob,
+                                uint64_t seed, uint64_t step, int64_t* neg_out, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!ctx->user_emb || !ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
+  int rc = rbpr_internal_adaptive_ready(ctx);
+  if (rc) return rc;
+  if (batch < 0 || width < 0 || num < 1) RBPR_FAIL(ctx, RBPR_ERR_ARG, "sample_adaptive: bad sizes");
+  if (!(sampling_prob > 0.0 && sampling_prob < 1.0))
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "sample_adaptive: sampling_prob must be in (0,1)");
+  if (batch == 0) return 0;
+  if (!users || (width > 0 && !seen) || !neg_out)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "sample_adaptive: null pointer");
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  AdaptiveParams p;
+  p.user_emb = ctx->user_emb;
+  p.fstd = ctx->ad_std;
+  p.order = ctx->ad_order;
+  p.pos = ctx->ad_pos;
+  p.I = ctx->I;
+  p.D = ctx->D;
+  p.log1m_p = log1p(-sampling_prob);
+  p.seed_lo = (uint32_t)seed;
+  p.seed_hi = (uint32_t)(seed >> 32);
+  p.step = step;
+  p.flag = ctx->flag;
+  const int64_t threads = batch * num * 8;
+  sample_adaptive_padded<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p, users, seen, batch, width, num, ctx->U, neg_out);
+  ctx->launches++;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

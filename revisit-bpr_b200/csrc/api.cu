@@ -1,6 +1,8 @@
 // Context management and table binding for librbpr.so (C ABI in include/rbpr.h).
 #include "common.cuh"
 
+void rbpr_internal_comm_destroy(rbpr_ctx* ctx);  // comm.cu
+
 extern "C" {
 
 int rbpr_abi_version(void) { return RBPR_ABI_VERSION; }
@@ -40,15 +42,13 @@ int rbpr_create(int device, rbpr_ctx** out) {
 void rbpr_destroy(rbpr_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  rbpr_internal_comm_destroy(ctx);
   cudaFree(ctx->coo_user);
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
-  cudaFree(ctx->keys_in);
-  cudaFree(ctx->keys_out);
-  cudaFree(ctx->pos_in);
-  cudaFree(ctx->pos_out);
-  cudaFree(ctx->cub_tmp);
+  cudaFree(ctx->ord);
+  cudaFree(ctx->cnt);
   cudaFree(ctx->stats);
   for (int b = 0; b < 2; ++b) {
     cudaFree(ctx->partials[b]);
@@ -62,6 +62,14 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);
   cudaFree(ctx->score_buf);
+  cudaFree(ctx->ad_snap);
+  cudaFree(ctx->ad_snap_sorted);
+  cudaFree(ctx->ad_std);
+  cudaFree(ctx->ad_ids);
+  cudaFree(ctx->ad_order);
+  cudaFree(ctx->ad_pos);
+  cudaFree(ctx->ad_offsets);
+  cudaFree(ctx->ad_tmp);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   delete ctx;
 }

@@ -36,13 +36,10 @@ struct rbpr_ctx {
   float* item_grad = nullptr;   // (I*D + I) dense item (+bias) gradient accumulator
   float* user_grad = nullptr;   // (U*D) dense user gradient accumulator (multi-occurrence users)
   uint32_t* touched = nullptr;  // (I) item touched in this step
-  uint64_t* keys_in = nullptr;  // (cap) (step<<32 | triple)
-  uint64_t* keys_out = nullptr;
-  int32_t* pos_in = nullptr;  // (cap) original position
-  int32_t* pos_out = nullptr;
+  uint32_t* ord = nullptr;  // (cap) arrival rank of each slot among its user's slots of the step
   int64_t cap = 0;
-  void* cub_tmp = nullptr;
-  size_t cub_tmp_bytes = 0;
+  uint32_t* cnt = nullptr;  // (cnt_cap) per-step user occurrence counters of the wave being prepared
+  int64_t cnt_cap = 0;
   // per-wave scratch, double-buffered: wave w+1 is sorted/sampled on `aux` while wave w trains
   void* records[2] = {nullptr, nullptr};  // (records_cap) int4 {u, i+, i-, head}
   int64_t records_cap = 0;
@@ -58,9 +55,19 @@ struct rbpr_ctx {
   int64_t* stage_idx = nullptr;  // staging for the *_host entry point
   int64_t* stage_neg = nullptr;
   int64_t stage_cap = 0;
+  // adaptive sampler state (owned): transposed snapshot, per-factor std, sorted order + inverse
+  float *ad_snap = nullptr, *ad_snap_sorted = nullptr, *ad_std = nullptr;
+  int32_t *ad_ids = nullptr, *ad_order = nullptr, *ad_pos = nullptr;
+  int64_t* ad_offsets = nullptr;
+  void* ad_tmp = nullptr;
+  size_t ad_tmp_bytes = 0, ad_cells = 0;
   // score scratch
   float* score_buf = nullptr;
   size_t score_buf_bytes = 0;
+  // data-parallel communicator (NCCL, bound at run time; comm.cu)
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+  int64_t collectives = 0;
   // instrumentation
   int64_t launches = 0;
   bool timing = false;

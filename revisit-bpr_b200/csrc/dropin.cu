@@ -2,8 +2,6 @@
 // by a DataLoader) — the drop-in side of the C ABI.  The fast path (rbpr_train_steps) takes triple
 // ids and samples on the device; these take what `Model.forward(batch)`, `Sampler.sample(batch)`
 // and eval-mode `MF.forward(user, item)` receive.  See include/rbpr.h for the call sites replaced.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "train_kernels.cuh"
 
 using namespace rbpr_dev;
@@ -17,9 +15,9 @@ int rbpr_internal_check_ready_tables(rbpr_ctx* ctx, const rbpr_hparams* hp);
 
 namespace {
 
-__global__ void explicit_keys(const int64_t* __restrict__ users, int64_t n, int64_t U,
-                              uint64_t* __restrict__ keys, int32_t* __restrict__ pos,
-                              int32_t* __restrict__ flag) {
+__global__ void explicit_count(const int64_t* __restrict__ users, int64_t n, int64_t U,
+                               uint32_t* __restrict__ cnt, uint32_t* __restrict__ ord,
+                               int32_t* __restrict__ flag) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   int64_t u = users[k];
@@ -27,27 +25,24 @@ __global__ void explicit_keys(const int64_t* __restrict__ users, int64_t n, int6
     atomicExch(flag, 7);
     u = 0;
   }
-  keys[k] = (uint64_t)u;
-  pos[k] = (int32_t)k;
+  ord[k] = atomicAdd(cnt + u, 1u);
 }
 
-__global__ void explicit_records(const uint64_t* __restrict__ keys, const int32_t* __restrict__ pos,
-                                 const int64_t* __restrict__ items, const int64_t* __restrict__ negs,
-                                 int64_t n, int64_t I, int4* __restrict__ records,
-                                 int32_t* __restrict__ flag) {
+__global__ void explicit_records(const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                                 const int64_t* __restrict__ negs, const uint32_t* __restrict__ cnt,
+                                 const uint32_t* __restrict__ ord, int64_t n, int64_t U, int64_t I,
+                                 int4* __restrict__ records, int32_t* __restrict__ flag) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint64_t key = keys[k];
-  const bool head = (k == 0) || keys[k - 1] != key;
-  const bool last = (k + 1 == n) || keys[k + 1] != key;
-  const int32_t q = pos[k];
-  int64_t i = items[q], j = negs[q];
+  int64_t u = users[k], i = items[k], j = negs[k];
+  if (u < 0 || u >= U) u = 0;  // flagged by explicit_count
   if (i < 0 || i >= I || j < 0 || j >= I) {
     atomicExch(flag, 8);
     i = j = 0;
   }
-  const int32_t flags = head ? (last ? (kRecHead | kRecSingle) : (kRecHead | kRecMultiHead)) : 0;
-  records[k] = make_int4((int32_t)key, (int32_t)i, (int32_t)j, flags);
+  const uint32_t total = cnt[u];
+  const int32_t flags = total <= 1u ? (kRecHead | kRecSingle) : (ord[k] == 0u ? (kRecHead | kRecMultiHead) : 0);
+  records[k] = make_int4((int32_t)u, (int32_t)i, (int32_t)j, flags);
 }
 
 // logits[b, k] = <U[users[b]], V[items[b, k]]> (+ item_bias[item]) (+ user_bias[user]); entries
@@ -156,19 +151,16 @@ int rbpr_train_step_triples(rbpr_ctx* ctx, const int64_t* users, const int64_t* 
   if (rc) return rc;
   if (n > 0) {
     const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-    explicit_keys<<<blocks, threads, 0, st>>>(users, n, ctx->U, ctx->keys_in, ctx->pos_in, ctx->flag);
-    int bits = 1;
-    while ((1ll << bits) < ctx->U) ++bits;
-    size_t tb = ctx->cub_tmp_bytes;
-    RBPR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tb, ctx->keys_in, ctx->keys_out,
-                                                   ctx->pos_in, ctx->pos_out, n, 0, bits, st));
-    explicit_records<<<blocks, threads, 0, st>>>(ctx->keys_out, ctx->pos_out, items, negs, n, ctx->I,
-                                                 reinterpret_cast<int4*>(ctx->records[0]), ctx->flag);
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->cnt, 0, (size_t)ctx->U * sizeof(uint32_t), st));
+    explicit_count<<<blocks, threads, 0, st>>>(users, n, ctx->U, ctx->cnt, ctx->ord, ctx->flag);
+    explicit_records<<<blocks, threads, 0, st>>>(users, items, negs, ctx->cnt, ctx->ord, n, ctx->U,
+                                                 ctx->I, reinterpret_cast<int4*>(ctx->records[0]),
+                                                 ctx->flag);
     ctx->launches += 2;
     RBPR_CUDA(ctx, cudaGetLastError());
   }
   return rbpr_internal_phase_a_apply(ctx, hp, reinterpret_cast<const int4*>(ctx->records[0]), (int)n,
-                                     step, reinterpret_cast<float2*>(logits_out), ctx->pos_out,
+                                     step, reinterpret_cast<float2*>(logits_out), nullptr,
                                      stats_out, st);
 }
 

@@ -2,8 +2,8 @@
 // curandStatePhilox4_32_10_t evaluates: with key = (seed_lo, seed_hi) and counter
 // (c0,c1,c2,c3) = (offset_lo, offset_hi, subsequence_lo, subsequence_hi) one call equals
 // curand_init(seed, subsequence, 4*offset, &s); curand4(&s).  Written out by hand so the
-// training kernel carries no generator state; oracle/philox.py and oracle/csrc/oracle.c
-// restate it for the CPU.
+// training kernel carries no generator state; oracle/philox.py (numpy)
+// restates it for the CPU.
 #pragma once
 #include <stdint.h>
 

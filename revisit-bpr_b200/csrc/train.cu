@@ -2,11 +2,12 @@
 // log-sigmoid loss + L2, exact synchronous-minibatch gradients, in-place update.
 //
 // A call is cut into WAVES of whole steps.  Per wave, on the context's auxiliary stream:
-//   P1  make_keys + cub radix sort + bpr_sample — the wave's triples are sorted by (step, triple
-//       id) == grouped by user inside every step (triples are the COO flattening of the CSR);
-//       a group of 8 lanes per slot draws the negative (Philox4x32-10, CSR rejection) and emits
-//       a 16-byte record {u, i+, i-, run flags}.  The static samplers depend on (seed, step,
-//       triple, CSR) only, so wave w+1 is prepared while wave w trains.
+//   P1  count_users + bpr_sample — per-step occurrence count of every user (one atomic per
+//       triple into an L2-resident counter table; no sort), then a group of 8 lanes per slot
+//       draws the negative (Philox4x32-10, CSR rejection) and emits a 16-byte record
+//       {u, i+, i-, flags} where the flags say whether the user occurs once in its step.  The
+//       static samplers depend on (seed, step, triple, CSR) only, so wave w+1 is prepared while
+//       wave w trains.
 // Per step, on the caller's stream (kernels in train_kernels.cuh):
 //   P2  bpr_phase_a — one lane group per triple, 128-bit row loads, shuffle-reduced dot, the two
 //       item-row gradients into the dense accumulator (vector red), single-occurrence users
@@ -15,8 +16,6 @@
 //   P3  bpr_apply — accumulated item gradient (SGD: touched rows; Adam: every row, which is
 //       torch.optim.Adam's dense semantics) and multi-occurrence users; clears the accumulators.
 // Reference call sites replaced: see include/rbpr.h (rbpr_train_steps).
-#include <cub/device/device_radix_sort.cuh>
-
 #include "train_kernels.cuh"
 
 using namespace rbpr_dev;
@@ -25,6 +24,7 @@ namespace {
 
 constexpr int64_t kWaveTriples = 1ll << 19;       // triples sorted + sampled per preparation wave
 constexpr int64_t kFirstWaveTriples = 1ll << 17;  // ... of the first wave of a call
+constexpr int64_t kCounterEntries = 1ll << 24;    // budget of the (steps in wave, U) counter table
 
 // One block per step: sums the per-warp float4 partials of that step in double.
 __global__ void reduce_stats(const float4* __restrict__ partials, int stride, double* __restrict__ out) {
@@ -60,18 +60,21 @@ __global__ void reduce_stats(const float4* __restrict__ partials, int stride, do
   }
 }
 
-__global__ void make_keys(const int64_t* __restrict__ triple_idx, int64_t n, int64_t batch,
-                          int64_t nnz, uint64_t* __restrict__ keys, int32_t* __restrict__ pos,
-                          int32_t* __restrict__ flag) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Per-step occurrence counts of users: slot k (step k / batch of the wave) takes a ticket from
+// cnt[step][user]; its arrival rank is kept so that ONE slot of a repeated user can be designated.
+__global__ void count_users(const int64_t* __restrict__ triple_idx, int64_t n, int64_t batch,
+                            int64_t nnz, int64_t U, const int32_t* __restrict__ coo_user,
+                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ ord,
+                            int32_t* __restrict__ flag) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   int64_t t = triple_idx[k];
   if (t < 0 || t >= nnz) {
     atomicExch(flag, 2);
     t = 0;
   }
-  keys[k] = ((uint64_t)(k / batch) << 32) | (uint64_t)(uint32_t)t;
-  if (pos != nullptr) pos[k] = (int32_t)k;
+  const int64_t u = coo_user[t];
+  ord[k] = atomicAdd(cnt + (k / batch) * U + u, 1u);
 }
 
 __global__ void expand_rows(const int64_t* __restrict__ indptr, int64_t U, int64_t nnz,
@@ -134,41 +137,28 @@ int check_ready(rbpr_ctx* ctx, const rbpr_hparams* hp) {
   if (ctx->csr_users != ctx->U)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "CSR has %lld rows but the user table has %lld",
               (long long)ctx->csr_users, (long long)ctx->U);
-  if (hp->sampler < RBPR_SAMPLER_UNIFORM || hp->sampler > RBPR_SAMPLER_INJECTED)
+  if (hp->sampler < RBPR_SAMPLER_UNIFORM || hp->sampler > RBPR_SAMPLER_ADAPTIVE)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "unknown sampler %d", hp->sampler);
   if (hp->sampler == RBPR_SAMPLER_WEIGHTED && (!ctx->alias_prob || !ctx->alias_idx))
     RBPR_FAIL(ctx, RBPR_ERR_STATE, "weighted sampler requested but alias table not bound");
   return 0;
 }
 
-int ensure_capacity(rbpr_ctx* ctx, int64_t n, int64_t steps) {
+// Per-wave preparation scratch: arrival ranks (n slots) and the user counters (cnt_entries).
+int ensure_capacity(rbpr_ctx* ctx, int64_t n, int64_t steps, int64_t cnt_entries) {
   if (n > ctx->cap) {
-    cudaFree(ctx->keys_in);
-    cudaFree(ctx->keys_out);
-    cudaFree(ctx->pos_in);
-    cudaFree(ctx->pos_out);
-    ctx->keys_in = ctx->keys_out = nullptr;
-    ctx->pos_in = ctx->pos_out = nullptr;
+    cudaFree(ctx->ord);
+    ctx->ord = nullptr;
     ctx->cap = 0;
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->keys_in, n * sizeof(uint64_t)));
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->keys_out, n * sizeof(uint64_t)));
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->pos_in, n * sizeof(int32_t)));
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->pos_out, n * sizeof(int32_t)));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ord, n * sizeof(uint32_t)));
     ctx->cap = n;
-    // size the radix-sort temporary for the full capacity now (keys-only and pairs, widest bit
-    // range) so that no later call allocates or frees inside a training loop
-    size_t need_k = 0, need_p = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, need_k, ctx->keys_in, ctx->keys_out, n, 0, 64);
-    cub::DeviceRadixSort::SortPairs(nullptr, need_p, ctx->keys_in, ctx->keys_out, ctx->pos_in,
-                                    ctx->pos_out, n, 0, 64);
-    const size_t need = need_k > need_p ? need_k : need_p;
-    if (need > ctx->cub_tmp_bytes) {
-      cudaFree(ctx->cub_tmp);
-      ctx->cub_tmp = nullptr;
-      ctx->cub_tmp_bytes = 0;
-      RBPR_CUDA(ctx, cudaMalloc(&ctx->cub_tmp, need));
-      ctx->cub_tmp_bytes = need;
-    }
+  }
+  if (cnt_entries > ctx->cnt_cap) {
+    cudaFree(ctx->cnt);
+    ctx->cnt = nullptr;
+    ctx->cnt_cap = 0;
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->cnt, cnt_entries * sizeof(uint32_t)));
+    ctx->cnt_cap = cnt_entries;
   }
   if (steps > ctx->stats_cap) {
     cudaFree(ctx->stats);
@@ -196,6 +186,10 @@ void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_
   p.indptr = ctx->indptr;
   p.indices = ctx->indices;
   p.coo_user = ctx->coo_user;
+  p.cnt = ctx->cnt;
+  p.ord = ctx->ord;
+  p.U = ctx->U;
+  p.nnz = ctx->nnz;
   p.alias_prob = ctx->alias_prob;
   p.alias_idx = ctx->alias_idx;
   p.flag = ctx->flag;
@@ -226,44 +220,16 @@ cudaEvent_t next_event(rbpr_ctx* ctx) {
   return ctx->ev[ctx->ev_used++];
 }
 
-// Sort (step,t) keys for n triples split into batches; fills keys_out (+pos_out).
-int sort_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t batch,
-                 bool need_pos, cudaStream_t st) {
+// Occurrence counts for n triples split into steps of `batch` (capacity ensured by the caller).
+int count_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t batch,
+                  cudaStream_t st) {
   const int64_t steps = (n + batch - 1) / batch;
-  int rc = ensure_capacity(ctx, n, steps);
-  if (rc) return rc;
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->cnt, 0, (size_t)steps * ctx->U * sizeof(uint32_t), st));
   const int threads = 256;
-  const int blocks = (int)((n + threads - 1) / threads);
-  make_keys<<<blocks, threads, 0, st>>>(triple_idx, n, batch, ctx->nnz, ctx->keys_in,
-                                        need_pos ? ctx->pos_in : nullptr, ctx->flag);
+  count_users<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(
+      triple_idx, n, batch, ctx->nnz, ctx->U, ctx->coo_user, ctx->cnt, ctx->ord, ctx->flag);
   ctx->launches++;
-  int step_bits = 0;
-  while ((1ll << step_bits) < steps) ++step_bits;
-  int nnz_bits = 1;
-  while ((1ll << nnz_bits) < ctx->nnz) ++nnz_bits;
-  // keys: low 32 bits = triple id (< nnz), high = step index. Sort bits [0,nnz_bits) and
-  // [32, 32+step_bits): cub sorts a contiguous bit range, so sort [0, 32+step_bits).
-  const int end_bit = (step_bits == 0) ? nnz_bits : 32 + step_bits;
-  size_t need = 0;
-  if (need_pos)
-    cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->keys_in, ctx->keys_out, ctx->pos_in,
-                                    ctx->pos_out, n, 0, end_bit, st);
-  else
-    cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->keys_in, ctx->keys_out, n, 0, end_bit, st);
-  if (need > ctx->cub_tmp_bytes) {
-    cudaFree(ctx->cub_tmp);
-    ctx->cub_tmp = nullptr;
-    ctx->cub_tmp_bytes = 0;
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->cub_tmp, need));
-    ctx->cub_tmp_bytes = need;
-  }
-  size_t tb = ctx->cub_tmp_bytes;
-  if (need_pos)
-    RBPR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tb, ctx->keys_in, ctx->keys_out,
-                                                   ctx->pos_in, ctx->pos_out, n, 0, end_bit, st));
-  else
-    RBPR_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp, tb, ctx->keys_in, ctx->keys_out,
-                                                  n, 0, end_bit, st));
+  RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
 }
 
@@ -420,13 +386,20 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
 
 }  // namespace
 
+// defined in adaptive.cu
+int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void* records, int64_t n,
+                                      uint64_t step, double sampling_prob, cudaStream_t st);
+
+// defined in comm.cu
+int rbpr_internal_allreduce_item_grads(rbpr_ctx* ctx, cudaStream_t st);
+
 // ---- helpers shared with dropin.cu ---------------------------------------------------------------
 int rbpr_internal_check_ready_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
   return check_tables(ctx, hp);
 }
 
 int rbpr_internal_reserve_sort(rbpr_ctx* ctx, int64_t n) {
-  int rc = ensure_capacity(ctx, n, 1);
+  int rc = ensure_capacity(ctx, n, 1, ctx->U);
   if (rc) return rc;
   return ensure_step_scratch(ctx, n, 1, 4 * ctx->sm_count * 16);
 }
@@ -537,14 +510,20 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "train: n and batch must be < 2^31 per call");
   if (hp->sampler == RBPR_SAMPLER_INJECTED && !neg_in)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "train: injected sampler needs neg_in");
+  if (hp->sampler == RBPR_SAMPLER_ADAPTIVE && neg_out == nullptr) {
+    // fine: negatives are only reported when asked for
+  }
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
-  const bool need_pos = (neg_in != nullptr && hp->sampler == RBPR_SAMPLER_INJECTED) || neg_out;
   const int64_t steps = (n + batch - 1) / batch;
   // A call is processed in WAVES of whole steps (<= kWaveTriples triples): wave w+1 is sorted and
   // sampled on the context's auxiliary stream while wave w trains on the caller's stream (the
   // static samplers depend on (seed, step, triple, CSR) only, never on the model).
-  int64_t spw = kWaveTriples / batch;
+  // The adaptive sampler reads the CURRENT user rows: it is sampled step by step on the caller's
+  // stream, never ahead of the model.
+  const bool adaptive = hp->sampler == RBPR_SAMPLER_ADAPTIVE;
+  int64_t spw = adaptive ? 1 : kWaveTriples / batch;
+  if (spw > kCounterEntries / ctx->U) spw = kCounterEntries / ctx->U;  // (steps, U) counter table
   if (spw < 1) spw = 1;
   if (spw > steps) spw = steps;
   // the first wave is short (its preparation is the only one that is not overlapped)
@@ -566,14 +545,16 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
   const int stride = blocks * (kPhaseAThreads / 32);
   // scratch is sized for a full wave from the first call on, so later (longer) calls never allocate
   const int64_t alloc_cap = wave_cap > kWaveTriples ? wave_cap : kWaveTriples;
-  const int64_t alloc_spw = (kWaveTriples / batch) > spw ? (kWaveTriples / batch) : spw;
-  rc = ensure_capacity(ctx, alloc_cap, steps);
+  int64_t spw_cap = kWaveTriples / batch;
+  if (spw_cap > kCounterEntries / ctx->U) spw_cap = kCounterEntries / ctx->U;
+  const int64_t alloc_spw = spw_cap > spw ? spw_cap : spw;
+  rc = ensure_capacity(ctx, alloc_cap, steps, alloc_spw * ctx->U);
   if (rc) return rc;
   rc = ensure_step_scratch(ctx, alloc_cap, alloc_spw, stride);
   if (rc) return rc;
   TrainParams p;
   fill_train_params(ctx, p, seed, hp);
-  const bool piped = nwaves > 1;
+  const bool piped = nwaves > 1 && !adaptive;
   cudaStream_t prep_st = piped ? ctx->aux : st;
   if (piped) {
     RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, st));
@@ -584,23 +565,41 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
     const int64_t off = wave_step0(w) * batch;
     const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
     if (piped && w >= 2) RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_free[b], 0));
-    int r = sort_batches(ctx, triple_idx + off, nw, batch, need_pos, prep_st);
+    int r = count_batches(ctx, triple_idx + off, nw, batch, prep_st);
     if (r) return r;
     TrainParams q = p;
-    q.keys = ctx->keys_out;
-    q.pos = need_pos ? ctx->pos_out : nullptr;  // positions are local to the wave
+    q.triple_idx = triple_idx + off;
+    q.batch = batch;
     q.neg_in = neg_in ? neg_in + off : nullptr;
     q.neg_out = neg_out ? neg_out + off : nullptr;
-    r = run_sample(ctx, q, ctx->records[b], nw, step0 + (uint64_t)wave_step0(w), prep_st);
-    if (r) return r;
+    if (adaptive) {
+      const uint64_t s_glob = step0 + (uint64_t)wave_step0(w);
+      r = rbpr_internal_sample_adaptive_csr(ctx, q, ctx->records[b], nw, s_glob,
+                                            (double)hp->adaptive_prob, prep_st);
+      if (r) return r;
+      // AdaptiveSampler.sample refreshes its snapshot AFTER the draw of every N-th call
+      // (neg_samplers.py:122-123), i.e. from the item table before this step's update
+      if (hp->adaptive_every > 0 && (s_glob + 1) % (uint64_t)hp->adaptive_every == 0) {
+        r = rbpr_adaptive_update_stats(ctx, prep_st);
+        if (r) return r;
+      }
+    } else {
+      r = run_sample(ctx, q, ctx->records[b], nw, step0 + (uint64_t)wave_step0(w), prep_st);
+      if (r) return r;
+    }
     if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_ready[b], ctx->aux));
     return 0;
   };
-  rc = prepare(0);
-  if (rc) return rc;
+  if (piped) {
+    rc = prepare(0);
+    if (rc) return rc;
+  }
   for (int64_t w = 0; w < nwaves; ++w) {
     const int b = (int)(w & 1);
-    if (w + 1 < nwaves) {
+    if (!piped) {  // just in time, on the caller's stream
+      rc = prepare(w);
+      if (rc) return rc;
+    } else if (w + 1 < nwaves) {
       rc = prepare(w + 1);
       if (rc) return rc;
     }
@@ -617,7 +616,12 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
       rc = run_phase_a(ctx, p, hp, recs, reinterpret_cast<float4*>(ctx->partials[b]) + s * stride,
                        blocks, st);
       if (rc) return rc;
-      rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st);
+      const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
+      if (multi) {  // the one exchange of the step: dense item gradient, summed over ranks
+        rc = rbpr_internal_allreduce_item_grads(ctx, st);
+        if (rc) return rc;
+      }
+      rc = run_apply(ctx, p.step, hp, multi, 1, recs, p.n, st);
       if (rc) return rc;
     }
     reduce_stats<<<(unsigned)wsteps, 256, 0, st>>>(
@@ -686,15 +690,14 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
   if (n < 0 || n >= (1ll << 31)) RBPR_FAIL(ctx, RBPR_ERR_ARG, "grad_step: bad n");
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
-  rc = ensure_capacity(ctx, n > 0 ? n : 1, 1);
+  rc = ensure_capacity(ctx, n > 0 ? n : 1, 1, ctx->U);
   if (rc) return rc;
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, RBPR_STATS_PER_STEP * sizeof(double), st));
   if (n > 0) {
     if (!triple_idx) RBPR_FAIL(ctx, RBPR_ERR_ARG, "grad_step: null triple_idx");
     if (hp->sampler == RBPR_SAMPLER_INJECTED && !neg_in)
       RBPR_FAIL(ctx, RBPR_ERR_ARG, "grad_step: injected sampler needs neg_in");
-    const bool need_pos = (neg_in != nullptr && hp->sampler == RBPR_SAMPLER_INJECTED) || neg_out;
-    rc = sort_batches(ctx, triple_idx, n, n, need_pos, st);
+    rc = count_batches(ctx, triple_idx, n, n, st);
     if (rc) return rc;
     int lanes, nv;
     rbpr_geometry(ctx->D, &lanes, &nv);
@@ -707,8 +710,8 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
     TrainParams p;
     fill_train_params(ctx, p, seed, hp);
-    p.keys = ctx->keys_out;
-    p.pos = need_pos ? ctx->pos_out : nullptr;
+    p.triple_idx = triple_idx;
+    p.batch = n;
     p.neg_in = neg_in;
     p.neg_out = neg_out;
     rc = run_sample(ctx, p, ctx->records[0], n, step, st);

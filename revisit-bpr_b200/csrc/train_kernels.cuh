@@ -26,8 +26,12 @@ struct TrainParams {
   const int64_t* __restrict__ indptr;
   const int32_t* __restrict__ indices;
   const int32_t* __restrict__ coo_user;
-  const uint64_t* __restrict__ keys;  // sorted (step<<32|t) of this step
-  const int32_t* __restrict__ pos;    // original positions (or null)
+  const int64_t* __restrict__ triple_idx;  // the wave's triple ids, input order
+  const uint32_t* __restrict__ cnt;        // (steps in wave, U) occurrences of each user per step
+  const uint32_t* __restrict__ ord;        // arrival rank of each slot among its user's slots
+  int64_t batch;                           // triples per step
+  int64_t U;
+  int64_t nnz;
   const int64_t* __restrict__ neg_in;
   int64_t* __restrict__ neg_out;
   const float* __restrict__ alias_prob;
@@ -73,6 +77,7 @@ struct ApplyParams {
   float* __restrict__ user_v;
   int32_t* __restrict__ user_last;
 };
+
 
 // record.w flags
 constexpr int kRecHead = 1;       // first triple of a user run inside its step
@@ -205,37 +210,38 @@ __device__ __forceinline__ void adam_catchup4(float4& p, float4& m, float4& v, i
 
 constexpr int kPhaseAThreads = 128;
 
-// P1 — negative sampling for EVERY step of a call in one launch.  A group of 8 lanes per sorted
-// slot resolves (user, item), draws the negative with a cooperative 9-ary CSR probe, and emits a
-// 16-byte record {u, i+, i-, flags} (kRecHead / kRecSingle / kRecMultiHead of the user run).  The
-// static samplers depend only on (seed, step, triple, CSR), never on the model, so the whole
-// call's dependent-load chains (keys -> coo/indices -> indptr -> probes) run at full occupancy
-// here instead of sitting on the critical path of the row-gather kernel.
-constexpr int kSampleLanes = 8;
+// P1 — negative sampling for every step of a WAVE in one launch.  A group of 8 lanes per slot
+// resolves (user, item), draws the negative with a cooperative 9-ary CSR probe, and emits a
+// 16-byte record {u, i+, i-, flags} in input order.  The run flags come from the per-step user
+// occurrence counts built by count_users (train.cu): kRecSingle if the user occurs once in the
+// step, kRecMultiHead for ONE designated slot (arrival rank 0) of a user that occurs several times.
+// The static samplers depend only on (seed, step, triple, CSR), never on the model, so a whole
+// wave's dependent-load chains run here, one wave ahead of the row-gather kernel.
+constexpr int kSampleLanes = 8;  // measured: 1 lane per slot (binary search) is 13% slower (profiles/r01p)
+
+__device__ __forceinline__ int32_t slot_flags(const TrainParams& p, uint64_t k, int32_t uu) {
+  const uint64_t sl = k / (uint64_t)p.batch;
+  const uint32_t total = __ldg(p.cnt + sl * (uint64_t)p.U + (uint64_t)uu);
+  if (total <= 1u) return kRecHead | kRecSingle;
+  return (__ldg(p.ord + k) == 0u) ? (kRecHead | kRecMultiHead) : 0;
+}
+
 static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __restrict__ records,
                                                          uint64_t n_slots, uint64_t step0) {
   const Group<kSampleLanes> g;
   const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSampleLanes;
   if (k >= n_slots) return;  // whole group leaves together
-  const uint64_t key = __ldg(p.keys + k);
-  const uint32_t t = (uint32_t)key;
+  int64_t t64 = __ldg(p.triple_idx + k);
+  if (t64 < 0 || t64 >= p.nnz) t64 = 0;  // flagged by count_users
+  const uint32_t t = (uint32_t)t64;
   const int32_t uu = __ldg(p.coo_user + t);
   const int32_t i = __ldg(p.indices + t);
-  bool head = true, last = true;
-  if (k > 0u) {
-    const uint64_t kprev = __ldg(p.keys + k - 1);
-    head = (kprev >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)kprev) != uu;
-  }
-  if (k + 1u < n_slots) {
-    const uint64_t knext = __ldg(p.keys + k + 1);
-    last = (knext >> 32) != (key >> 32) || __ldg(p.coo_user + (uint32_t)knext) != uu;
-  }
-  const int32_t flags = head ? (last ? (kRecHead | kRecSingle) : (kRecHead | kRecMultiHead)) : 0;
+  const int32_t flags = slot_flags(p, k, uu);
   int32_t j;
   if (p.sampler == RBPR_SAMPLER_INJECTED) {
-    j = (int32_t)__ldg(p.neg_in + __ldg(p.pos + k));
+    j = (int32_t)__ldg(p.neg_in + k);
   } else {
-    p.step = step0 + (key >> 32);
+    p.step = step0 + k / (uint64_t)p.batch;
     const uint32_t lo = (uint32_t)__ldg(p.indptr + uu), hi = (uint32_t)__ldg(p.indptr + uu + 1);
     j = draw_negative<kSampleLanes>(p, t, lo, hi, g);
     if (j < 0) {
@@ -245,7 +251,7 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
   }
   if (g.gl == 0) {
     if (records != nullptr) records[k] = make_int4(uu, i, j, flags);
-    if (p.neg_out != nullptr) p.neg_out[__ldg(p.pos + k)] = (int64_t)j;
+    if (p.neg_out != nullptr) p.neg_out[k] = (int64_t)j;
   }
 }
 

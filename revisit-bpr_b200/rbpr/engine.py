@@ -245,6 +245,37 @@ class Engine(Context):
                                                      _stream()))
         return logits, stats
 
+    # ---- adaptive sampler ---------------------------------------------------------------------
+    def set_adaptive(self, sampling_prob: float, every: int = 0) -> None:
+        self.hp.sampler = native.SAMPLER_ADAPTIVE
+        self.hp.adaptive_prob = float(sampling_prob)
+        self.hp.adaptive_every = int(every)
+
+    def adaptive_update_stats(self) -> bool:
+        """Snapshot the item table, per-factor std, sorted factor orders (context-owned)."""
+        self._check(self.lib.rbpr_adaptive_update_stats(self.ctx, _stream()))
+        return True
+
+    def adaptive_stats(self) -> dict[str, torch.Tensor]:
+        """Views of the context-owned adaptive state: std (D,), order (D,I), pos (D,I)."""
+        std, order, pos = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.rbpr_adaptive_stats(self.ctx, C.byref(std), C.byref(order), C.byref(pos)))
+        return {"std": _wrap_device(std.value, (self.D,), "<f4", self.device),
+                "order": _wrap_device(order.value, (self.D, self.I), "<i4", self.device),
+                "pos": _wrap_device(pos.value, (self.D, self.I), "<i4", self.device)}
+
+    def sample_adaptive_padded(self, users: torch.Tensor, seen: torch.Tensor, num: int,
+                               sampling_prob: float, seed: int, step: int, _stats: object = None) -> torch.Tensor:
+        users = users.to(self.device, torch.int64).contiguous()
+        seen = seen.to(self.device, torch.int64).contiguous()
+        if seen.dim() != 2 or seen.size(0) != users.numel():
+            raise ValueError("seen_items must be (batch, width) with one row per user")
+        out = torch.empty((users.numel(), num), dtype=torch.int64, device=self.device)
+        self._check(self.lib.rbpr_sample_adaptive_padded(
+            self.ctx, _ptr(users), _ptr(seen), users.numel(), seen.size(1), num, float(sampling_prob),
+            seed & (2**64 - 1), step, _ptr(out), _stream()))
+        return out
+
     def pair_logits(self, users: torch.Tensor, items: torch.Tensor, mask: torch.Tensor | None = None,
                     user_bias: torch.Tensor | None = None) -> torch.Tensor:
         """logits (B, K) for users (B,) and items (B, K) [+ biases]; mask==0 entries -> -1e13."""
@@ -259,6 +290,34 @@ class Engine(Context):
                                               users.numel(), per_user, _ptr(user_bias), _ptr(out),
                                               _stream()))
         return out
+
+    # ---- data-parallel communicator -------------------------------------------------------------
+    def init_comm(self, group=None) -> None:
+        """Join the library's own NCCL communicator (one rank per process of the default
+        torch.distributed group): rank 0's unique id travels through torch.distributed.  After
+        this, train_steps / train_steps_host run the data-parallel step inside the library."""
+        import importlib.util
+        import os
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if "RBPR_NCCL_LIB" not in os.environ:  # the libnccl PyTorch itself ships
+            spec = importlib.util.find_spec("nvidia")
+            for root in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["RBPR_NCCL_LIB"] = cand
+                    break
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            self._check(self.lib.rbpr_comm_unique_id(self.ctx, C.c_void_p(uid.data_ptr())))
+        dev_uid = uid.to(self.device)
+        dist.broadcast(dev_uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = dev_uid.cpu()
+        self._check(self.lib.rbpr_comm_init(self.ctx, world, rank, C.c_void_p(uid.data_ptr())))
+        self.world, self.rank = world, rank
+
+    def collective_count(self) -> int:
+        return int(self.lib.rbpr_collective_count(self.ctx))
 
     # ---- data-parallel split ---------------------------------------------------------------
     def grad_step(self, triple_idx: torch.Tensor, seed: int, step: int,
@@ -335,13 +394,17 @@ class Engine(Context):
         return ms.value, n.value
 
 
-def _wrap_device_f32(ptr: int, numel: int, device: torch.device) -> torch.Tensor:
+def _wrap_device(ptr: int, shape: tuple, typestr: str, device: torch.device) -> torch.Tensor:
     class _Arr:  # __cuda_array_interface__ carrier
         pass
     a = _Arr()
-    a.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False),
+    a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
                                   "version": 2, "strides": None}
     return torch.as_tensor(a, device=device)
+
+
+def _wrap_device_f32(ptr: int, numel: int, device: torch.device) -> torch.Tensor:
+    return _wrap_device(ptr, (numel,), "<f4", device)
 
 
 def build_alias(w: np.ndarray) -> tuple[np.ndarray, np.ndarray]:

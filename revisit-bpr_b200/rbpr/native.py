@@ -5,27 +5,24 @@ import ctypes as C
 import os
 from pathlib import Path
 
-# Load every kernel of librbpr.so when the CUDA context is created instead of at first launch:
-# lazy loading otherwise pages cubins in from disk in the middle of a training loop (seen as
-# 10-400 ms stalls on fresh boxes).  Only effective if set before the process initialises CUDA.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 LIB_PATH = Path(__file__).resolve().parent.parent / "librbpr.so"
 
 OPT_SGD, OPT_ADAM = 0, 1
-SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED = 0, 1, 2
+SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
     "rbpr_abi_version", "rbpr_create", "rbpr_destroy", "rbpr_last_error", "rbpr_bind_tables",
-    "rbpr_bind_adam_state", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_sample_negatives",
+    "rbpr_bind_adam_state", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_adaptive_update_stats", "rbpr_adaptive_stats",
+    "rbpr_sample_adaptive_padded", "rbpr_sample_negatives",
     "rbpr_train_steps", "rbpr_sync_check", "rbpr_train_steps_host", "rbpr_grad_step",
     "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
     "rbpr_score_dense", "rbpr_train_step_triples", "rbpr_pair_logits", "rbpr_sample_negatives_padded",
     "rbpr_topk_metrics_dense",
+    "rbpr_comm_unique_id", "rbpr_comm_init", "rbpr_comm_allreduce_item_grads", "rbpr_collective_count",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
 )
 
@@ -35,7 +32,7 @@ class HParams(C.Structure):
         ("optimizer", C.c_int32), ("sampler", C.c_int32), ("lr", C.c_float),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("reg_user", C.c_float), ("reg_item", C.c_float), ("reg_neg", C.c_float),
-        ("reserved0", C.c_float),
+        ("adaptive_prob", C.c_float), ("adaptive_every", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -69,6 +66,9 @@ def load() -> C.CDLL:
         "rbpr_bind_adam_state": (C.c_int, [vp] * 8),
         "rbpr_bind_csr": (C.c_int, [vp, vp, vp, i64, i64, vp]),
         "rbpr_bind_item_alias": (C.c_int, [vp, vp, vp]),
+        "rbpr_adaptive_update_stats": (C.c_int, [vp, vp]),
+        "rbpr_adaptive_stats": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "rbpr_sample_adaptive_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_double, u64, u64, vp, vp]),
         "rbpr_sample_negatives": (C.c_int, [vp, vp, i64, u64, u64, i32, vp, vp]),
         "rbpr_train_steps": (C.c_int, [vp, vp, i64, i64, u64, u64, hp, vp, vp, vp, vp]),
         "rbpr_sync_check": (C.c_int, [vp, vp]),
@@ -85,6 +85,10 @@ def load() -> C.CDLL:
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),
         "rbpr_topk_metrics_dense": (C.c_int, [vp, vp, vp, i64, i64, i32, C.POINTER(i32), i32, i32,
                                               vp, vp, vp, vp, vp]),
+        "rbpr_comm_unique_id": (C.c_int, [vp, vp]),
+        "rbpr_comm_init": (C.c_int, [vp, i32, i32, vp]),
+        "rbpr_comm_allreduce_item_grads": (C.c_int, [vp, vp]),
+        "rbpr_collective_count": (i64, [vp]),
         "rbpr_launch_count": (i64, [vp]),
         "rbpr_kernel_timing": (C.c_int, [vp, i32]),
         "rbpr_kernel_time_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]),

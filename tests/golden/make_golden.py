@@ -35,6 +35,39 @@ def import_reference():
     return Model, MF, UniformSampler, NDCG, Recall
 
 
+def adaptive_case(Model, MF):
+    """The reference AdaptiveSampler on fixed inputs.  Its two random draws (factor, geometric) are
+    recovered by replaying the same generator on the same calls, so the golden file pins the
+    DETERMINISTIC part: (factor, geometric draw, user row, seen row, snapshot) -> item."""
+    from revisit_bpr.modules import AdaptiveSampler
+    rng = np.random.default_rng(11)
+    U, I, D, B = 60, 45, 12, 96
+    indptr, indices = tiny_csr(U, I, 2, 25, rng)
+    torch.manual_seed(17)
+    model = Model(MF(torch.nn.Embedding(U, D, padding_idx=0), torch.nn.Embedding(I, D, padding_idx=0)))
+    with torch.no_grad():
+        model.logits_model._user_emb.weight.mul_(D * 2.0)
+        model.logits_model._item_emb.weight.mul_(D * 2.0)
+    users = torch.as_tensor(rng.integers(1, U, size=B))
+    seen = padded_seen(indptr, indices, users.tolist())
+    p = 0.2
+    sampler = AdaptiveSampler(model, I, p, torch.Generator().manual_seed(5), every=1000)
+    sampler.update_stats()
+    batch = {"user": users, "item": torch.zeros(B, 1, dtype=torch.long), "seen_items": seen}
+    negs = sampler.sample(batch)
+    # replay the generator: same calls in the same order (neg_samplers.py:84-94)
+    g = torch.Generator().manual_seed(5)
+    feats = model.logits_model.get_features()
+    factor = torch.multinomial(feats["user"].abs()[users] * sampler._factor_std, num_samples=1, generator=g)
+    geom = torch.empty_like(factor).geometric_(p, generator=g)
+    np.savez_compressed(OUT / "adaptive.npz", indptr=indptr, indices=indices, users=users.numpy(),
+                        seen=seen.numpy(), user_emb=feats["user"].detach().numpy(),
+                        item_emb=feats["item"].detach().numpy(), snapshot=sampler._factor_to_items.numpy(),
+                        factor_std=sampler._factor_std.numpy().ravel(), factor=factor.numpy().ravel(),
+                        geom=geom.numpy().ravel(), negs=negs.numpy().ravel(), p=p)
+    print("adaptive negs", negs.ravel()[:8].tolist(), "factors", factor.ravel()[:8].tolist())
+
+
 def tiny_csr(num_users, num_items, deg_lo, deg_hi, rng):
     indptr = [0, 0]
     idx = []
@@ -155,6 +188,7 @@ def main():
                **{**common, "steps": 9})
     metrics_case(NDCG, Recall)
     sampler_case(UniformSampler)
+    adaptive_case(Model, MF)
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_hparams_layout_matches_header():
     from rbpr import native
-    assert ctypes.sizeof(native.HParams) == 40
+    assert ctypes.sizeof(native.HParams) == 48
     assert native.HParams.lr.offset == 8 and native.HParams.reg_user.offset == 24
 
 
