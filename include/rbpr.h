@@ -273,6 +273,18 @@ int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* tar
                             int32_t linear_gain, float* ndcg_out, float* recall_out,
                             float* precision_out, int32_t* topk_items, void* stream);
 
+/* logits[b, seen[b,c]] = -1e13 and logits[b,0] = -1e13 for the reference's padded seen matrix
+ * (batch,width) int64; logits (batch,n_cols) float, in place.  Replaces
+ * BPRExperiment._remove_seen_items (experiments/bpr/exp.py:369-374). */
+int rbpr_mask_seen_padded(rbpr_ctx* ctx, float* logits, const int64_t* seen, int64_t batch,
+                          int64_t width, int64_t n_cols, void* stream);
+
+/* Per-row ROC AUC over (positive, negative) pairs: positives target != 0, negatives target == 0 and
+ * mask != 0 (mask may be NULL = all ones); 0/0 -> NaN.  Replaces RocAucManySlow.compute
+ * (revisit_bpr/metrics/auc.py:149-166).  auc_out (n_rows,) float.  Device pointers. */
+int rbpr_auc_dense(rbpr_ctx* ctx, const float* scores, const float* target, const float* mask,
+                   int64_t n_rows, int64_t n_cols, float* auc_out, void* stream);
+
 /* Instrumentation: number of kernels this context has launched so far, and the device time
  * (ms, CUDA events on the launch stream) spent in the dominant training kernel since the
  * last reset, with the number of launches sampled.  Timing is off unless enabled; when on,

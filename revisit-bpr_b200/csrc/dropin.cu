@@ -133,6 +133,85 @@ sample_padded(const int64_t* __restrict__ seen, int64_t B, int64_t S, uint32_t I
   if (g.gl == 0) out[slot] = (int64_t)res;
 }
 
+// logits[b, seen[b, c]] = -1e13 for every entry of the padded seen matrix; logits[b, 0] = -1e13
+// (BPRExperiment._remove_seen_items, experiments/bpr/exp.py:369-374).  Padding entries are 0.
+__global__ void mask_seen_padded(float* __restrict__ logits, const int64_t* __restrict__ seen,
+                                 int64_t B, int64_t S, int64_t I, int32_t* __restrict__ flag) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B * (S + 1)) return;
+  const int64_t row = q / (S + 1), c = q % (S + 1);
+  int64_t it = (c == S) ? 0 : seen[row * S + c];
+  if (it < 0 || it >= I) {
+    atomicExch(flag, 8);
+    return;
+  }
+  logits[row * I + it] = -1e13f;
+}
+
+// RocAucManySlow (revisit_bpr/metrics/auc.py:149-166): per row, the fraction of (positive, negative)
+// pairs with score[pos] > score[neg]; positives = target != 0, negatives = target == 0 and
+// mask != 0.  One CTA per row: positives staged in shared memory in chunks, one pass over the row
+// per chunk counting, for every negative, the positives that beat it.  0/0 -> NaN like the reference.
+__global__ void __launch_bounds__(256)
+auc_rows(const float* __restrict__ scores, const float* __restrict__ target,
+         const float* __restrict__ mask, int64_t I, float* __restrict__ out) {
+  constexpr int CH = 1024;
+  __shared__ float pos_s[CH];
+  __shared__ int s_npos_chunk;
+  __shared__ unsigned long long s_wins, s_npos, s_nneg;
+  const int64_t row = blockIdx.x;
+  const float* sr = scores + row * I;
+  const float* tr = target + row * I;
+  const float* mr = mask ? mask + row * I : nullptr;
+  if (threadIdx.x == 0) {
+    s_wins = 0ull;
+    s_npos = 0ull;
+    s_nneg = 0ull;
+  }
+  __syncthreads();
+  // count negatives once
+  unsigned long long nneg = 0;
+  for (int64_t i = threadIdx.x; i < I; i += blockDim.x)
+    nneg += (tr[i] == 0.f && (mr == nullptr || mr[i] != 0.f));
+  atomicAdd(&s_nneg, nneg);
+  int64_t next = 0;  // first column not yet scanned for positives
+  while (next < I) {
+    if (threadIdx.x == 0) s_npos_chunk = 0;
+    __syncthreads();
+    // gather up to CH positives from columns [next, ...): sequential chunking by column blocks
+    int64_t base = next;
+    for (; base < I; base += blockDim.x) {
+      const int64_t i = base + threadIdx.x;
+      const bool is_pos = i < I && tr[i] != 0.f;
+      if (is_pos) {
+        const int slot = atomicAdd(&s_npos_chunk, 1);
+        if (slot < CH) pos_s[slot] = sr[i];
+      }
+      __syncthreads();
+      const int got = s_npos_chunk;
+      __syncthreads();
+      if (got > CH - (int)blockDim.x) {  // the next block of columns might overflow: stop here
+        base += blockDim.x;
+        break;
+      }
+    }
+    next = base;
+    const int np = min(s_npos_chunk, CH);
+    unsigned long long wins = 0;
+    for (int64_t i = threadIdx.x; i < I; i += blockDim.x) {
+      if (!(tr[i] == 0.f && (mr == nullptr || mr[i] != 0.f))) continue;
+      const float v = sr[i];
+      int w = 0;
+      for (int q = 0; q < np; ++q) w += (pos_s[q] > v);
+      wins += (unsigned long long)w;
+    }
+    atomicAdd(&s_wins, wins);
+    if (threadIdx.x == 0) s_npos += (unsigned long long)np;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[row] = (float)((double)s_wins / ((double)s_npos * (double)s_nneg));
+}
+
 }  // namespace
 
 extern "C" {
@@ -203,6 +282,34 @@ int rbpr_sample_negatives_padded(rbpr_ctx* ctx, const int64_t* seen, int64_t bat
   sample_padded<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       seen, batch, width, (uint32_t)num_items, ctx->alias_prob, ctx->alias_idx, sampler,
       (uint32_t)seed, (uint32_t)(seed >> 32), step, num, neg_out, ctx->flag);
+  ctx->launches++;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int rbpr_mask_seen_padded(rbpr_ctx* ctx, float* logits, const int64_t* seen, int64_t batch,
+                          int64_t width, int64_t n_cols, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (batch < 0 || width < 0 || n_cols < 1) RBPR_FAIL(ctx, RBPR_ERR_ARG, "mask_seen_padded: bad sizes");
+  if (batch == 0) return 0;
+  if (!logits || (width > 0 && !seen)) RBPR_FAIL(ctx, RBPR_ERR_ARG, "mask_seen_padded: null pointer");
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t total = batch * (width + 1);
+  mask_seen_padded<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, seen, batch, width,
+                                                                             n_cols, ctx->flag);
+  ctx->launches++;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int rbpr_auc_dense(rbpr_ctx* ctx, const float* scores, const float* target, const float* mask,
+                   int64_t n_rows, int64_t n_cols, float* auc_out, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (n_rows < 0 || n_cols < 1) RBPR_FAIL(ctx, RBPR_ERR_ARG, "auc_dense: bad sizes");
+  if (n_rows == 0) return 0;
+  if (!scores || !target || !auc_out) RBPR_FAIL(ctx, RBPR_ERR_ARG, "auc_dense: null pointer");
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  auc_rows<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(scores, target, mask, n_cols, auc_out);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;

@@ -1,0 +1,131 @@
+"""Datasets / collators the BPR configs name (reference experiments/bpr/dataset.py), same class
+names and constructor arguments, same batch dictionaries.
+
+On-disk format (reference bin/datasets/format-repro.sh:56-81): `<split>.jsonl` lines
+{"user": u, "item": i}; `<split>-user-seen-items.jsonl` lines {"user": u, "seen_items": [...]};
+`<split>-grouped.jsonl` lines {"user": u, "item": [...]}.  Ids are 1-based, 0 is the padding id.
+
+`SparseSamplingInMemoryWithCollator` additionally exposes the interaction matrix as CSR
+(`csr()`), which is what the fast path binds (rbpr_bind_csr) — the reference's dense padded
+`(num_users, max_seen)` matrix is still built because `collate_fn` must return `seen_items`.
+"""
+from __future__ import annotations
+
+import json
+from collections import defaultdict
+from itertools import islice
+from pathlib import Path
+from typing import Any, Iterator
+
+import numpy as np
+import torch
+from torch.nn.utils.rnn import pad_sequence
+from torch.utils.data import Dataset, IterableDataset, get_worker_info
+
+
+def _read_seen(path: Path | str) -> dict[int, list[int]]:
+    with Path(path).open("r", encoding="utf-8") as fh:
+        return {rec["user"]: rec["seen_items"] for rec in map(json.loads, fh)}
+
+
+class InMemory(Dataset):
+    def __init__(self, path: Path | str, seen_items_path: Path | str) -> None:
+        with Path(path).open("r", encoding="utf-8") as fh:
+            self._samples = [json.loads(line) for line in fh]
+        self._seen_items = _read_seen(seen_items_path)
+
+    def __len__(self) -> int:
+        return len(self._samples)
+
+    def __getitem__(self, idx: int) -> dict[str, Any]:
+        sample = self._samples[idx]
+        return {**sample, "seen_items": self._seen_items[sample["user"]]}
+
+
+class Iter(IterableDataset):
+    def __init__(self, path: Path | str, seen_items_path: Path | str) -> None:
+        self._path = Path(path)
+        self._seen_items = _read_seen(seen_items_path)
+
+    def __iter__(self) -> Iterator[dict[str, Any]]:
+        info = get_worker_info()
+        start, step = (info.id, info.num_workers) if info is not None and info.num_workers > 0 else (0, 1)
+        with self._path.open("r", encoding="utf-8") as fh:
+            for line in islice(fh, start, None, step):
+                sample = json.loads(line)
+                sample["seen_items"] = self._seen_items[sample["user"]]
+                yield sample
+
+
+class SparseSamplingInMemoryWithCollator(Dataset):
+    """Train set as COO triples; `__getitem__` is the triple index, `collate_fn` fancy-indexes."""
+
+    def __init__(self, path: Path | str, seen_items_path: Path | str, num_users: int, num_items: int,
+                 padding_value: float = 0, put_on_cuda: bool = False) -> None:
+        users, items = [], []
+        with Path(path).open("r", encoding="utf-8") as fh:
+            for rec in map(json.loads, fh):
+                users.append(rec["user"])
+                items.append(rec["item"])
+        users_a, items_a = np.asarray(users, dtype=np.int64), np.asarray(items, dtype=np.int64)
+        if users_a.size and (users_a.max() >= num_users or items_a.max() >= num_items or users_a.min() < 0
+                             or items_a.min() < 0):
+            raise IndexError("user / item id outside the (num_users, num_items) matrix")
+        # CSR of the de-duplicated matrix, rows ascending: the COO flattening the reference takes
+        # from scipy's dok -> csr conversion
+        key = np.unique(users_a * np.int64(num_items) + items_a)
+        coo_u, coo_i = key // num_items, key % num_items
+        self._indptr = np.zeros(num_users + 1, dtype=np.int64)
+        np.cumsum(np.bincount(coo_u, minlength=num_users), out=self._indptr[1:])
+        self._indices = coo_i.astype(np.int32)
+        self._user_ids = torch.from_numpy(coo_u)
+        self._item_ids = torch.from_numpy(coo_i)
+        seen: list[torch.Tensor] = [torch.tensor([0]) for _ in range(num_users)]
+        for u, row in _read_seen(seen_items_path).items():
+            seen[u] = torch.tensor(row, dtype=torch.long)
+        self._seen_items = pad_sequence(seen, batch_first=True, padding_value=padding_value)
+        self.num_users, self.num_items = num_users, num_items
+        if put_on_cuda and torch.cuda.is_available():
+            self._user_ids = self._user_ids.cuda()
+            self._item_ids = self._item_ids.cuda()
+            self._seen_items = self._seen_items.cuda()
+
+    def __len__(self) -> int:
+        return len(self._user_ids)
+
+    def __getitem__(self, idx: int) -> int:
+        return idx
+
+    def collate_fn(self, indices: list[int]) -> dict[str, torch.Tensor]:
+        idx = torch.as_tensor(indices, device=self._user_ids.device)
+        users, items = self._user_ids[idx], self._item_ids[idx]
+        return {"user": users, "item": items, "seen_items": self._seen_items[users]}
+
+    def csr(self) -> tuple[np.ndarray, np.ndarray]:
+        """(indptr (num_users+1,) int64, indices (nnz,) int32 ascending per row)."""
+        return self._indptr, self._indices
+
+
+class AllItemsCollator:
+    """Eval batches: every item scored for every user, multi-hot target, padded seen items."""
+
+    def __init__(self, num_items: int, padding_value: float = 0) -> None:
+        self._num_items = num_items
+        self._padding_value = padding_value
+
+    def __call__(self, instances: list[dict[str, Any]]) -> dict[str, torch.Tensor]:
+        cols = defaultdict(list)
+        for inst in instances:
+            for k, v in inst.items():
+                cols[k].append(v)
+        n = len(instances)
+        target = torch.zeros(n, self._num_items)
+        for r, pos in enumerate(cols["item"]):
+            target[r, torch.as_tensor(pos, dtype=torch.long)] = 1.0
+        return {
+            "user": torch.as_tensor(cols["user"]),
+            "item": torch.arange(self._num_items, dtype=torch.long).unsqueeze(0).repeat(n, 1),
+            "target": target,
+            "seen_items": pad_sequence([torch.as_tensor(s) for s in cols["seen_items"]], batch_first=True,
+                                       padding_value=self._padding_value),
+        }

@@ -1,0 +1,213 @@
+"""`experiments.bpr.Experiment` (reference experiments/bpr/exp.py:44-405) — the hook wiring that
+puts the BPR hot path inside the Trainer, with the reference's constructor signature so the jinja
+configs' `experiment:` block instantiates unchanged:
+
+  * GET_BATCH_COMPLETED on the train engine: `_train_batch` writes `batch["neg"]` (exp.py:356-367)
+    from the device samplers — static (uniform, or popularity-weighted when the config supplies
+    `item_counts` and `neg_sampling_alpha`, exp.py:85-91,282-293) or adaptive (exp.py:295-342) with
+    its statistics refreshed every int(I·ln I / batch) iterations (exp.py:194-207);
+  * FORWARD_COMPLETED on the eval engine: `_remove_seen_items` (exp.py:369-374);
+  * ITERATION_COMPLETED: running means of bpr_loss / l2_reg / logits_diff (exp.py:383-405) and
+    the configured metrics (`attach_metrics`).
+
+Model, optimizer and loaders are built from the config with `instantiate` (hydra's when installed).
+Trackers, checkpoint rotation, progress bars and S3 sync of the reference are control plane and are
+not reproduced; the corresponding constructor arguments are accepted and ignored.
+"""
+from __future__ import annotations
+
+import json
+import math
+import random
+from pathlib import Path
+from typing import Any, Callable, Literal
+
+import numpy as np
+import torch
+
+from experiments.options import attach_early_stopping, attach_metrics
+from experiments.trainer import Events, ModelEvents, Trainer
+from rbpr import native
+from rbpr.engine import Context
+from revisit_bpr.metrics import Metric
+
+try:
+    from hydra.utils import instantiate
+except ImportError:
+    from experiments._instantiate import instantiate
+
+try:
+    from accelerate import Accelerator
+except ImportError:
+    from experiments._accel import Accelerator
+
+
+class BPRExperiment:
+    def __init__(
+        self,
+        exp_config: dict[str, Any] | Callable[[], dict[str, Any]],
+        dir: Path | None = None,  # noqa: A002
+        n_checkpoints: int = 2,
+        mixed_precision: str | None = None,
+        datasets_key: str = "datasets",
+        metrics: dict[str, Metric] | None = None,
+        trackers_params: dict[str, Any] | None = None,
+        events: dict[str, list[tuple[Any, Callable]]] | None = None,
+        seed: int = 13,
+        debug: bool = False,
+        skip_seen: bool = True,
+        save_logits: bool = False,
+        save_user_metrics: bool = False,
+        log_momentum: bool = False,
+        early_stopping_metric: str | None = None,
+        early_stopping_patience: int = 200,
+        early_stopping_direction: Literal["min", "max"] = "max",
+        neg_sampling_alpha: float = 0.0,
+        adaptive_sampling_prob: float | None = None,
+    ) -> None:
+        self._config = exp_config if isinstance(exp_config, dict) else exp_config()
+        self._dir = dir
+        self._seed = seed
+        self._debug = debug
+        self._skip_seen = skip_seen
+        self._early_stopping_metric = early_stopping_metric
+        self._early_stopping_patience = early_stopping_patience
+        self._early_stopping_direction = early_stopping_direction
+        self._datasets_key = datasets_key
+        self._metrics = metrics or {}
+        self._events = events or {}
+        self._adaptive_sampling_prob = adaptive_sampling_prob
+        if mixed_precision not in (None, "no"):
+            raise NotImplementedError("the CUDA BPR path is fp32 only (the reference configs use no mixed precision)")
+        del n_checkpoints, trackers_params, save_logits, save_user_metrics, log_momentum  # control plane
+        # popularity weights count^alpha (exp.py:85-91); all ones = uniform
+        self._item_counts = torch.ones(self._config["num_items"], dtype=torch.float32)
+        self._weighted = False
+        if (path := self._config[datasets_key].pop("item_counts", None)) is not None:
+            with open(path, "r", encoding="utf-8") as fh:
+                for rec in map(json.loads, fh):
+                    self._item_counts[rec["item"]] = float(rec["count"]) ** neg_sampling_alpha
+            self._weighted = bool((self._item_counts != 1).any())
+
+    @property
+    def metrics(self) -> dict[str, Any]:
+        return self._state.metrics
+
+    @property
+    def _adaptive(self) -> bool:
+        return self._adaptive_sampling_prob is not None and isinstance(self._adaptive_sampling_prob, float)
+
+    # ---- run -------------------------------------------------------------------------------------
+    def run(self) -> Any:
+        self._accelerator = Accelerator()
+        self._seed_everything()
+        for m in self._metrics.values():
+            m.set_accelerator(self._accelerator)
+        dev = self._accelerator.device
+        self._model = self._accelerator.prepare(instantiate(self._config["model"]))
+        self._optimizer = instantiate(self._config["optimizer"])(self._model.parameters())
+        loaders_cfg = self._config[self._datasets_key]
+        max_iters = {k: d.pop("max_iters", None) for k, d in loaders_cfg.items()}
+        self._datasets = {key: instantiate(cfg, generator=torch.Generator().manual_seed(self._seed))
+                          for key, cfg in loaders_cfg.items()}
+        for loader in self._datasets.values():
+            if hasattr(loader.dataset, "collate_fn"):
+                loader.collate_fn = loader.dataset.collate_fn
+        self.trainer = self._get_trainer(self._model, self._optimizer, self._datasets)
+        # counter-based device sampler: seed + iteration, like the reference's reseeded generator
+        self._neg_seed = self._seed + self.trainer.engines["train"].state.iteration
+        self._neg_calls = 0
+        self._sampler_ctx = Context(dev)
+        if self._weighted:
+            self._sampler_ctx.bind_item_weights(self._item_counts)
+        if self._adaptive:
+            self._update_adaptive_stats()
+        self._state = self.trainer.run(self._datasets, max_iters=max_iters, epochs=self._config["epochs"])
+        self._accelerator.wait_for_everyone()
+        return self._state
+
+    def interrupt(self) -> None:
+        for e in self.trainer.engines.values():
+            e.interrupt()
+
+    def _seed_everything(self) -> None:
+        random.seed(self._seed)
+        np.random.seed(self._seed)
+        torch.manual_seed(self._seed)
+
+    def _get_trainer(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, datasets: dict[str, Any]) -> Trainer:
+        trainer = Trainer(model, optimizer=optimizer, accelerator=self._accelerator,
+                          custom_engines=self._config.get("custom_engines", {}))
+        if self._adaptive:
+            bs = getattr(datasets["train"], "total_batch_size", None) or datasets["train"].batch_size
+            every = max(1, int(self._config["num_items"] * math.log(self._config["num_items"]) / bs))
+            trainer.add_event("train", Events.GET_BATCH_COMPLETED(every=every), self._update_adaptive_stats)
+        trainer.add_event("train", Events.GET_BATCH_COMPLETED, self._train_batch)
+        if self._skip_seen:
+            trainer.add_event("eval", ModelEvents.FORWARD_COMPLETED, self._remove_seen_items)
+        if self._early_stopping_metric is not None:
+            attach_early_stopping(trainer, metric_name=self._early_stopping_metric,
+                                  patience=self._early_stopping_patience, direction=self._early_stopping_direction)
+        if self._debug:
+            trainer.add_event("train", Events.ITERATION_COMPLETED(every=2000), lambda e: e.terminate())
+        attach_metrics(trainer, self._accelerator, self._metrics)
+        for key, handlers in self._events.items():
+            for event, handler in handlers:
+                trainer.add_event(key, event, handler, accelerator=self._accelerator)
+        trainer.add_event("train", Events.EPOCH_STARTED, self._reset_metrics)
+        trainer.add_event("train", Events.ITERATION_COMPLETED, self._update_metrics)
+        return trainer
+
+    # ---- hooks on the hot path -------------------------------------------------------------------
+    def _to_device(self, batch: dict[str, torch.Tensor]) -> None:
+        dev = self._accelerator.device
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.device != dev:
+                batch[k] = v.to(dev, non_blocking=True)
+
+    @torch.no_grad()
+    def _train_batch(self, engine: Any) -> None:
+        batch = engine.state.batch
+        self._to_device(batch)
+        if batch["item"].dim() < 2:
+            batch["item"] = batch["item"].unsqueeze(-1)
+        num = batch["item"].size(-1)
+        if self._adaptive:
+            eng = self._model.logits_model.engine()
+            batch["neg"] = eng.sample_adaptive_padded(batch["user"], batch["seen_items"], num,
+                                                      self._adaptive_sampling_prob, self._neg_seed, self._neg_calls)
+        else:
+            kind = native.SAMPLER_WEIGHTED if self._weighted else native.SAMPLER_UNIFORM
+            batch["neg"] = self._sampler_ctx.sample_padded(batch["seen_items"], self._config["num_items"], num,
+                                                           self._neg_seed, self._neg_calls, kind)
+        self._neg_calls += 1
+
+    @torch.no_grad()
+    def _update_adaptive_stats(self) -> None:
+        flush = getattr(self._model, "flush", None)
+        if flush is not None:
+            flush()
+        self._model.logits_model.engine().adaptive_update_stats()
+
+    @torch.no_grad()
+    def _remove_seen_items(self, engine: Any) -> None:
+        batch, output = engine.state.batch, engine.state.output
+        if (seen := batch.get("seen_items")) is not None:
+            self._sampler_ctx.mask_seen_padded(output["logits"], seen)
+        self._to_device(batch)  # metrics read batch["target"] on the device next
+
+    def _reset_metrics(self, engine: Any) -> None:
+        if engine.state.was_interrupted:
+            return
+        for m in ("bpr_loss", "l2_reg", "logits_diff"):
+            engine.state.metrics[f"_{m}"] = torch.tensor(0.0, device=self._accelerator.device)
+
+    @torch.no_grad()
+    def _update_metrics(self, engine: Any) -> None:
+        state = engine.state
+        out = state.output
+        for m in ("bpr_loss", "l2_reg"):
+            state.metrics[f"_{m}"] += out[m]
+            state.metrics[m] = state.metrics[f"_{m}"] / state.epoch_iteration
+        state.metrics["_logits_diff"] += out["logits"].abs().mean()
+        state.metrics["logits_diff"] = state.metrics["_logits_diff"] / state.epoch_iteration

@@ -92,6 +92,25 @@ class Context:
             sampler, _ptr(out), _stream()))
         return out
 
+    def mask_seen_padded(self, logits: torch.Tensor, seen: torch.Tensor) -> torch.Tensor:
+        """In place: logits[b, seen[b,:]] = -1e13, logits[b, 0] = -1e13 (exp.py:369-374)."""
+        if not (logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 2):
+            raise ValueError("logits must be a contiguous float32 CUDA matrix")
+        seen = seen.to(self.device, torch.int64).contiguous()
+        self._check(self.lib.rbpr_mask_seen_padded(self.ctx, _ptr(logits), _ptr(seen), logits.size(0),
+                                                   seen.size(1), logits.size(1), _stream()))
+        return logits
+
+    def auc_dense(self, output: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
+        output = output.to(self.device, torch.float32).contiguous()
+        target = target.to(self.device, torch.float32).contiguous()
+        if mask is not None:
+            mask = mask.to(self.device, torch.float32).contiguous()
+        out = torch.empty(output.size(0), dtype=torch.float32, device=self.device)
+        self._check(self.lib.rbpr_auc_dense(self.ctx, _ptr(output), _ptr(target), _ptr(mask), output.size(0),
+                                            output.size(1), _ptr(out), _stream()))
+        return out
+
     def topk_metrics_dense(self, output: torch.Tensor, target: torch.Tensor, ks: Sequence[int],
                            linear_gain: bool = False, want_items: bool = False) -> dict[str, torch.Tensor]:
         """NDCG / Recall / Precision at every cut-off of `ks` from dense (B,I) scores and targets."""

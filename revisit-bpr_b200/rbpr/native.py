@@ -21,7 +21,7 @@ SYMBOLS = (
     "rbpr_train_steps", "rbpr_sync_check", "rbpr_train_steps_host", "rbpr_grad_step",
     "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
     "rbpr_score_dense", "rbpr_train_step_triples", "rbpr_pair_logits", "rbpr_sample_negatives_padded",
-    "rbpr_topk_metrics_dense",
+    "rbpr_topk_metrics_dense", "rbpr_mask_seen_padded", "rbpr_auc_dense",
     "rbpr_comm_unique_id", "rbpr_comm_init", "rbpr_comm_allreduce_item_grads", "rbpr_collective_count",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
 )
@@ -85,6 +85,8 @@ def load() -> C.CDLL:
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),
         "rbpr_topk_metrics_dense": (C.c_int, [vp, vp, vp, i64, i64, i32, C.POINTER(i32), i32, i32,
                                               vp, vp, vp, vp, vp]),
+        "rbpr_mask_seen_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, vp]),
+        "rbpr_auc_dense": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
         "rbpr_comm_unique_id": (C.c_int, [vp, vp]),
         "rbpr_comm_init": (C.c_int, [vp, i32, i32, vp]),
         "rbpr_comm_allreduce_item_grads": (C.c_int, [vp, vp]),

@@ -1,6 +1,7 @@
+from revisit_bpr.metrics.auc import RocAucManySlow
 from revisit_bpr.metrics.metric import MaskedMetric, Metric
 from revisit_bpr.metrics.ndcg import NDCG
 from revisit_bpr.metrics.precision import Precision
 from revisit_bpr.metrics.recall import Recall
 
-__all__ = ["Metric", "MaskedMetric", "NDCG", "Recall", "Precision"]
+__all__ = ["Metric", "MaskedMetric", "NDCG", "Recall", "Precision", "RocAucManySlow"]

@@ -1,0 +1,161 @@
+"""End-to-end GPU test of `experiments.bpr.Experiment` driven by a config in the reference's own
+schema (jinja2-templated YAML with `_target_` blocks, same keys as
+configs/RQ2/neg-sampling/*.yaml.j2) on a small jsonl dataset in the reference's on-disk format:
+train with the hooks (negatives, fused step), evaluate (all-item logits, seen masking, metrics),
+and check the reported metrics against the oracle evaluated on the final tables."""
+import json
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+CONFIG = """
+num_users: &num_users {{ (num_users | int) + 1 }}
+num_items: &num_items {{ (num_items | int) + 1 }}
+epochs: {{ epochs | default(2, true) | int }}
+experiment:
+  _target_: experiments.bpr.Experiment
+  early_stopping_metric: ndcg@10
+  early_stopping_patience: 13
+  {% if adaptive %}adaptive_sampling_prob: !!float {{ 1 / 20 | float }}{% endif %}
+  metrics:
+    ndcg@10: {_target_: revisit_bpr.metrics.NDCG, topk: 10}
+    recall@20: {_target_: revisit_bpr.metrics.Recall, topk: 20}
+    precision@5: {_target_: revisit_bpr.metrics.Precision, topk: 5}
+    auc: {_target_: revisit_bpr.metrics.RocAucManySlow}
+datasets:
+  train:
+    _target_: torch.utils.data.DataLoader
+    dataset:
+      _target_: experiments.bpr.dataset.SparseSamplingInMemoryWithCollator
+      path: {{ dataset }}/train.jsonl
+      seen_items_path: {{ dataset }}/train-user-seen-items.jsonl
+      num_users: *num_users
+      num_items: *num_items
+      put_on_cuda: true
+    batch_size: {{ train_batch_size | int }}
+    shuffle: true
+  eval:
+    _target_: torch.utils.data.DataLoader
+    dataset:
+      _target_: experiments.bpr.dataset.InMemory
+      path: {{ dataset }}/test-grouped.jsonl
+      seen_items_path: {{ dataset }}/train-user-seen-items.jsonl
+    collate_fn:
+      _target_: experiments.bpr.dataset.AllItemsCollator
+      num_items: *num_items
+    batch_size: 32
+    shuffle: false
+model:
+  _target_: revisit_bpr.models.bpr.Model
+  fuse_forward: true
+  logits_model:
+    _target_: revisit_bpr.models.bpr.MF
+    item_bias: {{ item_bias | default(true, true) }}
+    user_bias: false
+    user_emb: {_target_: torch.nn.Embedding, num_embeddings: *num_users, embedding_dim: {{ embedding_dim | int }}, padding_idx: 0}
+    item_emb: {_target_: torch.nn.Embedding, num_embeddings: *num_items, embedding_dim: {{ embedding_dim | int }}, padding_idx: 0}
+  reg_alphas: {user: 0.0016, item: 0.0001, neg: 0.00375}
+optimizer:
+  _partial_: true
+  _target_: {{ optimizer }}
+  lr: {{ lr }}
+"""
+
+
+def _write_dataset(tmp_path, n_users=80, n_items=60, seed=3):
+    from rbpr import synth
+    inter = synth.generate("t", n_users, n_items, n_users * 10, 9, 4, 0.8, seed)
+    rng = np.random.default_rng(seed)
+    train_rows, test_rows = {}, {}
+    for u in range(1, inter.num_users):
+        row = inter.indices[inter.indptr[u]:inter.indptr[u + 1]].tolist()
+        rng.shuffle(row)
+        k = max(1, len(row) // 5)
+        test_rows[u], train_rows[u] = sorted(row[:k]), sorted(row[k:])
+    with open(tmp_path / "train.jsonl", "w") as f:
+        for u, items in train_rows.items():
+            for i in items:
+                f.write(json.dumps({"user": u, "item": i}) + "\n")
+    with open(tmp_path / "train-user-seen-items.jsonl", "w") as f:
+        for u, items in train_rows.items():
+            f.write(json.dumps({"user": u, "seen_items": items}) + "\n")
+    with open(tmp_path / "test-grouped.jsonl", "w") as f:
+        for u, items in test_rows.items():
+            f.write(json.dumps({"user": u, "item": items}) + "\n")
+    return inter, train_rows, test_rows
+
+
+def _render(tmp_path, **kw):
+    import jinja2
+    text = jinja2.Template(CONFIG, undefined=jinja2.StrictUndefined).render(dataset=str(tmp_path), **kw)
+    return yaml.safe_load(text)
+
+
+@pytest.mark.parametrize("adaptive,optimizer,lr", [(False, "torch.optim.SGD", 0.05), (True, "torch.optim.Adam", 0.01)])
+def test_experiment_from_reference_style_config(tmp_path, adaptive, optimizer, lr):
+    from experiments._instantiate import instantiate
+    from oracle import ref_bpr
+    inter, train_rows, test_rows = _write_dataset(tmp_path)
+    cfg = _render(tmp_path, num_users=inter.num_users - 1, num_items=inter.num_items - 1, epochs=3, adaptive=adaptive,
+                  train_batch_size=64, embedding_dim=16, optimizer=optimizer, lr=lr, item_bias="true")
+    exp_cfg = cfg.pop("experiment")
+    exp = instantiate(exp_cfg, exp_config=lambda: cfg, dir=None, debug=False, seed=13, trackers_params={})
+    state = exp.run()
+    assert state is exp.trainer.engines["eval"].state
+    tr = exp.trainer.engines["train"].state
+    n_train = sum(len(v) for v in train_rows.values())
+    assert tr.epoch == 3 and tr.iteration == 3 * ((n_train + 63) // 64)
+    for k in ("loss", "bpr_loss", "l2_reg", "logits_diff"):
+        assert np.isfinite(tr.metrics[k].item()), k
+    np.testing.assert_allclose(tr.metrics["loss"].item(), tr.metrics["bpr_loss"].item() + tr.metrics["l2_reg"].item(), rtol=1e-4)
+    # eval metrics of the last evaluation == oracle metrics of the final tables
+    sd = exp._model.state_dict()
+    ref = ref_bpr.RefModel(sd["logits_model._user_emb.weight"].cpu(), sd["logits_model._item_emb.weight"].cpu(),
+                           sd["logits_model._item_bias"].cpu())
+    users = sorted(test_rows)
+    seen_pad = torch.nn.utils.rnn.pad_sequence([torch.as_tensor(train_rows[u]) for u in users], batch_first=True)
+    logits = ref.eval_logits(torch.as_tensor(users), seen_pad)
+    target = torch.zeros(len(users), inter.num_items)
+    for r, u in enumerate(users):
+        target[r, torch.as_tensor(test_rows[u])] = 1.0
+    np.testing.assert_allclose(exp.metrics["ndcg@10"].item(), ref_bpr.ndcg_at_k(logits, target, 10).mean().item(), atol=1e-4)
+    np.testing.assert_allclose(exp.metrics["recall@20"].item(), ref_bpr.recall_at_k(logits, target, 20).mean().item(), atol=1e-4)
+    srt = torch.gather(target, 1, torch.argsort(-logits, dim=-1))[:, :5]
+    np.testing.assert_allclose(exp.metrics["precision@5"].item(), (srt.sum(-1) / 5).mean().item(), atol=1e-4)
+    auc = []
+    for r in range(len(users)):  # RocAucManySlow restated (auc.py:149-166)
+        pos, neg = logits[r][target[r] != 0], logits[r][target[r] == 0]
+        auc.append((pos[:, None] > neg[None, :]).float().mean().item())
+    np.testing.assert_allclose(exp.metrics["auc"].item(), np.mean(auc), atol=1e-4)
+    assert 0.3 < exp.metrics["auc"].item() <= 1.0
+
+
+def test_auc_and_seen_mask_kernels():
+    from rbpr.engine import Context
+    from revisit_bpr.metrics import RocAucManySlow
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    out = torch.randn(7, 3000, generator=g)
+    tgt = (torch.rand(7, 3000, generator=g) < 0.4).float()  # > 1024 positives per row: several chunks
+    tgt[2] = 0  # no positives -> NaN
+    mask = (torch.rand(7, 3000, generator=g) < 0.8).float()
+    for mk in (None, mask):
+        got = RocAucManySlow().compute(out.to(dev), tgt.to(dev), None if mk is None else mk.to(dev)).cpu()
+        for r in range(7):
+            pos = out[r][tgt[r] != 0]
+            neg = out[r][(tgt[r] == 0) & ((mk[r] != 0) if mk is not None else torch.ones(3000, dtype=torch.bool))]
+            if pos.numel() == 0:
+                assert got[r].isnan()
+            else:
+                np.testing.assert_allclose(got[r].item(), (pos[:, None] > neg[None, :]).float().mean().item(), rtol=1e-5)
+    ctx = Context(dev)
+    logits = torch.randn(5, 40, generator=g).to(dev)
+    seen = torch.tensor([[3, 7, 0, 0], [1, 2, 3, 39], [0, 0, 0, 0], [5, 0, 0, 0], [9, 8, 7, 6]])
+    exp = logits.clone().cpu().scatter_(-1, seen, -1e13)
+    exp[:, 0] = -1e13
+    ctx.mask_seen_padded(logits, seen)
+    assert torch.equal(logits.cpu(), exp)
