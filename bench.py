@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period-ms", type=float, default=5.0, help="NVML sampling period (0 = off)")
     ap.add_argument("--cpu-steps", type=int, default=20)
-    ap.add_argument("--e2e-steps-per-call", type=int, default=25,
+    ap.add_argument("--e2e-steps-per-call", type=int, default=30,
                     help="steps handed to one host-buffer API call in the e2e leg")
     return ap.parse_args()
 

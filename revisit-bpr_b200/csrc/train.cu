@@ -499,9 +499,16 @@ int rbpr_sample_negatives(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, u
   return check_flag(ctx, st);
 }
 
-int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t batch,
-                     uint64_t seed, uint64_t step0, const rbpr_hparams* hp, const int64_t* neg_in,
-                     int64_t* neg_out, double* stats_out, void* stream) {
+}  // extern "C"
+
+// The training loop behind rbpr_train_steps / rbpr_train_steps_host.  With host sources the
+// wave's slice of triple ids (and injected negatives) is copied host->device by the preparation
+// stream right before that wave is counted and sampled, i.e. the PCIe transfer of wave w+1 overlaps
+// the training of wave w instead of preceding the whole call.
+static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64_t batch,
+                            uint64_t seed, uint64_t step0, const rbpr_hparams* hp, int64_t* neg_in,
+                            int64_t* neg_out, double* stats_out, const int64_t* host_idx,
+                            const int64_t* host_neg_in, void* stream) {
   int rc = check_ready(ctx, hp);
   if (rc) return rc;
   if (n == 0) return 0;
@@ -565,6 +572,12 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
     const int64_t off = wave_step0(w) * batch;
     const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
     if (piped && w >= 2) RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_free[b], 0));
+    if (host_idx != nullptr)
+      RBPR_CUDA(ctx, cudaMemcpyAsync(triple_idx + off, host_idx + off, nw * sizeof(int64_t),
+                                     cudaMemcpyHostToDevice, prep_st));
+    if (host_neg_in != nullptr)
+      RBPR_CUDA(ctx, cudaMemcpyAsync(neg_in + off, host_neg_in + off, nw * sizeof(int64_t),
+                                     cudaMemcpyHostToDevice, prep_st));
     int r = count_batches(ctx, triple_idx + off, nw, batch, prep_st);
     if (r) return r;
     TrainParams q = p;
@@ -638,6 +651,15 @@ int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_
   return 0;
 }
 
+extern "C" {
+
+int rbpr_train_steps(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t batch,
+                     uint64_t seed, uint64_t step0, const rbpr_hparams* hp, const int64_t* neg_in,
+                     int64_t* neg_out, double* stats_out, void* stream) {
+  return train_steps_impl(ctx, const_cast<int64_t*>(triple_idx), n, batch, seed, step0, hp,
+                          const_cast<int64_t*>(neg_in), neg_out, stats_out, nullptr, nullptr, stream);
+}
+
 int rbpr_train_steps_host(rbpr_ctx* ctx, const int64_t* triple_idx_host, int64_t n, int64_t batch,
                           uint64_t seed, uint64_t step0, const rbpr_hparams* hp,
                           const int64_t* neg_in_host, int64_t* neg_out_host,
@@ -658,18 +680,13 @@ int rbpr_train_steps_host(rbpr_ctx* ctx, const int64_t* triple_idx_host, int64_t
     RBPR_CUDA(ctx, cudaMalloc(&ctx->stage_neg, n * sizeof(int64_t)));
     ctx->stage_cap = n;
   }
-  RBPR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_idx, triple_idx_host, n * sizeof(int64_t),
-                                 cudaMemcpyHostToDevice, st));
   const bool inj = hp->sampler == RBPR_SAMPLER_INJECTED;
-  if (inj) {
-    if (!neg_in_host) RBPR_FAIL(ctx, RBPR_ERR_ARG, "train_host: injected sampler needs neg_in");
-    RBPR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_neg, neg_in_host, n * sizeof(int64_t),
-                                   cudaMemcpyHostToDevice, st));
-  }
+  if (inj && !neg_in_host) RBPR_FAIL(ctx, RBPR_ERR_ARG, "train_host: injected sampler needs neg_in");
+  // host->device copies happen wave by wave on the preparation stream (train_steps_impl);
   // neg_in and neg_out may alias the same staging buffer: each position is read before written
-  rc = rbpr_train_steps(ctx, ctx->stage_idx, n, batch, seed, step0, hp,
+  rc = train_steps_impl(ctx, ctx->stage_idx, n, batch, seed, step0, hp,
                         inj ? ctx->stage_neg : nullptr, neg_out_host ? ctx->stage_neg : nullptr,
-                        nullptr, st);
+                        nullptr, triple_idx_host, inj ? neg_in_host : nullptr, st);
   if (rc) return rc;
   const int64_t steps = (n + batch - 1) / batch;
   if (stats_out_host)
