@@ -194,7 +194,7 @@ rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t*
   const uint32_t t = (uint32_t)t64;
   const int32_t uu = __ldg(tp.coo_user + t);
   const int32_t i = __ldg(tp.indices + t);
-  const int32_t flags = slot_flags(tp, k, uu);
+  const int32_t flags = slot_flags(tp, k, 0u, uu);  // one step per launch
   AdaptiveParams p;
   p.user_emb = tp.user_emb;
   p.fstd = fstd;

@@ -44,6 +44,7 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   rbpr_internal_comm_destroy(ctx);
   cudaFree(ctx->coo_user);
+  cudaFree(ctx->bloom);
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);

@@ -33,6 +33,7 @@ struct rbpr_ctx {
   const int32_t* alias_idx = nullptr;
   // owned scratch
   int32_t* coo_user = nullptr;  // (nnz) triple -> user
+  uint32_t* bloom = nullptr;    // (U, 8) 256-bit membership filter per CSR row
   float* item_grad = nullptr;   // (I*D + I) dense item (+bias) gradient accumulator
   float* user_grad = nullptr;   // (U*D) dense user gradient accumulator (multi-occurrence users)
   uint32_t* touched = nullptr;  // (I) item touched in this step

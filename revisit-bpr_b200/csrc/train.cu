@@ -26,47 +26,16 @@ constexpr int64_t kWaveTriples = 1ll << 19;       // triples sorted + sampled pe
 constexpr int64_t kFirstWaveTriples = 1ll << 17;  // ... of the first wave of a call
 constexpr int64_t kCounterEntries = 1ll << 24;    // budget of the (steps in wave, U) counter table
 
-// One block per step: sums the per-warp float4 partials of that step in double.
-__global__ void reduce_stats(const float4* __restrict__ partials, int stride, double* __restrict__ out) {
-  __shared__ double red[4][8];
-  const float4* src = partials + (size_t)blockIdx.x * stride;
-  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
-    const float4 v = src[i];
-    a += (double)v.x;
-    b += (double)v.y;
-    c += (double)v.z;
-    d += (double)v.w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-    c += __shfl_xor_sync(0xffffffffu, c, o);
-    d += __shfl_xor_sync(0xffffffffu, d, o);
-  }
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-    red[0][warp] = a;
-    red[1][warp] = b;
-    red[2][warp] = c;
-    red[3][warp] = d;
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-    out[(size_t)blockIdx.x * RBPR_STATS_PER_STEP + threadIdx.x] = s;
-  }
-}
-
 // Per-step occurrence counts of users: slot k (step k / batch of the wave) takes a ticket from
 // cnt[step][user]; its arrival rank is kept so that ONE slot of a repeated user can be designated.
 __global__ void count_users(const int64_t* __restrict__ triple_idx, int64_t n, int64_t batch,
                             int64_t nnz, int64_t U, const int32_t* __restrict__ coo_user,
                             uint32_t* __restrict__ cnt, uint32_t* __restrict__ ord,
                             int32_t* __restrict__ flag) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid: x over the slots of one step, y = step of the wave
+  const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= batch) return;
+  const int64_t k = (int64_t)blockIdx.y * batch + local;
   if (k >= n) return;
   int64_t t = triple_idx[k];
   if (t < 0 || t >= nnz) {
@@ -74,12 +43,13 @@ __global__ void count_users(const int64_t* __restrict__ triple_idx, int64_t n, i
     t = 0;
   }
   const int64_t u = coo_user[t];
-  ord[k] = atomicAdd(cnt + (k / batch) * U + u, 1u);
+  ord[k] = atomicAdd(cnt + (int64_t)blockIdx.y * U + u, 1u);
 }
 
 __global__ void expand_rows(const int64_t* __restrict__ indptr, int64_t U, int64_t nnz,
                             uint32_t I, int32_t* __restrict__ coo_user,
-                            const int32_t* __restrict__ indices, int32_t* __restrict__ flag) {
+                            const int32_t* __restrict__ indices, uint32_t* __restrict__ bloom,
+                            int32_t* __restrict__ flag) {
   // one warp per row
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -95,6 +65,9 @@ __global__ void expand_rows(const int64_t* __restrict__ indptr, int64_t U, int64
     int32_t it = indices[q];
     if (it <= 0 || (uint32_t)it >= I) atomicExch(flag, 5);
     if (q > lo && indices[q - 1] >= it) atomicExch(flag, 6);
+    const uint32_t h1 = bloom_h1(it), h2 = bloom_h2(it);
+    atomicOr(bloom + row * 8 + (h1 >> 5), 1u << (h1 & 31u));
+    atomicOr(bloom + row * 8 + (h2 >> 5), 1u << (h2 & 31u));
   }
 }
 
@@ -107,7 +80,7 @@ __global__ void sample_only(const TrainParams p, const int64_t* __restrict__ tri
   int64_t t = triple_idx[k];
   int32_t uu = p.coo_user[t];
   uint32_t lo = (uint32_t)p.indptr[uu], hi = (uint32_t)p.indptr[uu + 1];
-  int32_t j = draw_negative<8>(p, (uint32_t)t, lo, hi, g);
+  int32_t j = draw_negative<8>(p, (uint32_t)t, uu, lo, hi, g);
   if (j < 0) {
     if (g.gl == 0) atomicExch(p.flag, 1);
     j = 1;
@@ -186,6 +159,7 @@ void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_
   p.indptr = ctx->indptr;
   p.indices = ctx->indices;
   p.coo_user = ctx->coo_user;
+  p.bloom = ctx->bloom;
   p.cnt = ctx->cnt;
   p.ord = ctx->ord;
   p.U = ctx->U;
@@ -226,8 +200,11 @@ int count_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t b
   const int64_t steps = (n + batch - 1) / batch;
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->cnt, 0, (size_t)steps * ctx->U * sizeof(uint32_t), st));
   const int threads = 256;
-  count_users<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(
-      triple_idx, n, batch, ctx->nnz, ctx->U, ctx->coo_user, ctx->cnt, ctx->ord, ctx->flag);
+  const int64_t per_step = batch < n ? batch : n;
+  if (steps > 65535) RBPR_FAIL(ctx, RBPR_ERR_ARG, "more than 65535 steps in one preparation wave");
+  const dim3 grid((unsigned)((per_step + threads - 1) / threads), (unsigned)steps);
+  count_users<<<grid, threads, 0, st>>>(triple_idx, n, batch, ctx->nnz, ctx->U, ctx->coo_user, ctx->cnt,
+                                        ctx->ord, ctx->flag);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -285,9 +262,10 @@ int ensure_step_scratch(rbpr_ctx* ctx, int64_t n, int64_t steps, int stride) {
 // P1 over all sorted slots of a wave.
 int run_sample(rbpr_ctx* ctx, const TrainParams& p, void* records, int64_t n, uint64_t step0,
                cudaStream_t st) {
-  const int64_t threads = n * kSampleLanes;
-  bpr_sample<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-      p, reinterpret_cast<int4*>(records), (uint64_t)n, step0);
+  const int64_t per_step = p.batch < n ? p.batch : n;
+  const int64_t steps = (n + p.batch - 1) / p.batch;
+  const dim3 grid((unsigned)((per_step * kSampleLanes + 255) / 256), (unsigned)steps);
+  bpr_sample<<<grid, 256, 0, st>>>(p, reinterpret_cast<int4*>(records), (uint64_t)n, step0);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -295,7 +273,7 @@ int run_sample(rbpr_ctx* ctx, const TrainParams& p, void* records, int64_t n, ui
 
 // P2 for one step: p.n / p.step / p.chunk set by the caller; records and partials of that step.
 int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int4* records,
-                float4* partials, int blocks, cudaStream_t st) {
+                float4* partials, int blocks, cudaStream_t st, int* launched_blocks) {
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
   p.partials = partials;
@@ -310,6 +288,7 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
   // the last (short) step of a call may need fewer CTAs; never more than `blocks` (partials stride)
   const int64_t need = ((int64_t)p.n + (kPhaseAThreads / lanes) - 1) / (kPhaseAThreads / lanes);
   const int nb = (int)(need < blocks ? (need > 0 ? need : 1) : blocks);
+  *launched_blocks = nb;
   int rc = (hp->optimizer == RBPR_OPT_SGD)
                ? rbpr_launch_phase_a_sgd(ctx, p, lanes, nv, records, nb, st)
                : rbpr_launch_phase_a_adam(ctx, p, lanes, nv, records, nb, st);
@@ -321,13 +300,18 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
 }
 
 // do_items / do_users select the halves of bpr_apply; records/n are the step's records (users).
+// partials/n_partials/stats_out: phase A's per-warp statistics of the step, summed by block 0.
 int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
-              const int4* records, int n, cudaStream_t st) {
+              const int4* records, int n, cudaStream_t st, const float4* partials = nullptr,
+              int n_partials = 0, double* stats_out = nullptr) {
   ApplyParams a;
   memset(&a, 0, sizeof(a));
   a.do_items = do_items;
   a.do_users = (records != nullptr && n > 0) ? 1 : 0;
-  if (!a.do_items && !a.do_users) return 0;
+  a.partials = partials;
+  a.n_partials = n_partials;
+  a.stats_out = stats_out;
+  if (!a.do_items && !a.do_users && !stats_out) return 0;
   a.records = records;
   a.n = n;
   a.user_emb = ctx->user_emb;
@@ -417,21 +401,18 @@ int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int
     const int stride = blocks * (kPhaseAThreads / 32);
     rc = ensure_step_scratch(ctx, n, 1, stride);
     if (rc) return rc;
-    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
     TrainParams p;
     fill_train_params(ctx, p, 0, hp);
     p.n = n;
     p.step = step;
     p.logit_out = logit_out;
     p.step_pos = step_pos;
-    rc = run_phase_a(ctx, p, hp, records, reinterpret_cast<float4*>(ctx->partials[0]), blocks, st);
+    int nb = 0;
+    rc = run_phase_a(ctx, p, hp, records, reinterpret_cast<float4*>(ctx->partials[0]), blocks, st, &nb);
     if (rc) return rc;
-    rc = run_apply(ctx, step, hp, 0, 1, records, n, st);
+    rc = run_apply(ctx, step, hp, 0, 1, records, n, st, reinterpret_cast<const float4*>(ctx->partials[0]),
+                   nb * (kPhaseAThreads / 32), ctx->stats);
     if (rc) return rc;
-    reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials[0]), stride,
-                                    ctx->stats);
-    ctx->launches++;
-    RBPR_CUDA(ctx, cudaGetLastError());
   }
   if (stats_out)
     RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats, RBPR_STATS_PER_STEP * sizeof(double),
@@ -453,10 +434,14 @@ int rbpr_bind_csr(rbpr_ctx* ctx, const int64_t* indptr, const int32_t* indices, 
   cudaFree(ctx->coo_user);
   ctx->coo_user = nullptr;
   RBPR_CUDA(ctx, cudaMalloc(&ctx->coo_user, nnz * sizeof(int32_t)));
+  cudaFree(ctx->bloom);
+  ctx->bloom = nullptr;
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->bloom, (size_t)num_users * 8 * sizeof(uint32_t)));
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->bloom, 0, (size_t)num_users * 8 * sizeof(uint32_t), st));
   const int64_t threads = num_users * 32;
   expand_rows<<<(int)((threads + 255) / 256), 256, 0, st>>>(indptr, num_users, nnz,
                                                             (uint32_t)ctx->I, ctx->coo_user,
-                                                            indices, ctx->flag);
+                                                            indices, ctx->bloom, ctx->flag);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   int rc = check_flag(ctx, st);
@@ -531,6 +516,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
   const bool adaptive = hp->sampler == RBPR_SAMPLER_ADAPTIVE;
   int64_t spw = adaptive ? 1 : kWaveTriples / batch;
   if (spw > kCounterEntries / ctx->U) spw = kCounterEntries / ctx->U;  // (steps, U) counter table
+  if (spw > 65535) spw = 65535;                                        // gridDim.y of the prep kernels
   if (spw < 1) spw = 1;
   if (spw > steps) spw = steps;
   // the first wave is short (its preparation is the only one that is not overlapped)
@@ -554,6 +540,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
   const int64_t alloc_cap = wave_cap > kWaveTriples ? wave_cap : kWaveTriples;
   int64_t spw_cap = kWaveTriples / batch;
   if (spw_cap > kCounterEntries / ctx->U) spw_cap = kCounterEntries / ctx->U;
+  if (spw_cap > 65535) spw_cap = 65535;
   const int64_t alloc_spw = spw_cap > spw ? spw_cap : spw;
   rc = ensure_capacity(ctx, alloc_cap, steps, alloc_spw * ctx->U);
   if (rc) return rc;
@@ -620,28 +607,24 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
     const int64_t wsteps = wave_steps(w);
     if (piped) RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
-    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[b], 0, (size_t)wsteps * stride * 16, st));
     for (int64_t s = 0; s < wsteps; ++s) {
       const int64_t soff = s * batch;
       p.n = (int)((nw - soff) < batch ? (nw - soff) : batch);
       p.step = step0 + (uint64_t)(wave_step0(w) + s);
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
-      rc = run_phase_a(ctx, p, hp, recs, reinterpret_cast<float4*>(ctx->partials[b]) + s * stride,
-                       blocks, st);
+      float4* parts = reinterpret_cast<float4*>(ctx->partials[b]) + s * stride;
+      int nb = 0;
+      rc = run_phase_a(ctx, p, hp, recs, parts, blocks, st, &nb);
       if (rc) return rc;
       const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
       if (multi) {  // the one exchange of the step: dense item gradient, summed over ranks
         rc = rbpr_internal_allreduce_item_grads(ctx, st);
         if (rc) return rc;
       }
-      rc = run_apply(ctx, p.step, hp, multi, 1, recs, p.n, st);
+      rc = run_apply(ctx, p.step, hp, multi, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32),
+                     ctx->stats + (wave_step0(w) + s) * RBPR_STATS_PER_STEP);
       if (rc) return rc;
     }
-    reduce_stats<<<(unsigned)wsteps, 256, 0, st>>>(
-        reinterpret_cast<const float4*>(ctx->partials[b]), stride,
-        ctx->stats + wave_step0(w) * RBPR_STATS_PER_STEP);
-    ctx->launches++;
-    RBPR_CUDA(ctx, cudaGetLastError());
     if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
   }
   if (stats_out)
@@ -724,7 +707,6 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     const int stride = blocks * (kPhaseAThreads / 32);
     rc = ensure_step_scratch(ctx, n, 1, stride);
     if (rc) return rc;
-    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->partials[0], 0, (size_t)stride * 16, st));
     TrainParams p;
     fill_train_params(ctx, p, seed, hp);
     p.triple_idx = triple_idx;
@@ -735,17 +717,16 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     if (rc) return rc;
       p.n = (int)n;
     p.step = step;
+    int nb = 0;
     rc = run_phase_a(ctx, p, hp, reinterpret_cast<const int4*>(ctx->records[0]),
-                     reinterpret_cast<float4*>(ctx->partials[0]), blocks, st);
+                     reinterpret_cast<float4*>(ctx->partials[0]), blocks, st, &nb);
     if (rc) return rc;
     // users are owned by this rank: finish the multi-occurrence ones now (items wait for the
-    // all-reduce, rbpr_apply_item_grads)
-    rc = run_apply(ctx, step, hp, 0, 0, reinterpret_cast<const int4*>(ctx->records[0]), (int)n, st);
+    // all-reduce, rbpr_apply_item_grads); block 0 also sums the step statistics
+    rc = run_apply(ctx, step, hp, 0, 0, reinterpret_cast<const int4*>(ctx->records[0]), (int)n, st,
+                   reinterpret_cast<const float4*>(ctx->partials[0]), nb * (kPhaseAThreads / 32),
+                   ctx->stats);
     if (rc) return rc;
-    reduce_stats<<<1, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->partials[0]), stride,
-                                    ctx->stats);
-    ctx->launches++;
-    RBPR_CUDA(ctx, cudaGetLastError());
   }
   if (stats_out)
     RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats, RBPR_STATS_PER_STEP * sizeof(double),

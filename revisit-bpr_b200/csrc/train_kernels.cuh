@@ -26,6 +26,7 @@ struct TrainParams {
   const int64_t* __restrict__ indptr;
   const int32_t* __restrict__ indices;
   const int32_t* __restrict__ coo_user;
+  const uint32_t* __restrict__ bloom;  // (U, 8) 256-bit membership filter of every CSR row, or null
   const int64_t* __restrict__ triple_idx;  // the wave's triple ids, input order
   const uint32_t* __restrict__ cnt;        // (steps in wave, U) occurrences of each user per step
   const uint32_t* __restrict__ ord;        // arrival rank of each slot among its user's slots
@@ -76,8 +77,11 @@ struct ApplyParams {
   float* __restrict__ user_m;
   float* __restrict__ user_v;
   int32_t* __restrict__ user_last;
+  // step statistics: block 0 sums phase A's per-warp partials in double (no extra launch)
+  const float4* __restrict__ partials;
+  int n_partials;
+  double* __restrict__ stats_out;  // (RBPR_STATS_PER_STEP) or null
 };
-
 
 // record.w flags
 constexpr int kRecHead = 1;       // first triple of a user run inside its step
@@ -129,12 +133,26 @@ __device__ __forceinline__ bool row_contains(const int32_t* __restrict__ idx, ui
   }
 }
 
+// 256-bit Bloom filter per user (two hash bits per seen item, built at bind time, L2-resident:
+// 32 B per user).  No false negatives, so accepting a candidate whose bits are not both set is
+// exact; only "maybe seen" candidates pay for the probe of the CSR row in DRAM.
+__device__ __forceinline__ uint32_t bloom_h1(int32_t j) { return ((uint32_t)j * 0x9E3779B1u) >> 24; }
+__device__ __forceinline__ uint32_t bloom_h2(int32_t j) { return ((uint32_t)j * 0x85EBCA77u) >> 24; }
+
 // Counter-based negative draw.  All lanes of the group evaluate the same Philox
 // block, so control flow is group-uniform.  Returns -1 after 256 blocks of failed attempts.
 template <int LANES>
-__device__ __forceinline__ int32_t draw_negative(const TrainParams& p, uint32_t t, uint32_t lo,
-                                                 uint32_t hi, const Group<LANES>& g) {
+__device__ __forceinline__ int32_t draw_negative(const TrainParams& p, uint32_t t, int32_t uu,
+                                                 uint32_t lo, uint32_t hi, const Group<LANES>& g) {
   const uint32_t n = p.draw_n, thresh = p.draw_thresh;
+  // every lane of the group reads the two filter words of a candidate itself (same address:
+  // one broadcast transaction, L2-resident table)
+  const uint32_t* bl = (p.bloom != nullptr) ? p.bloom + (size_t)uu * 8u : nullptr;
+  auto maybe_seen = [&](int32_t j) -> bool {
+    if (bl == nullptr) return true;
+    const uint32_t h1 = bloom_h1(j), h2 = bloom_h2(j);
+    return ((__ldg(bl + (h1 >> 5)) >> (h1 & 31u)) & (__ldg(bl + (h2 >> 5)) >> (h2 & 31u)) & 1u) != 0u;
+  };
   const uint32_t step_lo = (uint32_t)(p.step << 8), step_hi = (uint32_t)(p.step >> 24);
   for (uint32_t blk = 0; blk < 256u; ++blk) {
     const philox4 r = philox4x32_10(step_lo | blk, step_hi, t, 0u, p.seed_lo, p.seed_hi);
@@ -145,7 +163,7 @@ __device__ __forceinline__ int32_t draw_negative(const TrainParams& p, uint32_t 
         const uint32_t mlo = w[a] * n, mhi = __umulhi(w[a], n);
         if (mlo < thresh) continue;  // Lemire rejection: exactly uniform
         const int32_t j = 1 + (int32_t)mhi;
-        if (!row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
+        if (!maybe_seen(j) || !row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
       }
     } else {  // Walker alias over [0,I), two words per attempt
 #pragma unroll
@@ -156,7 +174,7 @@ __device__ __forceinline__ int32_t draw_negative(const TrainParams& p, uint32_t 
         const float uf = (float)(w[2 * a + 1] >> 8) * (1.0f / 16777216.0f);
         const int32_t j = (uf < __ldg(p.alias_prob + col)) ? col : __ldg(p.alias_idx + col);
         if (j == 0) continue;
-        if (!row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
+        if (!maybe_seen(j) || !row_contains<LANES>(p.indices, lo, hi, j, g)) return j;
       }
     }
   }
@@ -217,10 +235,14 @@ constexpr int kPhaseAThreads = 128;
 // step, kRecMultiHead for ONE designated slot (arrival rank 0) of a user that occurs several times.
 // The static samplers depend only on (seed, step, triple, CSR), never on the model, so a whole
 // wave's dependent-load chains run here, one wave ahead of the row-gather kernel.
-constexpr int kSampleLanes = 8;  // measured: 1 lane per slot (binary search) is 13% slower (profiles/r01p)
+#ifndef RBPR_SAMPLE_LANES
+#define RBPR_SAMPLE_LANES 2  // measured 1/2/4/8 lanes: 152/147/152/165 us per 262144-triple step (profiles/r01v)
+#endif
+constexpr int kSampleLanes = RBPR_SAMPLE_LANES;  // lanes per slot (instruction-bound kernel: fewer lanes = more slots per warp)
 
-__device__ __forceinline__ int32_t slot_flags(const TrainParams& p, uint64_t k, int32_t uu) {
-  const uint64_t sl = k / (uint64_t)p.batch;
+// (sl = step of the wave the slot belongs to; kernels take it from blockIdx.y — a 64-bit division
+// per slot was a third of the sampler's instructions)
+__device__ __forceinline__ int32_t slot_flags(const TrainParams& p, uint64_t k, uint64_t sl, int32_t uu) {
   const uint32_t total = __ldg(p.cnt + sl * (uint64_t)p.U + (uint64_t)uu);
   if (total <= 1u) return kRecHead | kRecSingle;
   return (__ldg(p.ord + k) == 0u) ? (kRecHead | kRecMultiHead) : 0;
@@ -228,22 +250,26 @@ __device__ __forceinline__ int32_t slot_flags(const TrainParams& p, uint64_t k, 
 
 static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __restrict__ records,
                                                          uint64_t n_slots, uint64_t step0) {
+  // grid: x over the slots of one step, y = step of the wave
   const Group<kSampleLanes> g;
-  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSampleLanes;
-  if (k >= n_slots) return;  // whole group leaves together
+  const uint32_t local = (blockIdx.x * blockDim.x + threadIdx.x) / kSampleLanes;
+  const uint64_t sl = blockIdx.y;
+  if (local >= (uint32_t)p.batch) return;  // whole group leaves together
+  const uint64_t k = sl * (uint64_t)p.batch + local;
+  if (k >= n_slots) return;
   int64_t t64 = __ldg(p.triple_idx + k);
   if (t64 < 0 || t64 >= p.nnz) t64 = 0;  // flagged by count_users
   const uint32_t t = (uint32_t)t64;
   const int32_t uu = __ldg(p.coo_user + t);
   const int32_t i = __ldg(p.indices + t);
-  const int32_t flags = slot_flags(p, k, uu);
+  const int32_t flags = slot_flags(p, k, sl, uu);
   int32_t j;
   if (p.sampler == RBPR_SAMPLER_INJECTED) {
     j = (int32_t)__ldg(p.neg_in + k);
   } else {
-    p.step = step0 + k / (uint64_t)p.batch;
+    p.step = step0 + sl;
     const uint32_t lo = (uint32_t)__ldg(p.indptr + uu), hi = (uint32_t)__ldg(p.indptr + uu + 1);
-    j = draw_negative<kSampleLanes>(p, t, lo, hi, g);
+    j = draw_negative<kSampleLanes>(p, t, uu, lo, hi, g);
     if (j < 0) {
       if (g.gl == 0) atomicExch(p.flag, 1);
       j = 1;
@@ -480,8 +506,7 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
       }
     }
   }
-  if (!p.do_items) return;
-  for (int64_t r = gid; r < p.I; r += groups) {
+  for (int64_t r = gid; p.do_items && r < p.I; r += groups) {
     if (!p.dense) {
       if (p.touched[r] == 0u) continue;
     }
@@ -523,6 +548,37 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
         p.item_bias[r] = b;
         p.bias_grad[r] = 0.f;
       }
+    }
+  }
+  if (blockIdx.x == 0 && p.stats_out != nullptr) {
+    __shared__ double red[4][8];
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) {
+      const float4 v = p.partials[i];
+      a += (double)v.x;
+      b += (double)v.y;
+      c += (double)v.z;
+      d += (double)v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      red[0][warp] = a;
+      red[1][warp] = b;
+      red[2][warp] = c;
+      red[3][warp] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+      p.stats_out[threadIdx.x] = t;
     }
   }
 }
