@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dim", type=int, default=128)
 ap.add_argument("--shape", default="ml-20m")
 ap.add_argument("--opt", default="sgd")
-ap.add_argument("--chunks", default="0,1,2,4,6,7,8")
+ap.add_argument("--chunks", default="0", help="unused (kept for old command lines)")
 ap.add_argument("--batches", default="256,4096,65536,262144")
 ap.add_argument("--zipf", type=float, default=None, help="override the item-popularity exponent")
 args = ap.parse_args()
