@@ -129,3 +129,29 @@ class AllItemsCollator:
             "seen_items": pad_sequence([torch.as_tensor(s) for s in cols["seen_items"]], batch_first=True,
                                        padding_value=self._padding_value),
         }
+
+
+class OnePosCollator:
+    """RQ1 / AUC protocol (reference dataset.py:193-225): each instance names its positive as an
+    index into its own `seen_items`; the batch scores that positive (column 0) against every item
+    the user has not seen (columns 1..), target = one-hot column 0.  One instance per batch."""
+
+    def __init__(self, num_items: int) -> None:
+        self._num_items = num_items
+
+    def __call__(self, instances: list[dict[str, Any]]) -> dict[str, torch.Tensor]:
+        cols = defaultdict(list)
+        for inst in instances:
+            for k, v in inst.items():
+                cols[k].append(v)
+        batch = {k: torch.tensor(v) for k, v in cols.items()}
+        seen = batch["seen_items"].view(-1)
+        positive = seen[batch["item"]]
+        unseen = torch.ones(self._num_items, dtype=torch.bool)
+        unseen[0] = False  # padding item
+        unseen[seen] = False
+        batch["item"] = torch.hstack((positive.unsqueeze(0), torch.arange(self._num_items)[unseen].unsqueeze(0)))
+        target = torch.zeros_like(batch["item"], dtype=torch.float)
+        target[:, 0] = 1.0
+        batch["target"] = target
+        return batch

@@ -12,7 +12,7 @@ import torch
 from revisit_bpr.metrics.metric import MaskedMetric, _context
 
 
-class RocAucManySlow(MaskedMetric):
+class _AucBase(MaskedMetric):
     def __init__(self) -> None:
         self._total_auc = self._total_count = 0
 
@@ -31,10 +31,7 @@ class RocAucManySlow(MaskedMetric):
         self._total_auc += self.compute(output, target, mask).sum()
 
     def compute(self, output: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
-        if output.size() != target.size():
-            raise IndexError(f"Different sizes in output and target tensors: output - {output.size()}, "
-                             f"target - {target.size()}.")
-        return _context(output.device).auc_dense(output, target, mask)
+        raise NotImplementedError
 
     def get_metric(self, reset: bool = False) -> torch.Tensor:
         metric = self._total_auc / self._total_count
@@ -46,3 +43,25 @@ class RocAucManySlow(MaskedMetric):
         device = torch.device("cpu") if self.accelerator is None else self.accelerator.device
         self._total_auc = torch.tensor(0.0, device=device)
         self._total_count = torch.tensor(0.0, device=device)
+
+
+class RocAucManySlow(_AucBase):
+    def compute(self, output: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
+        if output.size() != target.size():
+            raise IndexError(f"Different sizes in output and target tensors: output - {output.size()}, "
+                             f"target - {target.size()}.")
+        return _context(output.device).auc_dense(output, target, mask)
+
+
+class RocAucMany(RocAucManySlow):
+    """The reference's vectorised variant (auc.py:62-119) computes the same quantity."""
+
+
+class RocAucOne(_AucBase):
+    """One positive per row in column 0, negatives in columns 1.. (reference auc.py:10-59; the RQ1
+    protocol with OnePosCollator): fraction of unmasked negatives scored below the positive."""
+
+    def compute(self, output: torch.Tensor, _: torch.Tensor | None = None, mask: torch.Tensor | None = None) -> torch.Tensor:
+        target = torch.zeros_like(output)
+        target[:, 0] = 1.0
+        return _context(output.device).auc_dense(output, target, mask)

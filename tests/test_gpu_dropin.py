@@ -210,3 +210,40 @@ def test_padding_rows_receive_no_embedding_gradient():
     np.testing.assert_allclose(f["item"].detach().cpu().numpy(), ref.item_emb.detach().numpy(), atol=1e-6)
     np.testing.assert_allclose(f["item_bias"].detach().cpu().numpy(), ref.item_bias.detach().numpy(), atol=1e-6)
     assert f["user"][0].abs().sum().item() == 0 and f["item"][0].abs().sum().item() == 0
+
+
+def test_auc_one_fbeta_and_one_pos_collator():
+    """RQ1 protocol: OnePosCollator batch -> eval logits -> RocAucOne; FBeta from the top-k pass."""
+    from experiments.bpr.dataset import OnePosCollator
+    from revisit_bpr.metrics import FBeta, Precision, Recall, RocAucMany, RocAucManySlow, RocAucOne
+    from revisit_bpr.models import BPR
+    from revisit_bpr.models.bpr import MF
+    torch.manual_seed(9)
+    I = 50
+    mf = MF(torch.nn.Embedding(20, 12, padding_idx=0), torch.nn.Embedding(I, 12, padding_idx=0))
+    with torch.no_grad():
+        mf._user_emb.weight.mul_(40)
+        mf._item_emb.weight.mul_(40)
+    model = BPR(mf).to(DEV).eval()
+    batch = OnePosCollator(I)([{"user": 7, "item": 2, "seen_items": [4, 9, 17, 30]}])
+    assert batch["item"].shape == (1, 1 + (I - 1 - 4)) and batch["item"][0, 0].item() == 17
+    out = model({k: v.to(DEV) for k, v in batch.items()})["logits"]
+    got = RocAucOne().compute(out, batch["target"].to(DEV)).cpu()
+    lo = out.cpu()[0]
+    np.testing.assert_allclose(got.item(), (lo[0] > lo[1:]).float().mean().item(), rtol=1e-6)
+    mask = torch.ones_like(lo).unsqueeze(0)
+    mask[0, 5:20] = 0
+    got = RocAucOne().compute(out, None, mask.to(DEV)).cpu()
+    keep = mask[0, 1:] != 0
+    np.testing.assert_allclose(got.item(), (lo[0] > lo[1:][keep]).float().mean().item(), rtol=1e-6)
+    z = np.load(GOLDEN / "metrics.npz")
+    o, t = torch.as_tensor(z["output"]).to(DEV), torch.as_tensor(z["target"]).to(DEV)
+    a, b = RocAucMany().compute(o, t), RocAucManySlow().compute(o, t)
+    assert torch.equal(a.nan_to_num(-1), b.nan_to_num(-1))
+    for beta in (1.0, 0.5):
+        p, r = Precision(10).compute(o, t), Recall(10).compute(o, t)
+        exp = (1 + beta ** 2) * p * r / (beta ** 2 * p + r + 1e-13)
+        np.testing.assert_allclose(FBeta(10, beta).compute(o, t).cpu().numpy(), exp.cpu().numpy(), rtol=1e-6)
+    m = FBeta(10)
+    m(o, t)
+    assert set(m.state_dict()) == {"total_f", "total_count", "precision", "recall"}
