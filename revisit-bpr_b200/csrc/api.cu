@@ -27,6 +27,9 @@ int rbpr_create(int device, rbpr_ctx** out) {
     return RBPR_ERR_CUDA;
   }
   bool ok = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_phase_a, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_users, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming) == cudaSuccess;
   for (int b = 0; b < 2 && ok; ++b)
     ok = cudaEventCreateWithFlags(&ctx->ev_ready[b], cudaEventDisableTiming) == cudaSuccess &&
@@ -59,6 +62,9 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   }
   if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
+  if (ctx->ev_phase_a) cudaEventDestroy(ctx->ev_phase_a);
+  if (ctx->ev_users) cudaEventDestroy(ctx->ev_users);
   cudaFree(ctx->flag);
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);

@@ -46,7 +46,9 @@ struct rbpr_ctx {
   int64_t records_cap = 0;
   float* partials[2] = {nullptr, nullptr};  // per-warp step statistics (float4 each)
   int64_t partials_cap = 0;
-  cudaStream_t aux = nullptr;            // preparation stream (sort + negative sampling)
+  cudaStream_t aux = nullptr;            // preparation stream (counting + negative sampling)
+  cudaStream_t aux2 = nullptr;           // N>1: user half of bpr_apply, concurrent with the all-reduce
+  cudaEvent_t ev_phase_a = nullptr, ev_users = nullptr;
   cudaEvent_t ev_inputs = nullptr;       // caller's stream -> aux: inputs of the call are ready
   cudaEvent_t ev_ready[2] = {nullptr, nullptr};  // aux -> main: records[b] are ready
   cudaEvent_t ev_free[2] = {nullptr, nullptr};   // main -> aux: records[b] may be overwritten

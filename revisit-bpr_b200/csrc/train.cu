@@ -617,13 +617,25 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       rc = run_phase_a(ctx, p, hp, recs, parts, blocks, st, &nb);
       if (rc) return rc;
       const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
-      if (multi) {  // the one exchange of the step: dense item gradient, summed over ranks
+      double* step_stats = ctx->stats + (wave_step0(w) + s) * RBPR_STATS_PER_STEP;
+      if (multi) {
+        // The one exchange of the step: dense item gradient, summed over ranks.  The user half of
+        // the apply (local rows only) and the statistics run on a side stream meanwhile.
+        RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_phase_a, st));
+        RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2, ctx->ev_phase_a, 0));
+        rc = run_apply(ctx, p.step, hp, 0, 0, recs, p.n, ctx->aux2, parts, nb * (kPhaseAThreads / 32),
+                       step_stats);
+        if (rc) return rc;
+        RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_users, ctx->aux2));
         rc = rbpr_internal_allreduce_item_grads(ctx, st);
         if (rc) return rc;
+        rc = run_apply(ctx, p.step, hp, 1, 1, nullptr, 0, st);
+        if (rc) return rc;
+        RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_users, 0));
+      } else {
+        rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32), step_stats);
+        if (rc) return rc;
       }
-      rc = run_apply(ctx, p.step, hp, multi, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32),
-                     ctx->stats + (wave_step0(w) + s) * RBPR_STATS_PER_STEP);
-      if (rc) return rc;
     }
     if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
   }
