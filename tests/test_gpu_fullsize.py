@@ -157,3 +157,44 @@ def test_full_size_adam_msd_shape_smoke_and_flush():
     # p1 (value right after step 0) = p_end + drift must be reachable from p0 by ONE Adam step of size <= lr
     p1 = p + drift
     assert np.abs(p1 - ue.numpy()[only0]).max() <= lr * 1.0001 + 1e-7
+
+
+def test_host_buffer_path_multi_wave_matches_device_path(ml20m):
+    """rbpr_train_steps_host copies ids (and injected negatives) wave by wave on the preparation
+    stream: same negatives, statistics and tables as the device-resident call."""
+    from rbpr import native
+    from rbpr.engine import Engine
+    inter, D, B, steps = ml20m, 32, 100_000, 12  # 1.2 M triples: first wave + 2 full waves + tail
+    ue, ie = _tables(inter, D, 20.0)
+    t = torch.randperm(inter.nnz, generator=torch.Generator().manual_seed(8))[:B * steps]
+    out = []
+    for host in (False, True):
+        eng = Engine(ue.to(DEV), ie.to(DEV))
+        eng.bind_csr(torch.from_numpy(inter.indptr), torch.from_numpy(inter.indices))
+        eng.set_reg(REG)
+        eng.set_sgd(0.05)
+        eng.set_sampler(native.SAMPLER_UNIFORM)
+        if host:
+            stats, negs = eng.train_steps_host(t.pin_memory(), B, 5, 0, want_neg=True)
+            stats, negs = stats.clone(), negs.clone()
+        else:
+            stats, negs = eng.train_steps(t.to(DEV), B, 5, 0, want_neg=True)
+            eng.sync_check()
+            stats, negs = stats.cpu(), negs.cpu()
+        out.append((stats, negs, eng.user_emb.cpu(), eng.item_emb.cpu()))
+        # injected negatives through the same entry point reproduce the run
+        eng2 = Engine(ue.to(DEV), ie.to(DEV))
+        eng2.bind_csr(torch.from_numpy(inter.indptr), torch.from_numpy(inter.indices))
+        eng2.set_reg(REG)
+        eng2.set_sgd(0.05)
+        eng2.set_sampler(native.SAMPLER_INJECTED)
+        if host:
+            s2, n2 = eng2.train_steps_host(t.pin_memory(), B, 5, 0, neg_in=negs.pin_memory(), want_neg=True)
+            assert torch.equal(n2, negs)
+            np.testing.assert_allclose(s2.numpy(), stats.numpy(), rtol=1e-6)
+            np.testing.assert_allclose(eng2.item_emb.cpu().numpy(), out[-1][3].numpy(), atol=1e-6)
+    (s0, n0, u0, i0), (s1, n1, u1, i1) = out
+    assert torch.equal(n0, n1)
+    np.testing.assert_allclose(s0.numpy(), s1.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(u0.numpy(), u1.numpy(), atol=1e-6)
+    np.testing.assert_allclose(i0.numpy(), i1.numpy(), atol=1e-6)
