@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="ml-20m")
     ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--opt", default="sgd", choices=["sgd", "adam"],
+                    help="adam = BASELINE configs[2] (MSD shape, dim 256): lr 1e-3, betas (0.9,0.999), reg all=0.00043")
     ap.add_argument("--batch", type=int, default=262144,
                     help="triples per step and per GPU (train_batch_size is a free jinja variable of the reference configs)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic matrix (tests)")
@@ -243,8 +245,12 @@ def run_ours(args) -> None:
     ue, ie = init_tables(inter.num_users, inter.num_items, D)
     eng = Engine(ue.to(dev), ie.to(dev))
     eng.bind_csr(torch.from_numpy(inter.indptr), torch.from_numpy(inter.indices))
-    eng.set_reg(REG)
-    eng.set_sgd(LR)
+    if args.opt == "adam":  # configs/RQ2/neg-sampling/adam-ada-sampling-msd.yaml.j2:152-160
+        eng.set_reg({"all": 0.00043})
+        eng.set_adam(1e-3, (0.9, 0.999), 1e-8)
+    else:
+        eng.set_reg(REG)
+        eng.set_sgd(LR)
     eng.set_sampler(native.SAMPLER_UNIFORM)
 
     from rbpr.parallel import DataParallelTrainer, owned_triples
@@ -335,7 +341,8 @@ def run_ours(args) -> None:
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: synthetic {args.shape} shape "
                                    f"{inter.num_users - 1}x{inter.num_items - 1}, {inter.nnz} interactions, "
-                                   f"dim={D}, SGD lr={LR}, uniform on-device negatives, batch={B} triples/step"
+                                   f"dim={D}, {'Adam lr=0.001 (dense-Adam semantics, lazy user rows)' if args.opt == 'adam' else f'SGD lr={LR}'}, "
+                                   f"uniform on-device negatives, batch={B} triples/step"
                                    + (f" per GPU, users sharded by owner over {world} GPUs, one NCCL "
                                       "all-reduce of the dense item gradient per step" if world > 1 else ""),
                        "batch": B, "dim": D, "l2_policy": f"inputs larger than L2: working set "

@@ -69,6 +69,7 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);
   cudaFree(ctx->score_buf);
+  cudaFree(ctx->adam_tab);
   cudaFree(ctx->ad_snap);
   cudaFree(ctx->ad_snap_sorted);
   cudaFree(ctx->ad_std);

@@ -67,6 +67,10 @@ struct rbpr_ctx {
   // score scratch
   float* score_buf = nullptr;
   size_t score_buf_bytes = 0;
+  // per-step Adam scalars {lr_s/(1-b1^s), sqrt(1-b2^s)}, index = 1-based optimizer step
+  std::vector<float2> adam_host;
+  float2* adam_tab = nullptr;
+  int64_t adam_tab_cap = 0;
   // data-parallel communicator (NCCL, bound at run time; comm.cu)
   void* comm = nullptr;
   int world = 1, rank = 0;

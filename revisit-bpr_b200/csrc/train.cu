@@ -144,6 +144,38 @@ int ensure_capacity(rbpr_ctx* ctx, int64_t n, int64_t steps, int64_t cnt_entries
   return 0;
 }
 
+// Make the device table of Adam scalars cover optimizer steps [1, last]; entries from `first` on are
+// (re)computed with the CURRENT hyper-parameters (they describe steps that have not run yet),
+// earlier ones keep the learning rate they ran with; holes (resume at a late step) take the current
+// values.  Host double arithmetic == torch.optim.Adam's Python scalars.
+int ensure_adam_table(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t first, int64_t last,
+                      cudaStream_t st) {
+  if (hp->optimizer != RBPR_OPT_ADAM) return 0;
+  if (first < 1) first = 1;
+  if (last < first) last = first;
+  const int64_t old = (int64_t)ctx->adam_host.size();
+  if (last + 1 > old) ctx->adam_host.resize((size_t)last + 1, make_float2(0.f, 1.f));
+  const int64_t from = old < first ? (old < 1 ? 1 : old) : first;
+  for (int64_t s = from; s <= last; ++s) {
+    const double b1p = pow((double)hp->beta1, (double)s), b2p = pow((double)hp->beta2, (double)s);
+    ctx->adam_host[(size_t)s] = make_float2((float)((double)hp->lr / (1.0 - b1p)), (float)sqrt(1.0 - b2p));
+  }
+  int64_t lo = from;
+  if (last + 1 > ctx->adam_tab_cap) {
+    int64_t cap = ctx->adam_tab_cap > 0 ? ctx->adam_tab_cap : 4096;
+    while (cap < last + 1) cap *= 2;
+    cudaFree(ctx->adam_tab);
+    ctx->adam_tab = nullptr;
+    ctx->adam_tab_cap = 0;
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->adam_tab, (size_t)cap * sizeof(float2)));
+    ctx->adam_tab_cap = cap;
+    lo = 0;  // re-upload everything
+  }
+  RBPR_CUDA(ctx, cudaMemcpyAsync(ctx->adam_tab + lo, ctx->adam_host.data() + lo,
+                                 (size_t)(last + 1 - lo) * sizeof(float2), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
 void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_hparams* hp) {
   memset(&p, 0, sizeof(p));
   p.user_emb = ctx->user_emb;
@@ -154,6 +186,7 @@ void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_
   p.user_last = ctx->user_last;
   p.item_grad = ctx->item_grad;
   p.user_grad = ctx->user_grad;
+  p.adam_tab = ctx->adam_tab;
   p.bias_grad = ctx->item_bias ? ctx->item_grad + ctx->I * ctx->D : nullptr;
   p.touched = ctx->touched;
   p.indptr = ctx->indptr;
@@ -336,6 +369,7 @@ int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, i
   a.beta1 = hp->beta1;
   a.beta2 = hp->beta2;
   a.eps = hp->eps;
+  a.adam_tab = ctx->adam_tab;
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
   int rc = (hp->optimizer == RBPR_OPT_SGD) ? rbpr_launch_apply_sgd(ctx, a, lanes, nv, st)
@@ -400,6 +434,8 @@ int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int
     if (rc) return rc;
     const int stride = blocks * (kPhaseAThreads / 32);
     rc = ensure_step_scratch(ctx, n, 1, stride);
+    if (rc) return rc;
+    rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, st);
     if (rc) return rc;
     TrainParams p;
     fill_train_params(ctx, p, 0, hp);
@@ -545,6 +581,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
   rc = ensure_capacity(ctx, alloc_cap, steps, alloc_spw * ctx->U);
   if (rc) return rc;
   rc = ensure_step_scratch(ctx, alloc_cap, alloc_spw, stride);
+  if (rc) return rc;
+  rc = ensure_adam_table(ctx, hp, (int64_t)step0 + 1, (int64_t)step0 + steps, st);
   if (rc) return rc;
   TrainParams p;
   fill_train_params(ctx, p, seed, hp);
@@ -719,6 +757,8 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
     const int stride = blocks * (kPhaseAThreads / 32);
     rc = ensure_step_scratch(ctx, n, 1, stride);
     if (rc) return rc;
+    rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, st);
+    if (rc) return rc;
     TrainParams p;
     fill_train_params(ctx, p, seed, hp);
     p.triple_idx = triple_idx;
@@ -758,6 +798,8 @@ int rbpr_apply_item_grads(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, 
   int rc = check_ready(ctx, hp);
   if (rc) return rc;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, (cudaStream_t)stream);
+  if (rc) return rc;
   return run_apply(ctx, step, hp, 1, 1, nullptr, 0, (cudaStream_t)stream);
 }
 
@@ -776,7 +818,9 @@ int rbpr_flush_lazy(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* 
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  int rc = rbpr_launch_flush_users(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream);
+  int rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = rbpr_launch_flush_users(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream);
   if (rc) return rc;
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());

@@ -53,7 +53,7 @@ int rbpr_launch_flush_users(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp,
   if (lanes == L && nv == V) {                                                              \
     bpr_flush_users<L, V><<<blocks, 256, 0, st>>>(ctx->user_emb, ctx->user_m, ctx->user_v,  \
                                                   ctx->user_last, ctx->U, ctx->D, step,     \
-                                                  hp->lr, hp->beta1, hp->beta2, hp->eps);   \
+                                                  ctx->adam_tab, hp->beta1, hp->beta2, hp->eps); \
     return 0;                                                                               \
   }
   RBPR_FOR_EACH_GEOMETRY(X)

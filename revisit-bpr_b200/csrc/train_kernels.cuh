@@ -51,6 +51,7 @@ struct TrainParams {
   int sampler;
   float lr, beta1, beta2, eps;
   float reg_user, reg_item, reg_neg;
+  const float2* __restrict__ adam_tab;  // per-step Adam scalars (see adam_catchup4), or null for SGD
 };
 
 struct ApplyParams {
@@ -68,6 +69,7 @@ struct ApplyParams {
   int dense;  // 1: ignore touched flags (multi-GPU / Adam)
   uint64_t step;
   float lr, beta1, beta2, eps;
+  const float2* __restrict__ adam_tab;
   // user part: users occurring more than once in the step (records flagged kRecMultiHead)
   int do_items, do_users;
   const int4* __restrict__ records;
@@ -211,18 +213,15 @@ __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, float4 g,
 }
 
 // Replay Adam steps from+1..to with zero gradient (dense-Adam semantics for a row that received
-// no gradient in those steps).
+// no gradient in those steps).  tab[s] = {lr_s / (1 - beta1^s), sqrt(1 - beta2^s)} for optimizer
+// step s (1-based), computed on the host in double exactly like torch.optim.Adam's scalars and
+// with the learning rate that was in force at step s.
 __device__ __forceinline__ void adam_catchup4(float4& p, float4& m, float4& v, int64_t from,
-                                              int64_t to, float lr, float b1, float b2,
-                                              float eps) {
-  if (to <= from) return;
-  double b1p = pow((double)b1, (double)from), b2p = pow((double)b2, (double)from);
+                                              int64_t to, const float2* __restrict__ tab, float b1,
+                                              float b2, float eps) {
   for (int64_t s = from + 1; s <= to; ++s) {
-    b1p *= (double)b1;
-    b2p *= (double)b2;
-    const float step_size = (float)((double)lr / (1.0 - b1p));
-    const float bc2_sqrt = (float)sqrt(1.0 - b2p);
-    adam4(p, m, v, f4zero(), b1, b2, eps, step_size, bc2_sqrt);
+    const float2 t = __ldg(tab + s);
+    adam4(p, m, v, f4zero(), b1, b2, eps, t.x, t.y);
   }
 }
 
@@ -309,9 +308,9 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
 
   float step_size = 0.f, bc2_sqrt = 1.f;
   if (OPT == RBPR_OPT_ADAM) {
-    const double s = (double)(p.step + 1);  // 1-based optimizer step being applied
-    step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, s)));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, s));
+    const float2 t = __ldg(p.adam_tab + (p.step + 1));  // 1-based optimizer step being applied
+    step_size = t.x;
+    bc2_sqrt = t.y;
   }
 
   for (uint32_t k = (blockIdx.x * kPhaseAThreads + threadIdx.x) / LANES; k < n; k += ngroups) {
@@ -345,7 +344,7 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
           const int c = 4 * (g.gl + LANES * v);
           m[v] = colok[v] ? ld4(mrow + c) : f4zero();
           vv[v] = colok[v] ? ld4(vrow + c) : f4zero();
-          if (behind) adam_catchup4(u[v], m[v], vv[v], last, upto, p.lr, p.beta1, p.beta2, p.eps);
+          if (behind) adam_catchup4(u[v], m[v], vv[v], last, upto, p.adam_tab, p.beta1, p.beta2, p.eps);
         }
       }
     }
@@ -465,9 +464,9 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   float step_size = 0.f, bc2_sqrt = 1.f;
   if (OPT == RBPR_OPT_ADAM) {
-    const double s = (double)(p.step + 1);
-    step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, s)));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, s));
+    const float2 t = __ldg(p.adam_tab + (p.step + 1));
+    step_size = t.x;
+    bc2_sqrt = t.y;
   }
   if (p.do_users) {
     for (int64_t k = gid; k < p.n; k += groups) {
@@ -492,7 +491,7 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
         } else {
           float4 m = ld4(p.user_m + r * D + c), vv = ld4(p.user_v + r * D + c);
           if (last > 0 && last < (int64_t)p.step)
-            adam_catchup4(pp, m, vv, last, (int64_t)p.step, p.lr, p.beta1, p.beta2, p.eps);
+            adam_catchup4(pp, m, vv, last, (int64_t)p.step, p.adam_tab, p.beta1, p.beta2, p.eps);
           adam4(pp, m, vv, gr, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
           st4(p.user_m + r * D + c, m);
           st4(p.user_v + r * D + c, vv);
@@ -589,7 +588,8 @@ __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_
                                                        float* __restrict__ user_m,
                                                        float* __restrict__ user_v,
                                                        int32_t* __restrict__ user_last, int64_t U,
-                                                       int D, int64_t step, float lr, float b1,
+                                                       int D, int64_t step,
+                                                       const float2* __restrict__ tab, float b1,
                                                        float b2, float eps) {
   const Group<LANES> g;
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_
       if (c >= D) continue;
       float4 pp = ld4(user_emb + r * D + c), m = ld4(user_m + r * D + c),
              vv = ld4(user_v + r * D + c);
-      adam_catchup4(pp, m, vv, last, step, lr, b1, b2, eps);
+      adam_catchup4(pp, m, vv, last, step, tab, b1, b2, eps);
       st4(user_emb + r * D + c, pp);
       st4(user_m + r * D + c, m);
       st4(user_v + r * D + c, vv);
