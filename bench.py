@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="ml-20m")
     ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--sampler", default="uniform", choices=["uniform", "adaptive"],
+                    help="adaptive = BASELINE configs[3] (Yelp shape, dim 64): sampling_prob 1/100, statistics "
+                         "refreshed every int(I ln I / batch) steps")
     ap.add_argument("--opt", default="sgd", choices=["sgd", "adam"],
                     help="adam = BASELINE configs[2] (MSD shape, dim 256): lr 1e-3, betas (0.9,0.999), reg all=0.00043")
     ap.add_argument("--batch", type=int, default=262144,
@@ -251,7 +254,13 @@ def run_ours(args) -> None:
     else:
         eng.set_reg(REG)
         eng.set_sgd(LR)
-    eng.set_sampler(native.SAMPLER_UNIFORM)
+    if args.sampler == "adaptive":  # experiments/bpr/exp.py:194-207; config default prob 1/100
+        import math
+        every = max(1, int(inter.num_items * math.log(inter.num_items) / args.batch))
+        eng.set_adaptive(0.01, every)
+        eng.adaptive_update_stats()
+    else:
+        eng.set_sampler(native.SAMPLER_UNIFORM)
 
     from rbpr.parallel import DataParallelTrainer, owned_triples
     lo, hi = owned_triples(inter.indptr, world, rank)
@@ -342,7 +351,7 @@ def run_ours(args) -> None:
             "config": {"workload": f"BASELINE configs[1]: synthetic {args.shape} shape "
                                    f"{inter.num_users - 1}x{inter.num_items - 1}, {inter.nnz} interactions, "
                                    f"dim={D}, {'Adam lr=0.001 (dense-Adam semantics, lazy user rows)' if args.opt == 'adam' else f'SGD lr={LR}'}, "
-                                   f"uniform on-device negatives, batch={B} triples/step"
+                                   f"{args.sampler} on-device negatives, batch={B} triples/step"
                                    + (f" per GPU, users sharded by owner over {world} GPUs, one NCCL "
                                       "all-reduce of the dense item gradient per step" if world > 1 else ""),
                        "batch": B, "dim": D, "l2_policy": f"inputs larger than L2: working set "
