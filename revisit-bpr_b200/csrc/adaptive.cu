@@ -4,13 +4,13 @@
 //
 //   adaptive_update_stats : snapshot the item table transposed (D,I), unbiased per-factor std over
 //                           items 1..I-1, sort every factor column once (descending value, ties by
-//                           ascending item id) -> order[f][q], and its inverse pos[f][item].
+//                           ascending item id; one global radix sort on (factor, ~value) keys) -> order[f][q], and its inverse pos[f][item].
 //   sample_adaptive       : per slot: factor ~ Categorical(|u_f| * std_f), rank ~ Geometric(p)
 //                           clamped to the number of unseen items, item = rank-th unseen item in
 //                           the factor's order (from the top if u_f > 0, else from the bottom).
 //                           The rank-th UNSEEN position is the fixed point of
 //                           q <- r + #{masked positions <= q} (masked = seen items and item 0).
-#include <cub/device/device_segmented_radix_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "train_kernels.cuh"
 
@@ -19,8 +19,17 @@ using namespace rbpr_dev;
 namespace {
 
 // snapshot[f][i] = item_emb[i][f]; ids[f][i] = i   (tile transpose through shared memory)
+// key = (factor << 32) | ~monotone(value): ONE global ascending radix sort orders every factor
+// column by descending value; radix sort is stable, so ties keep ascending item id.
+__device__ __forceinline__ uint32_t desc_key(float x) {
+  const uint32_t u = __float_as_uint(x == 0.f ? 0.f : x);  // -0.0 == +0.0
+  const uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~asc;
+}
+
 __global__ void snapshot_transpose(const float* __restrict__ item_emb, int64_t I, int D,
-                                   float* __restrict__ snap, int32_t* __restrict__ ids) {
+                                   float* __restrict__ snap, int32_t* __restrict__ ids,
+                                   uint64_t* __restrict__ keys) {
   __shared__ float tile[32][33];
   const int64_t i0 = (int64_t)blockIdx.x * 32;
   const int f0 = blockIdx.y * 32;
@@ -34,8 +43,10 @@ __global__ void snapshot_transpose(const float* __restrict__ item_emb, int64_t I
     const int f = f0 + r;
     const int64_t i = i0 + threadIdx.x;
     if (f < D && i < I) {
-      snap[(int64_t)f * I + i] = tile[threadIdx.x][r];
+      const float v = tile[threadIdx.x][r];
+      snap[(int64_t)f * I + i] = v;
       ids[(int64_t)f * I + i] = (int32_t)i;
+      keys[(int64_t)f * I + i] = ((uint64_t)f << 32) | (uint64_t)desc_key(v);
     }
   }
 }
@@ -252,40 +263,39 @@ int rbpr_adaptive_update_stats(rbpr_ctx* ctx, void* stream) {
   const int D = ctx->D;
   const size_t cells = (size_t)I * D;
   if (ctx->ad_cells != cells) {
-    cudaFree(ctx->ad_snap); cudaFree(ctx->ad_snap_sorted); cudaFree(ctx->ad_ids);
-    cudaFree(ctx->ad_order); cudaFree(ctx->ad_pos); cudaFree(ctx->ad_std); cudaFree(ctx->ad_offsets);
+    cudaFree(ctx->ad_snap); cudaFree(ctx->ad_keys); cudaFree(ctx->ad_keys_sorted); cudaFree(ctx->ad_ids);
+    cudaFree(ctx->ad_order); cudaFree(ctx->ad_pos); cudaFree(ctx->ad_std);
     cudaFree(ctx->ad_tmp);
-    ctx->ad_snap = ctx->ad_snap_sorted = ctx->ad_std = nullptr;
+    ctx->ad_snap = ctx->ad_std = nullptr;
+    ctx->ad_keys = ctx->ad_keys_sorted = nullptr;
     ctx->ad_ids = ctx->ad_order = ctx->ad_pos = nullptr;
-    ctx->ad_offsets = nullptr;
     ctx->ad_tmp = nullptr;
     ctx->ad_tmp_bytes = 0;
     ctx->ad_cells = 0;
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_snap, cells * 4));
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_snap_sorted, cells * 4));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_keys, cells * 8));
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_keys_sorted, cells * 8));
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_ids, cells * 4));
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_order, cells * 4));
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_pos, cells * 4));
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_std, (size_t)D * 4));
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_offsets, (size_t)(D + 1) * 8));
-    std::vector<int64_t> off(D + 1);
-    for (int f = 0; f <= D; ++f) off[f] = (int64_t)f * I;
-    RBPR_CUDA(ctx, cudaMemcpy(ctx->ad_offsets, off.data(), (size_t)(D + 1) * 8, cudaMemcpyHostToDevice));
     size_t need = 0;
-    cub::DeviceSegmentedRadixSort::SortPairsDescending(
-        nullptr, need, ctx->ad_snap, ctx->ad_snap_sorted, ctx->ad_ids, ctx->ad_order, (int64_t)cells, D,
-        ctx->ad_offsets, ctx->ad_offsets + 1, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->ad_keys, ctx->ad_keys_sorted, ctx->ad_ids,
+                                    ctx->ad_order, (int64_t)cells, 0, 64, st);
     RBPR_CUDA(ctx, cudaMalloc(&ctx->ad_tmp, need > 0 ? need : 16));
     ctx->ad_tmp_bytes = need;
     ctx->ad_cells = cells;
   }
   dim3 grid((unsigned)((I + 31) / 32), (unsigned)((D + 31) / 32));
-  snapshot_transpose<<<grid, dim3(32, 8), 0, st>>>(ctx->item_emb, I, D, ctx->ad_snap, ctx->ad_ids);
+  snapshot_transpose<<<grid, dim3(32, 8), 0, st>>>(ctx->item_emb, I, D, ctx->ad_snap, ctx->ad_ids,
+                                                   ctx->ad_keys);
   factor_std<<<D, 256, 0, st>>>(ctx->ad_snap, I, ctx->ad_std);
   size_t tb = ctx->ad_tmp_bytes;
-  RBPR_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairsDescending(
-                     ctx->ad_tmp, tb, ctx->ad_snap, ctx->ad_snap_sorted, ctx->ad_ids, ctx->ad_order,
-                     (int64_t)cells, D, ctx->ad_offsets, ctx->ad_offsets + 1, 0, 32, st));
+  int fbits = 1;
+  while ((1 << fbits) < D) ++fbits;
+  RBPR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->ad_tmp, tb, ctx->ad_keys, ctx->ad_keys_sorted,
+                                                 ctx->ad_ids, ctx->ad_order, (int64_t)cells, 0,
+                                                 32 + fbits, st));
   invert_order<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(ctx->ad_order, I, D, ctx->ad_pos);
   ctx->launches += 4;
   RBPR_CUDA(ctx, cudaGetLastError());

@@ -71,12 +71,12 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->score_buf);
   cudaFree(ctx->adam_tab);
   cudaFree(ctx->ad_snap);
-  cudaFree(ctx->ad_snap_sorted);
+  cudaFree(ctx->ad_keys);
+  cudaFree(ctx->ad_keys_sorted);
   cudaFree(ctx->ad_std);
   cudaFree(ctx->ad_ids);
   cudaFree(ctx->ad_order);
   cudaFree(ctx->ad_pos);
-  cudaFree(ctx->ad_offsets);
   cudaFree(ctx->ad_tmp);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   delete ctx;

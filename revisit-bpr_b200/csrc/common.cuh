@@ -59,9 +59,9 @@ struct rbpr_ctx {
   int64_t* stage_neg = nullptr;
   int64_t stage_cap = 0;
   // adaptive sampler state (owned): transposed snapshot, per-factor std, sorted order + inverse
-  float *ad_snap = nullptr, *ad_snap_sorted = nullptr, *ad_std = nullptr;
+  float *ad_snap = nullptr, *ad_std = nullptr;
+  uint64_t *ad_keys = nullptr, *ad_keys_sorted = nullptr;
   int32_t *ad_ids = nullptr, *ad_order = nullptr, *ad_pos = nullptr;
-  int64_t* ad_offsets = nullptr;
   void* ad_tmp = nullptr;
   size_t ad_tmp_bytes = 0, ad_cells = 0;
   // score scratch
