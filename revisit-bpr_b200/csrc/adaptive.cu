@@ -91,6 +91,13 @@ __global__ void invert_order(const int32_t* __restrict__ order, int64_t I, int D
   pos[f * I + order[k]] = (int32_t)q;
 }
 
+// lanes per slot: the factor draw is two sequential fp32 passes over D that every lane of the group
+// repeats, so few lanes per slot (more slots per warp) wins; the seen-row scans stride by it
+#ifndef RBPR_ADA_LANES
+#define RBPR_ADA_LANES 8
+#endif
+constexpr int kAdaLanes = RBPR_ADA_LANES;
+
 struct AdaptiveParams {
   const float* __restrict__ user_emb;
   const float* __restrict__ fstd;      // (D)
@@ -104,19 +111,19 @@ struct AdaptiveParams {
   int32_t* __restrict__ flag;
 };
 
-// One group of 8 lanes per slot.  `masked(c)` enumerates the masked items of the slot's user:
+// One group of kAdaLanes lanes per slot.  `masked(c)` enumerates the masked items of the slot's user:
 // c in [0, n_mask) -> item id (0 = padding entries are ignored; item 0 itself is always masked).
 template <typename RowFn>
-__device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const Group<8>& g,
+__device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const Group<kAdaLanes>& g,
                                                  int64_t user, uint32_t sub_lo, uint32_t sub_hi,
                                                  int64_t n_entries, RowFn entry) {
   const int D = p.D;
   const float* urow = p.user_emb + user * D;
   // number of unseen, non-padding items
   int64_t n_seen = 0;
-  for (int64_t c = g.gl; c < n_entries; c += 8) n_seen += (entry(c) != 0);
+  for (int64_t c = g.gl; c < n_entries; c += kAdaLanes) n_seen += (entry(c) != 0);
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) n_seen += __shfl_xor_sync(g.mask, n_seen, o);
+  for (int o = kAdaLanes / 2; o > 0; o >>= 1) n_seen += __shfl_xor_sync(g.mask, n_seen, o);
   const int64_t n_unseen = (p.I - 1) - n_seen;
   if (n_unseen <= 0) {
     if (g.gl == 0) atomicExch(p.flag, 4);
@@ -153,12 +160,12 @@ __device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const 
   int64_t q = r;
   while (true) {
     int64_t c = 0;
-    for (int64_t e = g.gl; e < n_entries; e += 8) {
+    for (int64_t e = g.gl; e < n_entries; e += kAdaLanes) {
       const int64_t it = entry(e);
       c += (it != 0 && (int64_t)prow[it] <= q);
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
+    for (int o = kAdaLanes / 2; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
     c += (pos0 <= q);
     const int64_t nq = r + c;
     if (nq == q) break;
@@ -171,8 +178,8 @@ __global__ void __launch_bounds__(256)
 sample_adaptive_padded(const AdaptiveParams p, const int64_t* __restrict__ users,
                        const int64_t* __restrict__ seen, int64_t B, int64_t S, int64_t num,
                        int64_t U, int64_t* __restrict__ out) {
-  const Group<8> g;
-  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  const Group<kAdaLanes> g;
+  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kAdaLanes;
   if (slot >= B * num) return;
   const int64_t row = slot / num;
   int64_t user = users[row];
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(256)
 rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t* order,
                          const int32_t* pos, double log1m_p, int4* __restrict__ records,
                          uint64_t n_slots, uint64_t step) {
-  const Group<8> g;
-  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  const Group<kAdaLanes> g;
+  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kAdaLanes;
   if (k >= n_slots) return;
   int64_t t64 = __ldg(tp.triple_idx + k);
   if (t64 < 0 || t64 >= tp.nnz) t64 = 0;  // flagged by count_users
@@ -237,7 +244,7 @@ int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void
   if (rc) return rc;
   if (!(sampling_prob > 0.0 && sampling_prob < 1.0))
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "adaptive sampler: adaptive_prob must be in (0,1)");
-  const int64_t threads = n * 8;
+  const int64_t threads = n * kAdaLanes;
   rbpr_sample_adaptive_csr<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
       tp, ctx->ad_std, ctx->ad_order, ctx->ad_pos, log1p(-sampling_prob),
       reinterpret_cast<int4*>(records), (uint64_t)n, step);
@@ -339,7 +346,7 @@ int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64
   p.seed_hi = (uint32_t)(seed >> 32);
   p.step = step;
   p.flag = ctx->flag;
-  const int64_t threads = batch * num * 8;
+  const int64_t threads = batch * num * kAdaLanes;
   sample_adaptive_padded<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       p, users, seen, batch, width, num, ctx->U, neg_out);
   ctx->launches++;
