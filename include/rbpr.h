@@ -13,8 +13,9 @@
  * Ownership: embedding tables, optimizer state and CSR arrays are OWNED BY THE
  * CALLER (PyTorch storages in the shipped host shell); the library borrows the
  * pointers, updates tables in place, and never frees or reallocates them.  The
- * context owns only scratch (sorted batch, dense item-gradient accumulator,
- * touched flags, step statistics).
+ * context owns only scratch (per-wave records and user-occurrence counters, dense item- and
+ * user-gradient accumulators, touched flags, step statistics, the adaptive sampler's snapshot) and
+ * the NCCL communicator.
  *
  * Threading: a context is not thread-safe; one context per device per process.
  * All device work is enqueued on the cudaStream_t passed in (as void*).

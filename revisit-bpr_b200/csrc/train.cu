@@ -538,9 +538,6 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "train: n and batch must be < 2^31 per call");
   if (hp->sampler == RBPR_SAMPLER_INJECTED && !neg_in)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "train: injected sampler needs neg_in");
-  if (hp->sampler == RBPR_SAMPLER_ADAPTIVE && neg_out == nullptr) {
-    // fine: negatives are only reported when asked for
-  }
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t steps = (n + batch - 1) / batch;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU tuning sweep of the training path (not a bench line): per-step device time for
-combinations of batch size, steps per call and the RBPR_CHUNK override.
+a list of batch sizes.
 usage: python scripts/sweep.py [--dim 128] [--shape ml-20m]"""
 import argparse, os, sys, time
 from pathlib import Path
@@ -39,10 +39,6 @@ g = torch.Generator(device=dev).manual_seed(13)
 perm = torch.randperm(inter.nnz, generator=g, device=dev)
 
 def timeit(B, steps, chunk, reps=3):
-    if chunk:
-        os.environ["RBPR_CHUNK"] = str(chunk)
-    else:
-        os.environ.pop("RBPR_CHUNK", None)
     n = min(B * steps, inter.nnz)
     steps = n // B
     t = perm[:steps * B]
