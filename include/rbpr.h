@@ -286,6 +286,19 @@ int rbpr_mask_seen_padded(rbpr_ctx* ctx, float* logits, const int64_t* seen, int
 int rbpr_auc_dense(rbpr_ctx* ctx, const float* scores, const float* target, const float* mask,
                    int64_t n_rows, int64_t n_cols, float* auc_out, void* stream);
 
+/* ---- host-side JSONL ingest (no GPU involved; thread-safe; errors via rbpr_ingest_last_error) ---
+ * One mmap'ed pass over the reference's on-disk files (bin/datasets/format-repro.sh:56-81); other
+ * keys on a line are skipped.  Outputs are malloc'ed int64 arrays released with rbpr_ingest_free.
+ * Replaces the per-line json.loads loops of experiments/bpr/dataset.py:16-24,183-190.
+ *   pairs: {"<key_a>": int, "<key_b>": int}            -> a[n], b[n]
+ *   lists: {"<key_a>": int, "<key_list>": [int, ...]}  -> a[rows], offsets[rows+1], values[...]   */
+int rbpr_ingest_pairs(const char* path, const char* key_a, const char* key_b, int64_t** a_out,
+                      int64_t** b_out, int64_t* n_out);
+int rbpr_ingest_lists(const char* path, const char* key_a, const char* key_list, int64_t** a_out,
+                      int64_t** offsets_out, int64_t** values_out, int64_t* n_rows_out);
+void rbpr_ingest_free(void* p);
+const char* rbpr_ingest_last_error(void);
+
 /* Instrumentation: number of kernels this context has launched so far, and the device time
  * (ms, CUDA events on the launch stream) spent in the dominant training kernel since the
  * last reset, with the number of launches sampled.  Timing is off unless enabled; when on,

@@ -62,28 +62,25 @@ class SparseSamplingInMemoryWithCollator(Dataset):
 
     def __init__(self, path: Path | str, seen_items_path: Path | str, num_users: int, num_items: int,
                  padding_value: float = 0, put_on_cuda: bool = False) -> None:
-        users, items = [], []
-        with Path(path).open("r", encoding="utf-8") as fh:
-            for rec in map(json.loads, fh):
-                users.append(rec["user"])
-                items.append(rec["item"])
-        users_a, items_a = np.asarray(users, dtype=np.int64), np.asarray(items, dtype=np.int64)
-        if users_a.size and (users_a.max() >= num_users or items_a.max() >= num_items or users_a.min() < 0
-                             or items_a.min() < 0):
-            raise IndexError("user / item id outside the (num_users, num_items) matrix")
+        from rbpr import ingest  # native mmap parser (csrc/ingest.cu), no per-line json.loads
+        users_a, items_a = ingest.read_pairs(path, "user", "item")
         # CSR of the de-duplicated matrix, rows ascending: the COO flattening the reference takes
         # from scipy's dok -> csr conversion
-        key = np.unique(users_a * np.int64(num_items) + items_a)
-        coo_u, coo_i = key // num_items, key % num_items
-        self._indptr = np.zeros(num_users + 1, dtype=np.int64)
-        np.cumsum(np.bincount(coo_u, minlength=num_users), out=self._indptr[1:])
-        self._indices = coo_i.astype(np.int32)
+        self._indptr, self._indices, coo_u = ingest.pairs_to_csr(users_a, items_a, num_users, num_items)
         self._user_ids = torch.from_numpy(coo_u)
-        self._item_ids = torch.from_numpy(coo_i)
-        seen: list[torch.Tensor] = [torch.tensor([0]) for _ in range(num_users)]
-        for u, row in _read_seen(seen_items_path).items():
-            seen[u] = torch.tensor(row, dtype=torch.long)
-        self._seen_items = pad_sequence(seen, batch_first=True, padding_value=padding_value)
+        self._item_ids = torch.from_numpy(self._indices.astype(np.int64))
+        # dense 0-padded (num_users, max_seen) matrix of the reference; users without a line: [0]
+        su, soff, svals = ingest.read_lists(seen_items_path, "user", "seen_items")
+        if su.size and (su.min() < 0 or su.max() >= num_users):
+            raise IndexError("user id outside num_users in the seen-items file")
+        lens = np.diff(soff)
+        width = max(1, int(lens.max()) if lens.size else 1)
+        dense = np.full((num_users, width), padding_value, dtype=np.int64)
+        if svals.size:
+            rows = np.repeat(su, lens)
+            cols = np.arange(svals.size) - np.repeat(soff[:-1], lens)
+            dense[rows, cols] = svals
+        self._seen_items = torch.from_numpy(dense)
         self.num_users, self.num_items = num_users, num_items
         if put_on_cuda and torch.cuda.is_available():
             self._user_ids = self._user_ids.cuda()

@@ -23,6 +23,7 @@ SYMBOLS = (
     "rbpr_score_dense", "rbpr_train_step_triples", "rbpr_pair_logits", "rbpr_sample_negatives_padded",
     "rbpr_topk_metrics_dense", "rbpr_mask_seen_padded", "rbpr_auc_dense",
     "rbpr_comm_unique_id", "rbpr_comm_init", "rbpr_comm_allreduce_item_grads", "rbpr_collective_count",
+    "rbpr_ingest_pairs", "rbpr_ingest_lists", "rbpr_ingest_free", "rbpr_ingest_last_error",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
 )
 
@@ -91,6 +92,12 @@ def load() -> C.CDLL:
         "rbpr_comm_init": (C.c_int, [vp, i32, i32, vp]),
         "rbpr_comm_allreduce_item_grads": (C.c_int, [vp, vp]),
         "rbpr_collective_count": (i64, [vp]),
+        "rbpr_ingest_pairs": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(vp),
+                                        C.POINTER(i64)]),
+        "rbpr_ingest_lists": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(vp),
+                                        C.POINTER(vp), C.POINTER(i64)]),
+        "rbpr_ingest_free": (None, [vp]),
+        "rbpr_ingest_last_error": (C.c_char_p, []),
         "rbpr_launch_count": (i64, [vp]),
         "rbpr_kernel_timing": (C.c_int, [vp, i32]),
         "rbpr_kernel_time_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64)]),
