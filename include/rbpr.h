@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 2
+#define RBPR_ABI_VERSION 3
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -265,14 +265,16 @@ int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
  * (ties -> lower column first), hits against `target`, NDCG@k / Recall@k / Precision@k for every
  * cut-off.  Replaces prepare_target (revisit_bpr/metrics/metric.py:110-113: a full argsort per
  * metric), NDCG.compute (metrics/ndcg.py:8-24,69-78; linear_gain selects gain_function="linear"),
- * Recall.compute (metrics/recall.py:44-51), Precision.compute (metrics/precision.py:44-51).
+ * Recall.compute (metrics/recall.py:44-51), Precision.compute (metrics/precision.py:44-51),
+ * MAP.compute (metrics/map.py:45-64; map_normalized selects the min(n_pos,k) denominator).
  * A target value outside {0,1} raises RBPR_ERR_DATA at the next rbpr_sync_check
  * (validate_metric_inputs, metric.py:100-107).  Outputs (n_rows, n_ks) float or NULL;
  * topk_items (n_rows,k_max) int32 or NULL.  Device pointers, contiguous rows. */
 int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
                             int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,
                             int32_t linear_gain, float* ndcg_out, float* recall_out,
-                            float* precision_out, int32_t* topk_items, void* stream);
+                            float* precision_out, float* map_out, int32_t map_normalized,
+                            int32_t* topk_items, void* stream);
 
 /* logits[b, seen[b,c]] = -1e13 and logits[b,0] = -1e13 for the reference's padded seen matrix
  * (batch,width) int64; logits (batch,n_cols) float, in place.  Replaces

@@ -149,6 +149,8 @@ struct TopkParams {
   float* __restrict__ ndcg_out;
   float* __restrict__ recall_out;
   float* __restrict__ precision_out;
+  float* __restrict__ map_out;  // average precision @k (MAP.compute, revisit_bpr/metrics/map.py:45-64)
+  int map_normalized;           // denominator min(n_pos, k) instead of hits@k
   // dense-target mode (revisit_bpr.metrics on (B,I) tensors): positives = target[row, item] > 0
   const float* __restrict__ target;
   int64_t target_ld;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   __syncthreads();
   if (tid < p.n_ks) {
     const int kk = min(min(p.ks[tid], k), KCAP);
-    float ndcg = 0.f, recall = 0.f, precision = 0.f;
+    float ndcg = 0.f, recall = 0.f, precision = 0.f, ap = 0.f;
     if (kk > 0 && n_pos > 0) {
       const float dcg = hit_scan[kk - 1];
       const float idcg = disc_scan[min(kk, n_pos) - 1];
@@ -341,10 +343,23 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
       }
       recall = (float)hits / (float)n_pos;
       precision = (float)hits / (float)kk;
+      if (p.map_out != nullptr) {
+        float acc = 0.f;
+        int cum = 0;
+        for (int r = 0; r < kk; ++r) {
+          if ((hitbits[r >> 5] >> (r & 31)) & 1u) {
+            ++cum;
+            acc += (float)cum / (float)(r + 1);
+          }
+        }
+        const int denom = p.map_normalized ? min(n_pos, kk) : hits;
+        ap = denom > 0 ? acc / (float)denom : 0.f;
+      }
     }
     if (p.ndcg_out) p.ndcg_out[orow * p.n_ks + tid] = ndcg;
     if (p.recall_out) p.recall_out[orow * p.n_ks + tid] = recall;
     if (p.precision_out) p.precision_out[orow * p.n_ks + tid] = precision;
+    if (p.map_out) p.map_out[orow * p.n_ks + tid] = ap;
   }
 }
 
@@ -452,7 +467,8 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
 int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
                             int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,
                             int32_t linear_gain, float* ndcg_out, float* recall_out,
-                            float* precision_out, int32_t* topk_items, void* stream) {
+                            float* precision_out, float* map_out, int32_t map_normalized,
+                            int32_t* topk_items, void* stream) {
   if (!ctx) return RBPR_ERR_ARG;
   if (n_rows == 0) return 0;
   if (!scores || !target || n_rows < 0 || n_cols < 1 || n_cols >= (1ll << 31))
@@ -476,6 +492,8 @@ int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* tar
   tp.ndcg_out = ndcg_out;
   tp.recall_out = recall_out;
   tp.precision_out = precision_out;
+  tp.map_out = map_out;
+  tp.map_normalized = map_normalized;
   tp.target = target;
   tp.target_ld = n_cols;
   tp.linear_gain = linear_gain;

@@ -112,7 +112,8 @@ class Context:
         return out
 
     def topk_metrics_dense(self, output: torch.Tensor, target: torch.Tensor, ks: Sequence[int],
-                           linear_gain: bool = False, want_items: bool = False) -> dict[str, torch.Tensor]:
+                           linear_gain: bool = False, want_items: bool = False,
+                           map_normalized: bool = True) -> dict[str, torch.Tensor]:
         """NDCG / Recall / Precision at every cut-off of `ks` from dense (B,I) scores and targets."""
         output = output.to(self.device, torch.float32).contiguous()
         target = target.to(self.device, torch.float32).contiguous()
@@ -122,12 +123,13 @@ class Context:
         if k_max > native.MAX_TOPK:
             raise ValueError(f"topk={k_max} exceeds the kernel limit {native.MAX_TOPK}")
         out = {name: torch.empty((n, len(ks)), dtype=torch.float32, device=self.device)
-               for name in ("ndcg", "recall", "precision")}
+               for name in ("ndcg", "recall", "precision", "map")}
         items = torch.empty((n, k_max), dtype=torch.int32, device=self.device) if want_items else None
         ks_arr = (C.c_int32 * len(ks))(*ks)
         self._check(self.lib.rbpr_topk_metrics_dense(
             self.ctx, _ptr(output), _ptr(target), n, cols, k_max, ks_arr, len(ks), int(linear_gain),
-            _ptr(out["ndcg"]), _ptr(out["recall"]), _ptr(out["precision"]), _ptr(items), _stream()))
+            _ptr(out["ndcg"]), _ptr(out["recall"]), _ptr(out["precision"]), _ptr(out["map"]),
+            int(map_normalized), _ptr(items), _stream()))
         if want_items:
             out["items"] = items
         return out

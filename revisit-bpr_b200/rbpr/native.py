@@ -11,7 +11,7 @@ OPT_SGD, OPT_ADAM = 0, 1
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
@@ -85,7 +85,7 @@ def load() -> C.CDLL:
         "rbpr_pair_logits": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),
         "rbpr_topk_metrics_dense": (C.c_int, [vp, vp, vp, i64, i64, i32, C.POINTER(i32), i32, i32,
-                                              vp, vp, vp, vp, vp]),
+                                              vp, vp, vp, vp, i32, vp, vp]),
         "rbpr_mask_seen_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, vp]),
         "rbpr_auc_dense": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
         "rbpr_comm_unique_id": (C.c_int, [vp, vp]),

@@ -40,13 +40,13 @@ def validate_metric_inputs(output: torch.Tensor, target: torch.Tensor) -> None:
 
 
 def topk_metrics(output: torch.Tensor, target: torch.Tensor, topk: int, linear_gain: bool = False,
-                 validate: bool = False) -> dict[str, torch.Tensor]:
-    """{'ndcg','recall','precision'} -> (B,) at cut-off min(topk, I)."""
+                 validate: bool = False, map_normalized: bool = True) -> dict[str, torch.Tensor]:
+    """{'ndcg','recall','precision','map'} -> (B,) at cut-off min(topk, I)."""
     if output.dim() != 2:
         raise IndexError(f"metrics expect (users, items) tensors, got {tuple(output.shape)}")
     validate_metric_inputs(output, target)
     ctx = _context(output.device)
-    res = ctx.topk_metrics_dense(output, target, [topk], linear_gain=linear_gain)
+    res = ctx.topk_metrics_dense(output, target, [topk], linear_gain=linear_gain, map_normalized=map_normalized)
     if validate:
         try:
             ctx.sync_check()

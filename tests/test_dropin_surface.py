@@ -35,7 +35,8 @@ def test_exported_names():
         assert hasattr(bpr, n)
     for n in ("Sampler", "UniformSampler", "AdaptiveSampler"):
         assert hasattr(modules, n)
-    for n in ("Metric", "MaskedMetric", "NDCG", "Recall", "Precision"):
+    for n in ("Metric", "MaskedMetric", "NDCG", "Recall", "Precision", "MAP", "FBeta", "RocAucOne", "RocAucMany",
+              "RocAucManySlow"):
         assert hasattr(metrics, n)
     from experiments.trainer import ModelEvents, Trainer
     assert [e.value for e in ModelEvents] == ["forward_started", "forward_completed", "optimizer_started",

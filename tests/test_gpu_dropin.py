@@ -244,6 +244,15 @@ def test_auc_one_fbeta_and_one_pos_collator():
         p, r = Precision(10).compute(o, t), Recall(10).compute(o, t)
         exp = (1 + beta ** 2) * p * r / (beta ** 2 * p + r + 1e-13)
         np.testing.assert_allclose(FBeta(10, beta).compute(o, t).cpu().numpy(), exp.cpu().numpy(), rtol=1e-6)
+    from revisit_bpr.metrics import MAP
+    for k, normalized in ((3, True), (10, True), (10, False), (100, True)):  # map.py:45-64 restated
+        srt = torch.gather(t.cpu(), 1, torch.argsort(-o.cpu(), dim=-1))[:, :k]
+        prec = srt.cumsum(-1) / (torch.arange(srt.size(1)) + 1.0)
+        denom = t.cpu().sum(-1).clamp(max=srt.size(1)) if normalized else srt.sum(-1)
+        exp = torch.nan_to_num((prec * srt).sum(-1) / denom)
+        np.testing.assert_allclose(MAP(k, normalized).compute(o, t).cpu().numpy(), exp.numpy(), atol=1e-6)
+    ko, kt = torch.as_tensor(z["kat_output"]).to(DEV), torch.as_tensor(z["kat_target"]).to(DEV)
+    np.testing.assert_allclose(MAP(3).compute(ko, kt).cpu().numpy(), [0.25, 0.0, 1.0], atol=1e-6)  # SURVEY §4 KAT
     m = FBeta(10)
     m(o, t)
     assert set(m.state_dict()) == {"total_f", "total_count", "precision", "recall"}
