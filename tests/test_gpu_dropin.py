@@ -256,3 +256,43 @@ def test_auc_one_fbeta_and_one_pos_collator():
     m = FBeta(10)
     m(o, t)
     assert set(m.state_dict()) == {"total_f", "total_count", "precision", "recall"}
+
+
+@pytest.mark.parametrize("name", ["adam_all", "adam_bias_ui", "sgd_reg3"])
+def test_checkpoint_resume_reproduces_reference_trajectory(name, tmp_path):
+    """Stop after half of the reference-minted trajectory, torch.save model + optimizer state_dicts
+    (what accelerate.save_state stores, reference options.py:391-400), rebuild everything from the
+    files, finish the trajectory: same losses and final tables as the uninterrupted reference run.
+    Exercises the lazily-updated Adam user rows (flushed by state_dict) and the step counter."""
+    case = load_train_case(name)
+    steps = case["triples"].shape[0]
+    half = steps // 2
+
+    def batch_of(s):
+        t = case["triples"][s]
+        return {"user": torch.as_tensor(case["coo_user"][t], device=DEV),
+                "item": torch.as_tensor(case["indices"][t], dtype=torch.long, device=DEV).unsqueeze(-1),
+                "neg": torch.as_tensor(case["negs"][s], dtype=torch.long, device=DEV).unsqueeze(-1)}
+
+    model, opt = _model_from_case(case)
+    model.bind_optimizer(opt)
+    model.train()
+    for s in range(half):
+        out = model(batch_of(s))
+        np.testing.assert_allclose(out["bpr_loss"].item(), case["bpr_loss"][s], rtol=1e-4)
+    torch.save({"model": model.state_dict(), "optimizer": opt.state_dict()}, tmp_path / "ckpt.pt")
+    del model, opt
+    ckpt = torch.load(tmp_path / "ckpt.pt", map_location=DEV)
+    model2, opt2 = _model_from_case(case)  # fresh objects (initial tables), then restore
+    model2.load_state_dict(ckpt["model"])
+    opt2.load_state_dict(ckpt["optimizer"])
+    model2.bind_optimizer(opt2)
+    model2.train()
+    for s in range(half, steps):
+        out = model2(batch_of(s))
+        np.testing.assert_allclose(out["bpr_loss"].item(), case["bpr_loss"][s], rtol=1e-4)
+    sd = model2.state_dict()
+    np.testing.assert_allclose(sd["logits_model._user_emb.weight"].cpu().numpy(), case["final_user"], atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(sd["logits_model._item_emb.weight"].cpu().numpy(), case["final_item"], atol=1e-5, rtol=1e-4)
+    if case["opt"] == "Adam":
+        assert all(float(v["step"]) == steps for v in opt2.state_dict()["state"].values())
