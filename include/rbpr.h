@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 3
+#define RBPR_ABI_VERSION 4
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -42,7 +42,12 @@ typedef enum {
   RBPR_ERR_COMM = -5   /* NCCL error / libnccl not loadable */
 } rbpr_status;
 
-typedef enum { RBPR_OPT_SGD = 0, RBPR_OPT_ADAM = 1 } rbpr_optimizer;
+typedef enum {
+  RBPR_OPT_SGD = 0,     /* torch.optim.SGD(lr)                                              */
+  RBPR_OPT_ADAM = 1,    /* torch.optim.Adam(lr, betas, eps)                                 */
+  RBPR_OPT_SGDM = 2,    /* torch.optim.SGD(lr, momentum[, nesterov]), dampening 0           */
+  RBPR_OPT_RMSPROP = 3  /* torch.optim.RMSprop(lr, alpha, eps), momentum 0, not centered    */
+} rbpr_optimizer;
 
 typedef enum {
   RBPR_SAMPLER_UNIFORM = 0,  /* uniform over {1..I-1} \ seen(u)                */
@@ -61,7 +66,8 @@ typedef struct {
   int32_t optimizer; /* rbpr_optimizer */
   int32_t sampler;   /* rbpr_sampler   */
   float lr;
-  float beta1, beta2, eps; /* Adam */
+  float beta1, beta2, eps; /* Adam: betas, eps.  SGDM: beta1 = momentum, beta2 != 0 selects nesterov.
+                              RMSprop: beta2 = alpha, eps = eps.  (configs/RQ2/optimizers/*.yaml.j2) */
   float reg_user, reg_item, reg_neg;
   float adaptive_prob;    /* Geometric success probability (AdaptiveSampler sampling_prob)      */
   int32_t adaptive_every; /* refresh the item snapshot after every N-th sampled step (0: never) */
@@ -95,6 +101,12 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
  * torch.optim.Adam keeps (experiments/trainer.py:79). bias_* may be NULL iff no bias. */
 int rbpr_bind_adam_state(rbpr_ctx* ctx, float* user_m, float* user_v, int32_t* user_last_step,
                          float* item_m, float* item_v, float* bias_m, float* bias_v);
+
+/* State of the single-state optimizers (SGDM: momentum_buffer, RMSprop: square_avg), same shapes as
+ * the tables, zero-initialised by the caller; user_last_step as for Adam (lazy dense semantics:
+ * rows without gradient still move / decay, replayed when next touched or at rbpr_flush_lazy). */
+int rbpr_bind_state1(rbpr_ctx* ctx, float* user_s, int32_t* user_last_step, float* item_s,
+                     float* bias_s);
 
 /* Borrow the training interaction matrix in CSR form (device pointers):
  * indptr (U+1,) int64, indices (nnz,) int32 item ids, sorted ascending within a row.

@@ -95,6 +95,8 @@ def make_optimizer(model: RefModel, kind: str, **kw) -> torch.optim.Optimizer:
         return torch.optim.SGD(model.parameters(), **kw)
     if kind == "adam":
         return torch.optim.Adam(model.parameters(), **kw)
+    if kind == "rmsprop":
+        return torch.optim.RMSprop(model.parameters(), **kw)
     raise ValueError(kind)
 
 

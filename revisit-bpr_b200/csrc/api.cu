@@ -117,7 +117,7 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
   ctx->U = num_users;
   ctx->I = num_items;
   ctx->D = dim;
-  ctx->phase_a_blocks_per_sm[0] = ctx->phase_a_blocks_per_sm[1] = 0;
+  for (int o = 0; o < 4; ++o) ctx->phase_a_blocks_per_sm[o] = 0;
   return 0;
 }
 
@@ -135,6 +135,22 @@ int rbpr_bind_adam_state(rbpr_ctx* ctx, float* user_m, float* user_v, int32_t* u
   ctx->item_v = item_v;
   ctx->bias_m = bias_m;
   ctx->bias_v = bias_v;
+  return 0;
+}
+
+int rbpr_bind_state1(rbpr_ctx* ctx, float* user_s, int32_t* user_last_step, float* item_s,
+                     float* bias_s) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!user_s || !user_last_step || !item_s) RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_state1: null pointer");
+  if (((uintptr_t)user_s | (uintptr_t)item_s) & 15u)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_state1: state must be 16-byte aligned");
+  ctx->user_m = user_s;
+  ctx->user_v = nullptr;
+  ctx->user_last = user_last_step;
+  ctx->item_m = item_s;
+  ctx->item_v = nullptr;
+  ctx->bias_m = bias_s;
+  ctx->bias_v = nullptr;
   return 0;
 }
 

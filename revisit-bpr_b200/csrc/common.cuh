@@ -84,7 +84,7 @@ struct rbpr_ctx {
   double timed_ms = 0.0;
   int64_t timed_launches = 0;
   int sm_count = 148;
-  int phase_a_blocks_per_sm[2] = {0, 0};  // per optimizer, for the bound dim (0 = not prepared)
+  int phase_a_blocks_per_sm[4] = {0, 0, 0, 0};  // per optimizer, for the bound dim (0 = not prepared)
 };
 
 #define RBPR_FAIL(ctx, code, ...)                     \

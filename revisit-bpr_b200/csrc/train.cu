@@ -92,8 +92,14 @@ int check_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!hp) RBPR_FAIL(ctx, RBPR_ERR_ARG, "hparams is NULL");
   if (!ctx->user_emb || !ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
-  if (hp->optimizer != RBPR_OPT_SGD && hp->optimizer != RBPR_OPT_ADAM)
+  if (hp->optimizer < RBPR_OPT_SGD || hp->optimizer > RBPR_OPT_RMSPROP)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "unknown optimizer %d", hp->optimizer);
+  if (hp->optimizer == RBPR_OPT_SGDM || hp->optimizer == RBPR_OPT_RMSPROP) {
+    if (!ctx->user_m || !ctx->item_m || !ctx->user_last)
+      RBPR_FAIL(ctx, RBPR_ERR_STATE, "momentum / RMSprop requested but optimizer state not bound");
+    if (ctx->item_bias && !ctx->bias_m)
+      RBPR_FAIL(ctx, RBPR_ERR_STATE, "optimizer state of the item bias not bound");
+  }
   if (hp->optimizer == RBPR_OPT_ADAM) {
     if (!ctx->user_m || !ctx->user_v || !ctx->item_m || !ctx->item_v || !ctx->user_last)
       RBPR_FAIL(ctx, RBPR_ERR_STATE, "Adam requested but Adam state not bound");
@@ -246,11 +252,13 @@ int count_batches(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, int64_t b
 // CTAs of phase A: one lane group per triple, capped at ONE resident wave (the same number of
 // CTAs on every SM; groups then stride over the step's records).
 int pick_blocks(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t n, int lanes, int nv, int* blocks_out) {
-  const int o = hp->optimizer == RBPR_OPT_ADAM ? 1 : 0;
+  const int o = hp->optimizer;
   if (ctx->phase_a_blocks_per_sm[o] == 0) {
     int bps = 0;
-    int rc = o ? rbpr_phase_a_prepare_adam(ctx, ctx->D, lanes, nv, &bps)
-               : rbpr_phase_a_prepare_sgd(ctx, ctx->D, lanes, nv, &bps);
+    int rc = o == RBPR_OPT_ADAM   ? rbpr_phase_a_prepare_adam(ctx, ctx->D, lanes, nv, &bps)
+             : o == RBPR_OPT_SGDM ? rbpr_phase_a_prepare_sgdm(ctx, ctx->D, lanes, nv, &bps)
+             : o == RBPR_OPT_RMSPROP ? rbpr_phase_a_prepare_rms(ctx, ctx->D, lanes, nv, &bps)
+                                     : rbpr_phase_a_prepare_sgd(ctx, ctx->D, lanes, nv, &bps);
     if (rc) return rc;
     if (bps < 1) RBPR_FAIL(ctx, RBPR_ERR_CUDA, "phase-A kernel does not fit on an SM (dim=%d)", ctx->D);
     const char* e = getenv("RBPR_BLOCKS_PER_SM");  // tuning override
@@ -322,9 +330,10 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
   const int64_t need = ((int64_t)p.n + (kPhaseAThreads / lanes) - 1) / (kPhaseAThreads / lanes);
   const int nb = (int)(need < blocks ? (need > 0 ? need : 1) : blocks);
   *launched_blocks = nb;
-  int rc = (hp->optimizer == RBPR_OPT_SGD)
-               ? rbpr_launch_phase_a_sgd(ctx, p, lanes, nv, records, nb, st)
-               : rbpr_launch_phase_a_adam(ctx, p, lanes, nv, records, nb, st);
+  int rc = hp->optimizer == RBPR_OPT_SGD    ? rbpr_launch_phase_a_sgd(ctx, p, lanes, nv, records, nb, st)
+           : hp->optimizer == RBPR_OPT_ADAM ? rbpr_launch_phase_a_adam(ctx, p, lanes, nv, records, nb, st)
+           : hp->optimizer == RBPR_OPT_SGDM ? rbpr_launch_phase_a_sgdm(ctx, p, lanes, nv, records, nb, st)
+                                            : rbpr_launch_phase_a_rms(ctx, p, lanes, nv, records, nb, st);
   if (rc) return rc;
   if (timed) cudaEventRecord(e1, st);
   ctx->launches++;
@@ -363,7 +372,7 @@ int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, i
   a.touched = ctx->touched;
   a.I = ctx->I;
   a.D = ctx->D;
-  a.dense = dense || hp->optimizer == RBPR_OPT_ADAM;
+  a.dense = dense || hp->optimizer != RBPR_OPT_SGD;  // stateful optimizers move every item row
   a.step = step;
   a.lr = hp->lr;
   a.beta1 = hp->beta1;
@@ -372,8 +381,10 @@ int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, i
   a.adam_tab = ctx->adam_tab;
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  int rc = (hp->optimizer == RBPR_OPT_SGD) ? rbpr_launch_apply_sgd(ctx, a, lanes, nv, st)
-                                           : rbpr_launch_apply_adam(ctx, a, lanes, nv, st);
+  int rc = hp->optimizer == RBPR_OPT_SGD    ? rbpr_launch_apply_sgd(ctx, a, lanes, nv, st)
+           : hp->optimizer == RBPR_OPT_ADAM ? rbpr_launch_apply_adam(ctx, a, lanes, nv, st)
+           : hp->optimizer == RBPR_OPT_SGDM ? rbpr_launch_apply_sgdm(ctx, a, lanes, nv, st)
+                                            : rbpr_launch_apply_rms(ctx, a, lanes, nv, st);
   if (rc) return rc;
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
@@ -809,15 +820,17 @@ int rbpr_sync_check(rbpr_ctx* ctx, void* stream) {
 int rbpr_flush_lazy(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* stream) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!hp) RBPR_FAIL(ctx, RBPR_ERR_ARG, "hparams is NULL");
-  if (hp->optimizer != RBPR_OPT_ADAM) return 0;
-  if (!ctx->user_m || !ctx->user_v || !ctx->user_last)
-    RBPR_FAIL(ctx, RBPR_ERR_STATE, "Adam state not bound");
+  if (hp->optimizer == RBPR_OPT_SGD) return 0;
+  if (!ctx->user_m || !ctx->user_last || (hp->optimizer == RBPR_OPT_ADAM && !ctx->user_v))
+    RBPR_FAIL(ctx, RBPR_ERR_STATE, "optimizer state not bound");
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
   int rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, (cudaStream_t)stream);
   if (rc) return rc;
-  rc = rbpr_launch_flush_users(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream);
+  rc = hp->optimizer == RBPR_OPT_ADAM   ? rbpr_launch_flush_users_adam(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream)
+       : hp->optimizer == RBPR_OPT_SGDM ? rbpr_launch_flush_users_sgdm(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream)
+                                        : rbpr_launch_flush_users_rms(ctx, (int64_t)step, hp, lanes, nv, (cudaStream_t)stream);
   if (rc) return rc;
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());

@@ -204,26 +204,50 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
   const float denom = sqrtf(v) / bc2_sqrt + eps;
   p = p - step_size * (m / denom);
 }
-__device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, float4 g, float b1,
-                                      float b2, float eps, float step_size, float bc2_sqrt) {
-  adam1(p.x, m.x, v.x, g.x, b1, b2, eps, step_size, bc2_sqrt);
-  adam1(p.y, m.y, v.y, g.y, b1, b2, eps, step_size, bc2_sqrt);
-  adam1(p.z, m.z, v.z, g.z, b1, b2, eps, step_size, bc2_sqrt);
-  adam1(p.w, m.w, v.w, g.w, b1, b2, eps, step_size, bc2_sqrt);
-}
-
-// Replay Adam steps from+1..to with zero gradient (dense-Adam semantics for a row that received
-// no gradient in those steps).  tab[s] = {lr_s / (1 - beta1^s), sqrt(1 - beta2^s)} for optimizer
-// step s (1-based), computed on the host in double exactly like torch.optim.Adam's scalars and
-// with the learning rate that was in force at step s.
-__device__ __forceinline__ void adam_catchup4(float4& p, float4& m, float4& v, int64_t from,
-                                              int64_t to, const float2* __restrict__ tab, float b1,
-                                              float b2, float eps) {
-  for (int64_t s = from + 1; s <= to; ++s) {
-    const float2 t = __ldg(tab + s);
-    adam4(p, m, v, f4zero(), b1, b2, eps, t.x, t.y);
+// ---- optimizer arithmetic, one element ------------------------------------------------------------
+// OPT selects torch.optim.{SGD, Adam, SGD(momentum[, nesterov]), RMSprop(momentum=0)}.  s1 / s2 are the
+// optimizer state of the element (Adam: exp_avg / exp_avg_sq; SGDM: momentum_buffer; RMSprop:
+// square_avg).  Hyper-parameter slots (rbpr_hparams): SGDM beta1 = momentum, beta2 != 0 = nesterov;
+// RMSprop beta2 = alpha.  A zero-gradient step is the same function with g = 0 (dense semantics).
+struct OptScalars {
+  float lr, b1, b2, eps, step_size, bc2_sqrt;
+};
+template <int OPT>
+__device__ __forceinline__ void opt1(float& p, float& s1, float& s2, float g, const OptScalars& h) {
+  if (OPT == RBPR_OPT_SGD) {
+    p -= h.lr * g;
+  } else if (OPT == RBPR_OPT_ADAM) {
+    adam1(p, s1, s2, g, h.b1, h.b2, h.eps, h.step_size, h.bc2_sqrt);
+  } else if (OPT == RBPR_OPT_SGDM) {  // buf = mu*buf + g ; d = nesterov ? g + mu*buf : buf ; p -= lr*d
+    s1 = s1 * h.b1 + g;
+    p -= h.lr * ((h.b2 != 0.f) ? g + h.b1 * s1 : s1);
+  } else {  // RMSprop: sq = alpha*sq + (1-alpha) g^2 ; p -= lr * g / (sqrt(sq) + eps)
+    s1 = s1 * h.b2 + (1.0f - h.b2) * g * g;
+    p -= h.lr * (g / (sqrtf(s1) + h.eps));
   }
 }
+template <int OPT>
+__device__ __forceinline__ void opt4(float4& p, float4& s1, float4& s2, float4 g, const OptScalars& h) {
+  opt1<OPT>(p.x, s1.x, s2.x, g.x, h);
+  opt1<OPT>(p.y, s1.y, s2.y, g.y, h);
+  opt1<OPT>(p.z, s1.z, s2.z, g.z, h);
+  opt1<OPT>(p.w, s1.w, s2.w, g.w, h);
+}
+// Replay optimizer steps from+1..to with zero gradient (a row that received no gradient in those
+// steps still moves under the dense torch optimizers).  Adam takes its per-step scalars from tab.
+template <int OPT>
+__device__ __forceinline__ void opt_catchup4(float4& p, float4& s1, float4& s2, int64_t from, int64_t to,
+                                             const float2* __restrict__ tab, OptScalars h) {
+  for (int64_t s = from + 1; s <= to; ++s) {
+    if (OPT == RBPR_OPT_ADAM) {
+      const float2 t = __ldg(tab + s);
+      h.step_size = t.x;
+      h.bc2_sqrt = t.y;
+    }
+    opt4<OPT>(p, s1, s2, f4zero(), h);
+  }
+}
+__host__ __device__ constexpr bool opt_has_s2(int opt) { return opt == RBPR_OPT_ADAM; }
 
 constexpr int kPhaseAThreads = 128;
 
@@ -306,11 +330,11 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
 #pragma unroll
   for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
 
-  float step_size = 0.f, bc2_sqrt = 1.f;
+  OptScalars h = {p.lr, p.beta1, p.beta2, p.eps, 0.f, 1.f};
   if (OPT == RBPR_OPT_ADAM) {
     const float2 t = __ldg(p.adam_tab + (p.step + 1));  // 1-based optimizer step being applied
-    step_size = t.x;
-    bc2_sqrt = t.y;
+    h.step_size = t.x;
+    h.bc2_sqrt = t.y;
   }
 
   for (uint32_t k = (blockIdx.x * kPhaseAThreads + threadIdx.x) / LANES; k < n; k += ngroups) {
@@ -328,9 +352,9 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
       vi[v] = colok[v] ? ld4(irow + c) : f4zero();
       vj[v] = colok[v] ? ld4(jrow + c) : f4zero();
     }
-    float4 m[NV], vv[NV];  // Adam moments of the user row (ADAM instantiation only)
-    if (OPT == RBPR_OPT_ADAM) {
-      // Lazy dense-Adam catch-up of the user row to the optimizer steps already taken globally:
+    float4 m[NV], vv[NV];  // optimizer state of the user row (stateful optimizers only)
+    if (OPT != RBPR_OPT_SGD) {
+      // Lazy dense-optimizer catch-up of the user row to the optimizer steps already taken globally:
       // the caught-up row is what every triple of the user must see.  (bpr_apply redoes it for
       // users with several triples, whose row and moments are not written here.)
       const int64_t last = p.user_last[uu];
@@ -343,8 +367,8 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
         for (int v = 0; v < NV; ++v) {
           const int c = 4 * (g.gl + LANES * v);
           m[v] = colok[v] ? ld4(mrow + c) : f4zero();
-          vv[v] = colok[v] ? ld4(vrow + c) : f4zero();
-          if (behind) adam_catchup4(u[v], m[v], vv[v], last, upto, p.adam_tab, p.beta1, p.beta2, p.eps);
+          vv[v] = (opt_has_s2(OPT) && colok[v]) ? ld4(vrow + c) : f4zero();
+          if (behind) opt_catchup4<OPT>(u[v], m[v], vv[v], last, upto, p.adam_tab, h);
         }
       }
     }
@@ -425,13 +449,13 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
         st4(uout + cidx, o);
       } else {
         float4 pp4 = u[v];
-        adam4(pp4, m[v], vv[v], gu, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+        opt4<OPT>(pp4, m[v], vv[v], gu, h);
         st4(uout + cidx, pp4);
         st4(p.user_m + (size_t)uu * D + cidx, m[v]);
-        st4(p.user_v + (size_t)uu * D + cidx, vv[v]);
+        if (opt_has_s2(OPT)) st4(p.user_v + (size_t)uu * D + cidx, vv[v]);
       }
     }
-    if (OPT == RBPR_OPT_ADAM && single && uu != 0) {
+    if (OPT != RBPR_OPT_SGD && single && uu != 0) {
       __syncwarp(g.mask);  // every lane has read user_last before it moves
       if (g.gl == 0) p.user_last[uu] = (int32_t)(p.step + 1);
     }
@@ -462,11 +486,11 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
   const int D = p.D;
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  float step_size = 0.f, bc2_sqrt = 1.f;
+  OptScalars h = {p.lr, p.beta1, p.beta2, p.eps, 0.f, 1.f};
   if (OPT == RBPR_OPT_ADAM) {
     const float2 t = __ldg(p.adam_tab + (p.step + 1));
-    step_size = t.x;
-    bc2_sqrt = t.y;
+    h.step_size = t.x;
+    h.bc2_sqrt = t.y;
   }
   if (p.do_users) {
     for (int64_t k = gid; k < p.n; k += groups) {
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
       float* grow = p.user_grad + r * D;
       float* prow = p.user_emb + r * D;
       int64_t last = 0;
-      if (OPT == RBPR_OPT_ADAM) last = p.user_last[r];
+      if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = 4 * (g.gl + LANES * v);
@@ -489,17 +513,18 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
           pp.z -= p.lr * gr.z;
           pp.w -= p.lr * gr.w;
         } else {
-          float4 m = ld4(p.user_m + r * D + c), vv = ld4(p.user_v + r * D + c);
+          float4 m = ld4(p.user_m + r * D + c);
+          float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
           if (last > 0 && last < (int64_t)p.step)
-            adam_catchup4(pp, m, vv, last, (int64_t)p.step, p.adam_tab, p.beta1, p.beta2, p.eps);
-          adam4(pp, m, vv, gr, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+            opt_catchup4<OPT>(pp, m, vv, last, (int64_t)p.step, p.adam_tab, h);
+          opt4<OPT>(pp, m, vv, gr, h);
           st4(p.user_m + r * D + c, m);
-          st4(p.user_v + r * D + c, vv);
+          if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
         }
         st4(prow + c, pp);
         st4(grow + c, f4zero());
       }
-      if (OPT == RBPR_OPT_ADAM) {
+      if (OPT != RBPR_OPT_SGD) {
         __syncwarp(g.mask);
         if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
       }
@@ -523,10 +548,11 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
         pp.z -= p.lr * gr.z;
         pp.w -= p.lr * gr.w;
       } else {
-        float4 m = ld4(p.item_m + r * D + c), vv = ld4(p.item_v + r * D + c);
-        adam4(pp, m, vv, gr, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+        float4 m = ld4(p.item_m + r * D + c);
+        float4 vv = opt_has_s2(OPT) ? ld4(p.item_v + r * D + c) : f4zero();
+        opt4<OPT>(pp, m, vv, gr, h);
         st4(p.item_m + r * D + c, m);
-        st4(p.item_v + r * D + c, vv);
+        if (opt_has_s2(OPT)) st4(p.item_v + r * D + c, vv);
       }
       st4(prow + c, pp);
       st4(grow + c, f4zero());
@@ -539,10 +565,10 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
         if (OPT == RBPR_OPT_SGD) {
           b -= p.lr * gb;
         } else {
-          float m = p.bias_m[r], vv = p.bias_v[r];
-          adam1(b, m, vv, gb, p.beta1, p.beta2, p.eps, step_size, bc2_sqrt);
+          float m = p.bias_m[r], vv = opt_has_s2(OPT) ? p.bias_v[r] : 0.f;
+          opt1<OPT>(b, m, vv, gb, h);
           p.bias_m[r] = m;
-          p.bias_v[r] = vv;
+          if (opt_has_s2(OPT)) p.bias_v[r] = vv;
         }
         p.item_bias[r] = b;
         p.bias_grad[r] = 0.f;
@@ -582,15 +608,14 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
   }
 }
 
-// Bring all user rows to `step` applied Adam steps (dense semantics), grid-stride over rows.
-template <int LANES, int NV>
+// Bring all user rows to `step` applied optimizer steps (dense semantics), grid-stride over rows.
+template <int LANES, int NV, int OPT>
 __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_emb,
                                                        float* __restrict__ user_m,
                                                        float* __restrict__ user_v,
                                                        int32_t* __restrict__ user_last, int64_t U,
                                                        int D, int64_t step,
-                                                       const float2* __restrict__ tab, float b1,
-                                                       float b2, float eps) {
+                                                       const float2* __restrict__ tab, OptScalars h) {
   const Group<LANES> g;
   const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < U; r += groups) {
@@ -600,12 +625,12 @@ __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_
     for (int v = 0; v < NV; ++v) {
       const int c = 4 * (g.gl + LANES * v);
       if (c >= D) continue;
-      float4 pp = ld4(user_emb + r * D + c), m = ld4(user_m + r * D + c),
-             vv = ld4(user_v + r * D + c);
-      adam_catchup4(pp, m, vv, last, step, tab, b1, b2, eps);
+      float4 pp = ld4(user_emb + r * D + c), m = ld4(user_m + r * D + c);
+      float4 vv = opt_has_s2(OPT) ? ld4(user_v + r * D + c) : f4zero();
+      opt_catchup4<OPT>(pp, m, vv, last, step, tab, h);
       st4(user_emb + r * D + c, pp);
       st4(user_m + r * D + c, m);
-      st4(user_v + r * D + c, vv);
+      if (opt_has_s2(OPT)) st4(user_v + r * D + c, vv);
     }
     __syncwarp(g.mask);
     if (g.gl == 0) user_last[r] = (int32_t)step;
@@ -626,8 +651,18 @@ int rbpr_launch_apply_sgd(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lan
                           cudaStream_t st);
 int rbpr_launch_apply_adam(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,
                            cudaStream_t st);
-int rbpr_launch_flush_users(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv,
-                            cudaStream_t st);
+int rbpr_launch_flush_users_adam(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv,
+                                 cudaStream_t st);
+#define RBPR_DECLARE_OPT_LAUNCHERS(sfx)                                                                     \
+  int rbpr_launch_phase_a_##sfx(rbpr_ctx* ctx, const rbpr_dev::TrainParams& p, int lanes, int nv,           \
+                                const int4* records, int blocks, cudaStream_t st);                          \
+  int rbpr_phase_a_prepare_##sfx(rbpr_ctx* ctx, int dim, int lanes, int nv, int* blocks_per_sm);            \
+  int rbpr_launch_apply_##sfx(rbpr_ctx* ctx, const rbpr_dev::ApplyParams& p, int lanes, int nv,             \
+                              cudaStream_t st);                                                             \
+  int rbpr_launch_flush_users_##sfx(rbpr_ctx* ctx, int64_t step, const rbpr_hparams* hp, int lanes, int nv, \
+                                    cudaStream_t st);
+RBPR_DECLARE_OPT_LAUNCHERS(sgdm)
+RBPR_DECLARE_OPT_LAUNCHERS(rms)
 
 // Instantiate every (LANES, NV) pair rbpr_geometry can return for D in [4,1024], D % 4 == 0.
 #define RBPR_FOR_EACH_GEOMETRY(X) \

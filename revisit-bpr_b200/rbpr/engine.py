@@ -157,6 +157,8 @@ class Engine(Context):
         self.hp.lr = 0.0
         self.hp.beta1, self.hp.beta2, self.hp.eps = 0.9, 0.999, 1e-8
         self.adam_state: dict[str, torch.Tensor] | None = None
+        self.opt_state: dict[str, torch.Tensor] | None = None
+        self.opt_state_kind: str | None = None
         self.indptr = self.indices = None
         self.nnz = 0
         self._pin_stats = self._pin_neg = None
@@ -189,6 +191,34 @@ class Engine(Context):
             _ptr(state["item_m"]), _ptr(state["item_v"]), _ptr(state.get("bias_m")),
             _ptr(state.get("bias_v"))))
         return state
+
+    def _set_state1(self, kind: int, key: str, state: dict[str, torch.Tensor] | None) -> dict[str, torch.Tensor]:
+        """Bind (or create zeroed) single-state optimizer state: user_s, user_last (int32), item_s, bias_s."""
+        self.hp.optimizer = kind
+        if state is None:
+            state = self.opt_state if getattr(self, "opt_state_kind", None) == key else None
+        if state is None:
+            z = torch.zeros_like
+            state = {"user_s": z(self.user_emb), "item_s": z(self.item_emb),
+                     "user_last": torch.zeros(self.U, dtype=torch.int32, device=self.device)}
+            if self.item_bias is not None:
+                state["bias_s"] = z(self.item_bias)
+        self.opt_state, self.opt_state_kind = state, key
+        self._check(self.lib.rbpr_bind_state1(self.ctx, _ptr(state["user_s"]), _ptr(state["user_last"]),
+                                              _ptr(state["item_s"]), _ptr(state.get("bias_s"))))
+        return state
+
+    def set_sgd_momentum(self, lr: float, momentum: float, nesterov: bool = False,
+                         state: dict[str, torch.Tensor] | None = None) -> dict[str, torch.Tensor]:
+        """torch.optim.SGD(lr, momentum, nesterov) with dampening 0 (dense semantics, lazy user rows)."""
+        self.hp.lr, self.hp.beta1, self.hp.beta2 = lr, momentum, 1.0 if nesterov else 0.0
+        return self._set_state1(native.OPT_SGDM, "sgdm", state)
+
+    def set_rmsprop(self, lr: float, alpha: float = 0.99, eps: float = 1e-8,
+                    state: dict[str, torch.Tensor] | None = None) -> dict[str, torch.Tensor]:
+        """torch.optim.RMSprop(lr, alpha, eps) with momentum 0, not centered."""
+        self.hp.lr, self.hp.beta2, self.hp.eps = lr, alpha, eps
+        return self._set_state1(native.OPT_RMSPROP, "rmsprop", state)
 
     def set_sampler(self, kind: int) -> None:
         self.hp.sampler = kind

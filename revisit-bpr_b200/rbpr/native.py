@@ -7,16 +7,16 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent.parent / "librbpr.so"
 
-OPT_SGD, OPT_ADAM = 0, 1
+OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
     "rbpr_abi_version", "rbpr_create", "rbpr_destroy", "rbpr_last_error", "rbpr_bind_tables",
-    "rbpr_bind_adam_state", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_adaptive_update_stats", "rbpr_adaptive_stats",
+    "rbpr_bind_adam_state", "rbpr_bind_state1", "rbpr_bind_csr", "rbpr_bind_item_alias", "rbpr_adaptive_update_stats", "rbpr_adaptive_stats",
     "rbpr_sample_adaptive_padded", "rbpr_sample_negatives",
     "rbpr_train_steps", "rbpr_sync_check", "rbpr_train_steps_host", "rbpr_grad_step",
     "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
         "rbpr_last_error": (C.c_char_p, [vp]),
         "rbpr_bind_tables": (C.c_int, [vp, vp, i64, vp, i64, i32, vp]),
         "rbpr_bind_adam_state": (C.c_int, [vp] * 8),
+        "rbpr_bind_state1": (C.c_int, [vp] * 5),
         "rbpr_bind_csr": (C.c_int, [vp, vp, vp, i64, i64, vp]),
         "rbpr_bind_item_alias": (C.c_int, [vp, vp, vp]),
         "rbpr_adaptive_update_stats": (C.c_int, [vp, vp]),

@@ -144,16 +144,20 @@ class Model(torch.nn.Module):
         if g.get("weight_decay", 0) != 0 or g.get("maximize", False):
             raise NotImplementedError("weight_decay / maximize are not supported by the fused BPR step")
         if isinstance(opt, torch.optim.SGD):
-            if g.get("momentum", 0) != 0 or g.get("dampening", 0) != 0 or g.get("nesterov", False):
-                raise NotImplementedError("SGD momentum is not implemented in the fused BPR step yet")
-            self._opt_kind = native.OPT_SGD
+            if g.get("dampening", 0) != 0:
+                raise NotImplementedError("SGD dampening is not supported by the fused BPR step")
+            self._opt_kind = native.OPT_SGDM if g.get("momentum", 0) != 0 else native.OPT_SGD
+        elif isinstance(opt, torch.optim.RMSprop):
+            if g.get("momentum", 0) != 0 or g.get("centered", False):
+                raise NotImplementedError("RMSprop momentum / centered are not supported by the fused BPR step")
+            self._opt_kind = native.OPT_RMSPROP
         elif isinstance(opt, torch.optim.Adam) and not isinstance(opt, torch.optim.AdamW):
             if g.get("amsgrad", False):
                 raise NotImplementedError("amsgrad is not supported by the fused BPR step")
             self._opt_kind = native.OPT_ADAM
         else:
             raise NotImplementedError(f"{type(opt).__name__} is not implemented in the fused BPR step "
-                                      "(supported: torch.optim.SGD without momentum, torch.optim.Adam)")
+                                      "(supported: torch.optim.SGD [momentum, nesterov], Adam, RMSprop [momentum=0])")
         self._optimizer = opt
         self._adam_last = None
         steps = [int(s["step"]) for s in opt.state.values() if "step" in s]
@@ -184,6 +188,28 @@ class Model(torch.nn.Module):
         state["user_last"] = self._adam_last
         return state
 
+    def _state1(self, eng: Engine, key: str, with_step: bool) -> dict[str, torch.Tensor]:
+        """Single-state optimizers: the state tensors live in `optimizer.state` under torch's own
+        names (`momentum_buffer` / `square_avg`), so optimizer.state_dict() stays interchangeable."""
+        opt = self._optimizer
+        feats = self.logits_model.get_features()
+
+        def slot(p: torch.Tensor) -> torch.Tensor:
+            st = opt.state[p]
+            if st.get(key) is None:
+                st[key] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if with_step:
+                    st["step"] = torch.tensor(float(self._opt_step))
+            return st[key]
+
+        state = {"user_s": slot(feats["user"]), "item_s": slot(feats["item"])}
+        if feats["item_bias"] is not None:
+            state["bias_s"] = slot(feats["item_bias"])
+        if self._adam_last is None or self._adam_last.device != eng.device:
+            self._adam_last = torch.full((eng.U,), self._opt_step, dtype=torch.int32, device=eng.device)
+        state["user_last"] = self._adam_last
+        return state
+
     def _configure(self, eng: Engine) -> None:
         if self._optimizer is None:
             raise RuntimeError(
@@ -194,6 +220,12 @@ class Model(torch.nn.Module):
         eng.set_reg(self._reg_alphas)
         if self._opt_kind == native.OPT_SGD:
             eng.set_sgd(float(g["lr"]))
+        elif self._opt_kind == native.OPT_SGDM:
+            eng.set_sgd_momentum(float(g["lr"]), float(g["momentum"]), bool(g.get("nesterov", False)),
+                                 state=self._state1(eng, "momentum_buffer", with_step=False))
+        elif self._opt_kind == native.OPT_RMSPROP:
+            eng.set_rmsprop(float(g["lr"]), float(g["alpha"]), float(g["eps"]),
+                            state=self._state1(eng, "square_avg", with_step=True))
         else:
             eng.set_adam(float(g["lr"]), tuple(g["betas"]), float(g["eps"]), state=self._adam_state(eng))
 
@@ -202,7 +234,7 @@ class Model(torch.nn.Module):
         """Materialise lazily-deferred optimizer work (dense-Adam catch-up of user rows) and mirror
         the step counter into `optimizer.state`.  Called before eval, state_dict and checkpoints."""
         lm = self.logits_model
-        if self._optimizer is None or self._opt_kind != native.OPT_ADAM or not isinstance(lm, MF):
+        if self._optimizer is None or self._opt_kind in (None, native.OPT_SGD) or not isinstance(lm, MF):
             return
         if lm._engine is None or self._adam_last is None:
             return
@@ -240,6 +272,11 @@ class Model(torch.nn.Module):
         self._opt_step += 1
         stats32 = stats.to(torch.float32)
         pos, ng = logits[:, 0:1], logits[:, 1:2]
+        if lm._user_bias is not None:
+            # the user bias cancels in pos - neg (zero BPR gradient, so it never trains); it only
+            # shifts the two reported logits, like MF.forward does (reference model.py:139-144)
+            ub = lm._user_bias.detach()[user.to(lm._user_bias.device)].unsqueeze(-1)
+            pos, ng = pos + ub, ng + ub
         if self._anchor.device != stats32.device:
             self._anchor = torch.zeros((), requires_grad=True, device=stats32.device)
         bpr_loss, l2_reg = stats32[0], stats32[1]

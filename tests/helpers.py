@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-TRAIN_CASES = ["sgd_reg3", "sgd_bias_all", "sgd_noreg", "adam_all", "adam_bias_ui"]
+TRAIN_CASES = ["sgd_reg3", "sgd_bias_all", "sgd_noreg", "adam_all", "adam_bias_ui", "sgdm_nesterov", "rmsprop"]
 
 
 def load_train_case(name: str) -> dict:

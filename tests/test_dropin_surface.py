@@ -124,10 +124,14 @@ def test_cpu_calls_fail_loudly_and_optimizer_binding_rules():
         modules.UniformSampler(7, torch.Generator().manual_seed(1)).sample(
             {"item": torch.zeros(1, 1, dtype=torch.long), "seen_items": torch.zeros(1, 3, dtype=torch.long)})
     # optimizers the fused step stands in for
-    model.bind_optimizer(torch.optim.SGD(model.parameters(), lr=0.1))
-    model.bind_optimizer(torch.optim.Adam(model.parameters(), lr=0.1, betas=(0.8, 0.9)))
-    for bad in (torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9),
-                torch.optim.RMSprop(model.parameters(), lr=0.1),
+    for good in (torch.optim.SGD(model.parameters(), lr=0.1),
+                 torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True),
+                 torch.optim.Adam(model.parameters(), lr=0.1, betas=(0.8, 0.9)),
+                 torch.optim.RMSprop(model.parameters(), lr=0.1, alpha=0.9)):
+        model.bind_optimizer(good)
+    for bad in (torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, dampening=0.5),
+                torch.optim.RMSprop(model.parameters(), lr=0.1, momentum=0.5),
+                torch.optim.Adagrad(model.parameters(), lr=0.1),
                 torch.optim.Adam(model.parameters(), lr=0.1, weight_decay=0.1)):
         with pytest.raises(NotImplementedError):
             model.bind_optimizer(bad)

@@ -20,8 +20,12 @@ def _engine(case, dev):
     eng.bind_csr(torch.as_tensor(case["indptr"]), torch.as_tensor(case["indices"]))
     eng.set_reg(case["reg"])
     kw = case["opt_kw"]
-    if case["opt"] == "SGD":
+    if case["opt"] == "SGD" and kw.get("momentum", 0) == 0:
         eng.set_sgd(kw["lr"])
+    elif case["opt"] == "SGD":
+        eng.set_sgd_momentum(kw["lr"], kw["momentum"], kw.get("nesterov", False))
+    elif case["opt"] == "RMSprop":
+        eng.set_rmsprop(kw["lr"], kw.get("alpha", 0.99), kw.get("eps", 1e-8))
     else:
         eng.set_adam(kw["lr"], kw.get("betas", (0.9, 0.999)), kw.get("eps", 1e-8))
     eng.set_sampler(native.SAMPLER_INJECTED)
