@@ -118,3 +118,19 @@ def test_attach_metrics_and_early_stopping_host_logic():
         trainer.engines["eval"].run(batches)
         assert trainer.engines["eval"].state.metrics["dot"].item() == 4.0  # reset at every epoch start
     assert es.counter == 3 and trainer.engines["train"].should_terminate
+
+
+def test_library_jsonl_datasets_and_collator(tmp_path):
+    from revisit_bpr.datasets.jsonl import Collator, InMemory, Iter
+    rows = [{"user": 1, "item": 3, "seen_items": [3, 5]}, {"user": 2, "item": 0, "seen_items": [4]},
+            {"user": 3, "item": 1, "seen_items": [9, 8, 7]}]
+    p = tmp_path / "rq1.jsonl"
+    p.write_text("\n".join(json.dumps(r) for r in rows) + "\n")
+    ds = InMemory(p)
+    assert len(ds) == 3 and ds[2] == rows[2] and list(Iter(p)) == rows
+    batch = Collator(pad=["seen_items"])(rows)
+    assert batch["user"].tolist() == [1, 2, 3] and batch["item"].tolist() == [3, 0, 1]
+    assert batch["seen_items"].tolist() == [[3, 5, 0], [4, 0, 0], [9, 8, 7]]
+    assert batch["seen_items_mask"].tolist() == [[1, 1, 0], [1, 0, 0], [1, 1, 1]]
+    loader = torch.utils.data.DataLoader(Iter(p), batch_size=2, collate_fn=Collator(pad=["seen_items"]))
+    assert [b["user"].tolist() for b in loader] == [[1, 2], [3]]
