@@ -146,7 +146,10 @@ class Engine:
         st.dataloader = data
         st.max_epochs = max_epochs if max_epochs is not None else (st.max_epochs or 1)
         if epoch_length is None:
-            epoch_length = len(data) if hasattr(data, "__len__") else None
+            try:  # DataLoader over an IterableDataset has __len__ but raises TypeError
+                epoch_length = len(data)
+            except TypeError:
+                epoch_length = None
         st.epoch_length = epoch_length
         if st.epoch >= st.max_epochs:  # a finished engine restarts from scratch (ignite semantics)
             st.epoch, st.iteration = 0, 0

@@ -159,3 +159,69 @@ def test_auc_and_seen_mask_kernels():
     exp[:, 0] = -1e13
     ctx.mask_seen_padded(logits, seen)
     assert torch.equal(logits.cpu(), exp)
+
+
+RQ1_CONFIG = """
+num_users: &num_users {{ (num_users | int) + 1 }}
+num_items: &num_items {{ (num_items | int) + 1 }}
+epochs: 2
+experiment:
+  _target_: experiments.bpr.Experiment
+  skip_seen: false
+  metrics:
+    auc: {_target_: revisit_bpr.metrics.RocAucOne}
+datasets:
+  train:
+    _target_: torch.utils.data.DataLoader
+    dataset: {_target_: revisit_bpr.datasets.jsonl.Iter, path: {{ dataset }}/rq1-train.jsonl}
+    collate_fn: {_target_: revisit_bpr.datasets.jsonl.Collator, pad: [seen_items]}
+    batch_size: 16
+  eval:
+    _target_: torch.utils.data.DataLoader
+    dataset: {_target_: revisit_bpr.datasets.jsonl.Iter, path: {{ dataset }}/rq1-eval.jsonl}
+    collate_fn: {_target_: experiments.bpr.dataset.OnePosCollator, num_items: *num_items}
+    batch_size: 1
+model:
+  _target_: revisit_bpr.models.bpr.Model
+  fuse_forward: true
+  logits_model:
+    _target_: revisit_bpr.models.bpr.MF
+    user_emb: {_target_: torch.nn.Embedding, num_embeddings: *num_users, embedding_dim: 16, padding_idx: 0}
+    item_emb: {_target_: torch.nn.Embedding, num_embeddings: *num_items, embedding_dim: 16, padding_idx: 0}
+optimizer: {_partial_: true, _target_: torch.optim.SGD, lr: 0.05}
+"""
+
+
+def test_rq1_protocol_config(tmp_path):
+    """configs/RQ1/ours.yaml.j2 shape: jsonl.Iter + Collator(pad) train lines carrying their own
+    seen_items, OnePosCollator eval (one positive vs every unseen item), RocAucOne, skip_seen false."""
+    import jinja2
+    from experiments._instantiate import instantiate
+    inter, train_rows, test_rows = _write_dataset(tmp_path, n_users=40, n_items=50, seed=5)
+    with open(tmp_path / "rq1-train.jsonl", "w") as f:
+        for u, items in train_rows.items():
+            for i in items:
+                f.write(json.dumps({"user": u, "item": i, "seen_items": items}) + "\n")
+    with open(tmp_path / "rq1-eval.jsonl", "w") as f:  # positive = index into the user's seen list
+        for u, items in train_rows.items():
+            f.write(json.dumps({"user": u, "item": len(items) - 1, "seen_items": items}) + "\n")
+    cfg = yaml.safe_load(jinja2.Template(RQ1_CONFIG, undefined=jinja2.StrictUndefined).render(
+        dataset=str(tmp_path), num_users=inter.num_users - 1, num_items=inter.num_items - 1))
+    exp = instantiate(cfg.pop("experiment"), exp_config=lambda: cfg, dir=None, seed=13)
+    exp.run()
+    n_train = sum(len(v) for v in train_rows.values())
+    tr = exp.trainer.engines["train"].state
+    assert tr.epoch == 2 and tr.iteration == 2 * ((n_train + 15) // 16)
+    auc = exp.metrics["auc"].item()
+    # after training, the held positive (an item the user interacted with) outranks unseen items
+    assert 0.55 < auc <= 1.0, auc
+    # and equals the oracle on the final tables
+    sd = exp._model.state_dict()
+    ue, ie = sd["logits_model._user_emb.weight"].cpu(), sd["logits_model._item_emb.weight"].cpu()
+    vals = []
+    for u, items in train_rows.items():
+        pos = items[-1]
+        unseen = [i for i in range(1, inter.num_items) if i not in set(items)]
+        s = ie @ ue[u]
+        vals.append((s[pos] > s[unseen]).float().mean().item())
+    np.testing.assert_allclose(auc, np.mean(vals), atol=1e-4)
