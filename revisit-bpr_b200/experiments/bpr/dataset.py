@@ -152,3 +152,32 @@ class OnePosCollator:
         target[:, 0] = 1.0
         batch["target"] = target
         return batch
+
+
+class EpochChunks:
+    """Loader for the fast path (our extension): instead of B-sized index batches it yields, per
+    epoch, a shuffled permutation of all triple ids in chunks of `steps_per_chunk` steps —
+    `{"triple_idx": ids, "batch_size": B}` — which `revisit_bpr.models.BPR.forward` turns into that
+    many complete training steps in one library call.  The permutation is what
+    `DataLoader(shuffle=True, generator=g)` would draw (reference exp.py:111-115)."""
+
+    def __init__(self, dataset: SparseSamplingInMemoryWithCollator, batch_size: int, steps_per_chunk: int = 64,
+                 generator: torch.Generator | None = None, device: torch.device | str | None = None) -> None:
+        self.dataset, self.batch_size, self.steps_per_chunk = dataset, int(batch_size), int(steps_per_chunk)
+        self.generator, self.device = generator, device
+        self.total_batch_size = self.batch_size
+
+    @property
+    def steps_per_epoch(self) -> int:
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __len__(self) -> int:
+        return (self.steps_per_epoch + self.steps_per_chunk - 1) // self.steps_per_chunk
+
+    def __iter__(self) -> Iterator[dict[str, Any]]:
+        perm = torch.randperm(len(self.dataset), generator=self.generator)
+        if self.device is not None:
+            perm = perm.to(self.device)
+        chunk = self.batch_size * self.steps_per_chunk
+        for a in range(0, perm.numel(), chunk):
+            yield {"triple_idx": perm[a:a + chunk], "batch_size": self.batch_size}

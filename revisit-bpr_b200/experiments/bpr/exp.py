@@ -113,6 +113,11 @@ class BPRExperiment:
         for loader in self._datasets.values():
             if hasattr(loader.dataset, "collate_fn"):
                 loader.collate_fn = loader.dataset.collate_fn
+        # Our extension: `fast_train: true` at the top level of the config replaces the B-sized train
+        # batches by whole chunks of steps run inside the library (device sampling included).
+        self._fast = bool(self._config.get("fast_train", False))
+        if self._fast:
+            self._enable_fast_train(dev)
         self.trainer = self._get_trainer(self._model, self._optimizer, self._datasets)
         # counter-based device sampler: seed + iteration, like the reference's reseeded generator
         self._neg_seed = self._seed + self.trainer.engines["train"].state.iteration
@@ -120,11 +125,31 @@ class BPRExperiment:
         self._sampler_ctx = Context(dev)
         if self._weighted:
             self._sampler_ctx.bind_item_weights(self._item_counts)
-        if self._adaptive:
+        if self._adaptive and not self._fast:
             self._update_adaptive_stats()
         self._state = self.trainer.run(self._datasets, max_iters=max_iters, epochs=self._config["epochs"])
         self._accelerator.wait_for_everyone()
         return self._state
+
+    def _enable_fast_train(self, dev: torch.device) -> None:
+        from experiments.bpr.dataset import EpochChunks, SparseSamplingInMemoryWithCollator
+        loader = self._datasets["train"]
+        ds = loader.dataset
+        if not isinstance(ds, SparseSamplingInMemoryWithCollator):
+            raise NotImplementedError("fast_train needs the SparseSamplingInMemoryWithCollator train dataset")
+        bs = loader.batch_size
+        indptr, indices = ds.csr()
+        kind, every = native.SAMPLER_UNIFORM, 0
+        if self._adaptive:
+            kind = native.SAMPLER_ADAPTIVE
+            every = max(1, int(self._config["num_items"] * math.log(self._config["num_items"]) / bs))
+        elif self._weighted:
+            kind = native.SAMPLER_WEIGHTED
+        self._model.bind_interactions(torch.from_numpy(indptr), torch.from_numpy(indices), sampler=kind,
+                                      seed=self._seed, item_weights=self._item_counts if self._weighted else None,
+                                      adaptive_prob=self._adaptive_sampling_prob, adaptive_every=every)
+        self._datasets["train"] = EpochChunks(ds, bs, steps_per_chunk=int(self._config.get("fast_steps_per_chunk", 64)),
+                                              generator=torch.Generator().manual_seed(self._seed), device=dev)
 
     def interrupt(self) -> None:
         for e in self.trainer.engines.values():
@@ -138,11 +163,12 @@ class BPRExperiment:
     def _get_trainer(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, datasets: dict[str, Any]) -> Trainer:
         trainer = Trainer(model, optimizer=optimizer, accelerator=self._accelerator,
                           custom_engines=self._config.get("custom_engines", {}))
-        if self._adaptive:
+        if self._adaptive and not getattr(self, "_fast", False):
             bs = getattr(datasets["train"], "total_batch_size", None) or datasets["train"].batch_size
             every = max(1, int(self._config["num_items"] * math.log(self._config["num_items"]) / bs))
             trainer.add_event("train", Events.GET_BATCH_COMPLETED(every=every), self._update_adaptive_stats)
-        trainer.add_event("train", Events.GET_BATCH_COMPLETED, self._train_batch)
+        if not getattr(self, "_fast", False):
+            trainer.add_event("train", Events.GET_BATCH_COMPLETED, self._train_batch)
         if self._skip_seen:
             trainer.add_event("eval", ModelEvents.FORWARD_COMPLETED, self._remove_seen_items)
         if self._early_stopping_metric is not None:

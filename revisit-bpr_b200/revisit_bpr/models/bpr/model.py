@@ -257,6 +257,8 @@ class Model(torch.nn.Module):
         if not self.training:
             self.flush()
             return {"logits": lm(inputs["user"], inputs["item"], inputs, mask=inputs.get("mask"))}
+        if "triple_idx" in inputs:
+            return self._forward_triple_ids(inputs)
         user, item, neg = inputs["user"], inputs["item"], inputs["neg"]
         if item.dim() < 2:
             item = item.unsqueeze(-1)
@@ -282,6 +284,46 @@ class Model(torch.nn.Module):
         bpr_loss, l2_reg = stats32[0], stats32[1]
         return {"logits_pos": pos, "logits_neg": ng, "logits": pos - ng, "bpr_loss": bpr_loss,
                 "l2_reg": l2_reg, "loss": _AppliedStep.apply(self._anchor, bpr_loss + l2_reg)}
+
+    # ---- fast path: whole runs of steps from triple ids (our extension, not in the reference) -----
+    def bind_interactions(self, indptr: torch.Tensor, indices: torch.Tensor, sampler: int = native.SAMPLER_UNIFORM,
+                          seed: int = 13, item_weights: torch.Tensor | None = None,
+                          adaptive_prob: float | None = None, adaptive_every: int = 0) -> None:
+        """Give the model the training interaction matrix (CSR) and the negative-sampler settings, so
+        that `forward({"triple_idx": ids, "batch_size": B})` can run ceil(len(ids)/B) complete training
+        steps (device sampling, update) in ONE library call (rbpr_train_steps)."""
+        eng = self.logits_model.engine()
+        eng.bind_csr(indptr, indices)
+        if item_weights is not None:
+            eng.bind_item_weights(item_weights)
+        self._fast = {"sampler": sampler, "seed": int(seed), "adaptive_prob": adaptive_prob,
+                      "adaptive_every": int(adaptive_every), "stats_ready": False}
+
+    def _forward_triple_ids(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        fast = getattr(self, "_fast", None)
+        if fast is None:
+            raise RuntimeError("forward with 'triple_idx' needs model.bind_interactions(indptr, indices) first")
+        eng = self.logits_model.engine()
+        self._configure(eng)
+        if fast["sampler"] == native.SAMPLER_ADAPTIVE:
+            eng.set_adaptive(fast["adaptive_prob"], fast["adaptive_every"])
+            if not fast["stats_ready"]:
+                eng.adaptive_update_stats()
+                fast["stats_ready"] = True
+        else:
+            eng.set_sampler(fast["sampler"])
+        ids = inputs["triple_idx"].to(eng.device, torch.int64).contiguous()
+        batch = int(inputs["batch_size"])
+        stats, _ = eng.train_steps(ids, batch, fast["seed"], self._opt_step)
+        steps = stats.size(0)
+        self._opt_step += steps
+        st = stats.to(torch.float32)
+        if self._anchor.device != st.device:
+            self._anchor = torch.zeros((), requires_grad=True, device=st.device)
+        # per-step means over the call, so running means over "iterations" keep the per-step scale
+        bpr_loss, l2_reg = st[:, 0].mean(), st[:, 1].mean()
+        return {"bpr_loss": bpr_loss, "l2_reg": l2_reg, "loss": _AppliedStep.apply(self._anchor, bpr_loss + l2_reg),
+                "logits": (st[:, 2].sum() / st[:, 3].sum()).reshape(1, 1), "steps": steps, "step_stats": stats}
 
     @torch.no_grad()
     def regularization(self, inputs: dict[str, torch.Tensor]) -> torch.Tensor:

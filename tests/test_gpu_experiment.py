@@ -225,3 +225,40 @@ def test_rq1_protocol_config(tmp_path):
         s = ie @ ue[u]
         vals.append((s[pos] > s[unseen]).float().mean().item())
     np.testing.assert_allclose(auc, np.mean(vals), atol=1e-4)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_fast_train_extension_runs_whole_chunks_inside_the_library(tmp_path, adaptive):
+    """`fast_train: true` (our extension key): the same reference-schema config, but the train loader
+    hands over whole chunks of steps as triple ids and the library samples and trains them in one
+    call per chunk.  Same bookkeeping surface (Trainer events, running losses, eval metrics)."""
+    from experiments._instantiate import instantiate
+    from oracle import ref_bpr
+    inter, train_rows, test_rows = _write_dataset(tmp_path)
+    cfg = _render(tmp_path, num_users=inter.num_users - 1, num_items=inter.num_items - 1, epochs=4, adaptive=adaptive,
+                  train_batch_size=64, embedding_dim=16, optimizer="torch.optim.SGD", lr=0.05, item_bias="true")
+    cfg["fast_train"] = True
+    cfg["fast_steps_per_chunk"] = 4
+    exp_cfg = cfg.pop("experiment")
+    exp = instantiate(exp_cfg, exp_config=lambda: cfg, dir=None, debug=False, seed=13, trackers_params={})
+    exp.run()
+    n_train = sum(len(v) for v in train_rows.values())
+    steps_per_epoch = (n_train + 63) // 64
+    tr = exp.trainer.engines["train"].state
+    assert tr.epoch == 4 and tr.iteration == 4 * ((steps_per_epoch + 3) // 4)  # iterations are chunks
+    assert exp._model._opt_step == 4 * steps_per_epoch                        # ... steps are steps
+    for k in ("loss", "bpr_loss", "l2_reg", "logits_diff"):
+        assert np.isfinite(tr.metrics[k].item()), k
+    assert tr.metrics["bpr_loss"].item() < 64 * np.log(2)  # per-step scale, and it learned something
+    sd = exp._model.state_dict()
+    ref = ref_bpr.RefModel(sd["logits_model._user_emb.weight"].cpu(), sd["logits_model._item_emb.weight"].cpu(),
+                           sd["logits_model._item_bias"].cpu())
+    users = sorted(test_rows)
+    seen_pad = torch.nn.utils.rnn.pad_sequence([torch.as_tensor(train_rows[u]) for u in users], batch_first=True)
+    logits = ref.eval_logits(torch.as_tensor(users), seen_pad)
+    target = torch.zeros(len(users), inter.num_items)
+    for r, u in enumerate(users):
+        target[r, torch.as_tensor(test_rows[u])] = 1.0
+    np.testing.assert_allclose(exp.metrics["ndcg@10"].item(), ref_bpr.ndcg_at_k(logits, target, 10).mean().item(), atol=1e-4)
+    np.testing.assert_allclose(exp.metrics["recall@20"].item(), ref_bpr.recall_at_k(logits, target, 20).mean().item(), atol=1e-4)
+    assert exp.metrics["auc"].item() > 0.5
