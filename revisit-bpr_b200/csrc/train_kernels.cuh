@@ -337,8 +337,13 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
     h.bc2_sqrt = t.y;
   }
 
-  for (uint32_t k = (blockIdx.x * kPhaseAThreads + threadIdx.x) / LANES; k < n; k += ngroups) {
-    const int4 rec = __ldg(records + k);
+  // the next record of the group is fetched one iteration ahead: its latency hides behind this
+  // triple's row loads instead of heading the next iteration's dependent chain
+  uint32_t k = (blockIdx.x * kPhaseAThreads + threadIdx.x) / LANES;
+  int4 rec_next = (k < n) ? __ldg(records + k) : make_int4(0, 0, 0, 0);
+  for (; k < n; k += ngroups) {
+    const int4 rec = rec_next;
+    if (k + ngroups < n) rec_next = __ldg(records + k + ngroups);
     const int32_t uu = rec.x, i = rec.y, j = rec.z;
     const bool single = (rec.w & kRecSingle) != 0;
     const float* urow = p.user_emb + (size_t)uu * D;
