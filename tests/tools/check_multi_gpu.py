@@ -3,7 +3,7 @@
 with >= 2 GPUs):  W ranks x their share of a global batch  ==  the closed-form oracle on the whole
 batch (sum-reduced loss), item replicas bit-identical across ranks, user rows only on their owner.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29533 scripts/check_multi_gpu.py
+      --master-port 29533 tests/tools/check_multi_gpu.py
 """
 import os
 import sys
@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "revisit-bpr_b200"))
 from oracle import closed, philox  # noqa: E402  (checker only)
 from oracle.ref_bpr import resolve_reg  # noqa: E402

@@ -2,12 +2,12 @@
 """Config 5 of BASELINE.json: full-catalog scoring + NDCG@100 / Recall@20 on the ML-20M shape
 (10 000 held-out users, 20 % of each user's items held out), our kernels vs the reference's eval
 op sequence on the host cores (oracle port).  Diagnostic numbers for DESIGN.md, not the bench line.
-usage: python scripts/score_bench.py [--users 10000] [--dim 128]"""
+usage: python tests/tools/score_bench.py [--users 10000] [--dim 128]"""
 import argparse, json, os, sys, time
 from pathlib import Path
 import numpy as np
 import torch
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "revisit-bpr_b200"))
 import bench
 from rbpr import synth
