@@ -4,12 +4,12 @@ epochs) -> State`, `ModelEvents`, the same event order inside a step, eval on EP
 COMPLETED of the train engine, running-mean loss in `state.metrics["loss"]`.
 
 The step itself is the CUDA path: `model(batch)` in train mode performs forward, backward and the
-optimizer update in the fused kernels (revisit_bpr.models.bpr.Model), so `accelerator.backward`,
-`optimizer.step` and `optimizer.zero_grad` below do no work — they stay so that handlers attached
-to OPTIMIZER_STARTED / OPTIMIZER_COMPLETED and non-fused models keep their meaning."""
+optimizer update in the fused kernels (revisit_bpr.models.bpr.Model), so the `accelerator.backward`,
+`optimizer.step` and `optimizer.zero_grad` calls below do no work — they stay so that handlers
+attached to OPTIMIZER_STARTED / OPTIMIZER_COMPLETED and non-fused models keep their meaning."""
 from __future__ import annotations
 
-from copy import deepcopy
+import copy
 from typing import Any, Callable
 
 import torch
@@ -19,8 +19,6 @@ try:  # the real packages when present
 except ImportError:  # this image: stand-ins with the API subset used here
     from experiments._engine import Engine, EventEnum, Events, State
 
-_COUNTERS = ("name", "forward_iteration", "optimizer_iteration", "epoch_iteration", "was_interrupted")
-
 
 class ModelEvents(EventEnum):
     FORWARD_STARTED = "forward_started"
@@ -29,93 +27,91 @@ class ModelEvents(EventEnum):
     OPTIMIZER_COMPLETED = "optimizer_completed"
 
 
+# counter attribute of engine.state that each custom event advances / filters on
+_EVENT_COUNTER = {ModelEvents.FORWARD_STARTED: "forward_iteration", ModelEvents.FORWARD_COMPLETED: "forward_iteration",
+                  ModelEvents.OPTIMIZER_STARTED: "optimizer_iteration",
+                  ModelEvents.OPTIMIZER_COMPLETED: "optimizer_iteration"}
+# engine.state attributes that belong to a checkpoint of the engine
+_PERSISTED = ("name", "forward_iteration", "optimizer_iteration", "epoch_iteration", "was_interrupted")
+
+
 class Trainer:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, accelerator: Any,
                  custom_engines: dict[str, str] | None = None) -> None:
-        self.model = model
-        self.optimizer = optimizer
-        self._accelerator = accelerator
-        bind = getattr(getattr(model, "module", model), "bind_optimizer", None)
-        if bind is not None:  # the fused CUDA step stands in for this optimizer
-            bind(optimizer)
+        self.model, self.optimizer, self._accelerator = model, optimizer, accelerator
+        fused = getattr(getattr(model, "module", model), "bind_optimizer", None)
+        if fused is not None:  # the fused CUDA step stands in for this optimizer
+            fused(optimizer)
         self.engines = {"train": Engine(self._train_step), "eval": Engine(self._eval_step)}
-        for name, base in (custom_engines or {}).items():
-            self.engines[name] = deepcopy(self.engines[base])
-        attr = {ModelEvents.FORWARD_STARTED: "forward_iteration", ModelEvents.FORWARD_COMPLETED: "forward_iteration",
-                ModelEvents.OPTIMIZER_STARTED: "optimizer_iteration",
-                ModelEvents.OPTIMIZER_COMPLETED: "optimizer_iteration"}
-        for name, eng in self.engines.items():
-            eng.register_events(*ModelEvents, event_to_attr=attr)
-            eng.state.name = name
-            eng.state.was_interrupted = False
-            eng.state.epoch_iteration = 0
-            eng.state_dict_user_keys.extend(_COUNTERS)
+        for alias, source in (custom_engines or {}).items():
+            self.engines[alias] = copy.deepcopy(self.engines[source])
+        # handler order as in the reference: the eval pass first, then the per-engine bookkeeping
         self.add_event("train", Events.EPOCH_STARTED | Events.COMPLETED, self._run_eval)
-        for name in self.engines:
-            self.add_event(name, Events.EPOCH_STARTED, self._reset_epoch)
-            self.add_event(name, Events.ITERATION_COMPLETED, self._count_iteration)
-            self.add_event(name, Events.ITERATION_COMPLETED, self._mean_loss)
+        for label, engine in self.engines.items():
+            self._prepare_engine(label, engine)
+
+    def _prepare_engine(self, label: str, engine: Engine) -> None:
+        engine.register_events(*ModelEvents, event_to_attr=_EVENT_COUNTER)
+        st = engine.state
+        st.name, st.was_interrupted, st.epoch_iteration = label, False, 0
+        engine.state_dict_user_keys.extend(_PERSISTED)
+        engine.add_event_handler(Events.EPOCH_STARTED, self._on_epoch_started)
+        engine.add_event_handler(Events.ITERATION_COMPLETED, self._on_iteration_completed)
 
     def add_event(self, engine: str, event_name: Any, handler: Callable, *args: Any, **kwargs: Any) -> None:
         self.engines[engine].add_event_handler(event_name, handler, *args, **kwargs)
 
     def run(self, loaders: dict[str, Any], max_iters: dict[str, int] | None = None,
             epochs: int | None = None) -> State:
-        self._loaders = loaders
-        self._max_iters = max_iters or {}
-        self.engines["train"].run(loaders["train"], epoch_length=self._max_iters.get("train"), max_epochs=epochs)
+        self._loaders, self._max_iters = loaders, dict(max_iters or {})
+        self.engines["train"].run(loaders["train"], max_epochs=epochs, epoch_length=self._max_iters.get("train"))
         return self.engines["eval" if "eval" in loaders else "train"].state
 
-    # ---- steps ---------------------------------------------------------------------------------
+    # ---- one step --------------------------------------------------------------------------------
+    def _forward(self, engine: Engine, batch: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        engine.state.forward_iteration += 1
+        engine.fire_event(ModelEvents.FORWARD_STARTED)
+        engine.state.output = self.model(batch)
+        engine.fire_event(ModelEvents.FORWARD_COMPLETED)
+        return engine.state.output
+
     def _train_step(self, engine: Engine, batch: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
         self.model.train()
-        state = engine.state
         with self._accelerator.accumulate(self.model):
-            state.forward_iteration += 1
-            engine.fire_event(ModelEvents.FORWARD_STARTED)
-            output = state.output = self.model(batch)  # fused: loss, gradients AND update
-            engine.fire_event(ModelEvents.FORWARD_COMPLETED)
-            if "loss" not in output:
-                return output
-            self._accelerator.backward(output["loss"])
-            state.optimizer_iteration += 1
-            engine.fire_event(ModelEvents.OPTIMIZER_STARTED)
-            self.optimizer.step()
-            engine.fire_event(ModelEvents.OPTIMIZER_COMPLETED)
-            self.optimizer.zero_grad()
-            state.metrics["_loss"] += output["loss"].detach()
-        return output
+            out = self._forward(engine, batch)  # fused model: loss, gradients AND the update
+            if "loss" in out:
+                self._accelerator.backward(out["loss"])
+                engine.state.optimizer_iteration += 1
+                engine.fire_event(ModelEvents.OPTIMIZER_STARTED)
+                self.optimizer.step()
+                engine.fire_event(ModelEvents.OPTIMIZER_COMPLETED)
+                self.optimizer.zero_grad()
+                engine.state.metrics["_loss"] += out["loss"].detach()
+        return out
 
     @torch.no_grad()
     def _eval_step(self, engine: Engine, batch: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
         self.model.eval()
-        state = engine.state
-        state.forward_iteration += 1
-        engine.fire_event(ModelEvents.FORWARD_STARTED)
-        output = state.output = self.model(batch)
-        engine.fire_event(ModelEvents.FORWARD_COMPLETED)
-        if "loss" in output:
-            state.metrics["_loss"] += output["loss"].detach()
-        return output
+        out = self._forward(engine, batch)
+        if "loss" in out:
+            engine.state.metrics["_loss"] += out["loss"].detach()
+        return out
 
-    # ---- bookkeeping handlers --------------------------------------------------------------------
+    # ---- bookkeeping -----------------------------------------------------------------------------
     def _run_eval(self) -> None:
-        train, ev = self.engines["train"].state, self.engines["eval"].state
-        if train.was_interrupted and not ev.was_interrupted:
-            return  # resumed after an interruption that hit the train engine: eval already ran
-        loader = self._loaders.get("eval")
-        if loader is not None:
+        # an eval pass runs before every train epoch and once after training; when a resumed run was
+        # interrupted inside the TRAIN engine its eval pass had already finished
+        if self.engines["train"].state.was_interrupted and not self.engines["eval"].state.was_interrupted:
+            return
+        if (loader := self._loaders.get("eval")) is not None:
             self.engines["eval"].run(loader, epoch_length=self._max_iters.get("eval"))
 
-    def _reset_epoch(self, engine: Engine) -> None:
-        if engine.state.was_interrupted:
-            return
-        engine.state.metrics["_loss"] = torch.tensor(0.0, device=self._accelerator.device)
-        engine.state.epoch_iteration = 0
+    def _on_epoch_started(self, engine: Engine) -> None:
+        if not engine.state.was_interrupted:
+            engine.state.epoch_iteration = 0
+            engine.state.metrics["_loss"] = torch.tensor(0.0, device=self._accelerator.device)
 
-    def _count_iteration(self, engine: Engine) -> None:
-        engine.state.epoch_iteration += 1
-
-    def _mean_loss(self, engine: Engine) -> None:
-        m = engine.state.metrics
-        m["loss"] = m["_loss"] / engine.state.epoch_iteration
+    def _on_iteration_completed(self, engine: Engine) -> None:
+        st = engine.state
+        st.epoch_iteration += 1
+        st.metrics["loss"] = st.metrics["_loss"] / st.epoch_iteration

@@ -6,7 +6,6 @@ batch dict these produce)."""
 from __future__ import annotations
 
 import json
-from itertools import islice
 from pathlib import Path
 from typing import Any, Iterator
 
@@ -15,10 +14,17 @@ from torch.nn.utils.rnn import pad_sequence
 from torch.utils.data import Dataset, IterableDataset, get_worker_info
 
 
+def _objects(path: Path, first: int = 0, stride: int = 1) -> Iterator[dict[str, Any]]:
+    """Objects of lines first, first+stride, ... of a JsonLines file."""
+    with path.open("r", encoding="utf-8") as fh:
+        for number, line in enumerate(fh):
+            if number >= first and (number - first) % stride == 0:
+                yield json.loads(line)
+
+
 class InMemory(Dataset):
     def __init__(self, path: Path | str) -> None:
-        with Path(path).open("r", encoding="utf-8") as fh:
-            self._samples = [json.loads(line) for line in fh]
+        self._samples = list(_objects(Path(path)))
 
     def __len__(self) -> int:
         return len(self._samples)
@@ -28,17 +34,16 @@ class InMemory(Dataset):
 
 
 class Iter(IterableDataset):
-    """Streams the file; with DataLoader workers, worker w reads lines w, w+W, w+2W, ..."""
+    """Streams the file; with W DataLoader workers, worker w reads lines w, w+W, w+2W, ..."""
 
     def __init__(self, path: Path | str) -> None:
         self._path = Path(path)
 
     def __iter__(self) -> Iterator[dict[str, Any]]:
         info = get_worker_info()
-        start, step = (info.id, info.num_workers) if info is not None and info.num_workers > 0 else (0, 1)
-        with self._path.open("r", encoding="utf-8") as fh:
-            for line in islice(fh, start, None, step):
-                yield json.loads(line)
+        if info is None or info.num_workers <= 0:
+            return _objects(self._path)
+        return _objects(self._path, info.id, info.num_workers)
 
 
 class Collator:
@@ -46,18 +51,18 @@ class Collator:
         self._pad = set(pad or [])
         self._padding_value = padding_value
 
+    def _column(self, key: str, values: list[Any]) -> torch.Tensor:
+        if key not in self._pad:
+            return torch.tensor(values)
+        rows = [torch.as_tensor(v) for v in values]
+        return pad_sequence(rows, batch_first=True, padding_value=self._padding_value)
+
     def __call__(self, instances: list[dict[str, Any]]) -> dict[str, torch.Tensor]:
         columns: dict[str, list[Any]] = {}
         for inst in instances:
             for key, value in inst.items():
                 columns.setdefault(key, []).append(value)
-        batch: dict[str, torch.Tensor] = {}
-        for key, values in columns.items():
-            if key in self._pad:
-                batch[key] = pad_sequence([torch.as_tensor(v) for v in values], batch_first=True,
-                                          padding_value=self._padding_value)
-            else:
-                batch[key] = torch.tensor(values)
+        batch = {key: self._column(key, values) for key, values in columns.items()}
         for key in self._pad:
             batch[f"{key}_mask"] = batch[key].ne(self._padding_value).float()
         return batch

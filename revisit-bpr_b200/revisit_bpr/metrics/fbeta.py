@@ -1,54 +1,35 @@
-"""F-beta@k (reference revisit_bpr/metrics/fbeta.py:8-73): (1+b^2)·P·R / (b^2·P + R + 1e-13) from the
-Precision@k and Recall@k of the same top-k pass (one kernel call yields both)."""
+"""F-beta@k: (1 + b^2) * P * R / (b^2 * P + R + 1e-13) per user, from the Precision@k and Recall@k of
+ONE top-k pass of the CUDA kernel (reference behaviour: revisit_bpr/metrics/fbeta.py:8-73, which
+evaluates two separate metric objects and therefore sorts twice)."""
 from __future__ import annotations
 
 from typing import Any
 
 import torch
 
-from revisit_bpr.metrics.metric import Metric, topk_metrics
-from revisit_bpr.metrics.precision import Precision
-from revisit_bpr.metrics.recall import Recall
+from revisit_bpr.metrics.metric import _TopkMean, topk_metrics
 
 
-class FBeta(Metric):
+class FBeta(_TopkMean):
+    _key = "f"
+
     def __init__(self, topk: int, beta: float = 1.0) -> None:
-        assert topk > 0, f"Invalid topk value: {topk}"
-        self._topk = topk
+        super().__init__(topk)
         self._beta = beta
-        self._precision = Precision(self._topk)
-        self._recall = Recall(self._topk)
-        self._total_f = self._total_count = 0
-
-    def state_dict(self) -> dict[str, Any]:
-        return {"total_f": self._total_f, "total_count": self._total_count,
-                "precision": self._precision.state_dict(), "recall": self._recall.state_dict()}
-
-    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        self._total_f, self._total_count = state_dict["total_f"], state_dict["total_count"]
-        self._precision.load_state_dict(state_dict["precision"])
-        self._recall.load_state_dict(state_dict["recall"])
-        if self.accelerator is None:
-            return
-        self._total_f = self._total_f.to(self.accelerator.device)
-        self._total_count = self._total_count.to(self.accelerator.device)
-
-    def __call__(self, output: torch.Tensor, target: torch.Tensor) -> None:
-        self._total_count += torch.tensor(target.size(0), device=output.device)
-        self._total_f += self.compute(output, target).sum()
 
     def compute(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        res = topk_metrics(output, target, self._topk, validate=True)
-        p, r, b2 = res["precision"], res["recall"], self._beta ** 2
-        return (1.0 + b2) * p * r / (b2 * p + r + 1e-13)
+        both = topk_metrics(output, target, self._topk, validate=True)
+        b2 = self._beta * self._beta
+        num = (1.0 + b2) * both["precision"] * both["recall"]
+        return num / (b2 * both["precision"] + both["recall"] + 1e-13)
 
-    def get_metric(self, reset: bool = False) -> torch.Tensor:
-        metric = self._total_f / self._total_count
-        if reset:
-            self.reset()
-        return metric
+    # The reference keeps (never updated) Precision / Recall sub-metrics in its state; their entries
+    # are reproduced so that checkpoints written by either implementation load in the other.
+    def state_dict(self) -> dict[str, Any]:
+        state = super().state_dict()
+        state["precision"] = {"total_precision": 0, "total_count": 0}
+        state["recall"] = {"total_recall": 0, "total_count": 0}
+        return state
 
-    def reset(self) -> None:
-        device = torch.device("cpu") if self.accelerator is None else self.accelerator.device
-        self._total_f = torch.tensor(0.0, device=device)
-        self._total_count = torch.tensor(0.0, device=device)
+    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        super().load_state_dict({k: v for k, v in state_dict.items() if k in ("total_f", "total_count")})
