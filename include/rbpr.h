@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 4
+#define RBPR_ABI_VERSION 5
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -299,6 +299,41 @@ int rbpr_mask_seen_padded(rbpr_ctx* ctx, float* logits, const int64_t* seen, int
  * (revisit_bpr/metrics/auc.py:149-166).  auc_out (n_rows,) float.  Device pointers. */
 int rbpr_auc_dense(rbpr_ctx* ctx, const float* scores, const float* target, const float* mask,
                    int64_t n_rows, int64_t n_cols, float* auc_out, void* stream);
+
+/* ---- item-neighbourhood logits models (reference revisit_bpr/models/bpr/model.py:156-251) --------
+ * A seen entry (b,s) is "kept" unless seen[b,s] occurs among item[b,:] (model.py:184-190,230-235).
+ * item (batch,n_items) int64, seen (batch,width) int64 (0-padded like the reference's collator; row
+ * 0 is an ordinary row here, as in the reference, whose Parameter has no padding gradient mask),
+ * keep (batch,width) uint8, logits / grad_logits (batch,n_items) float.  Ids outside
+ * [0,num_items) raise the device flag (next rbpr_sync_check).  Device pointers.
+ *
+ * ItemKNN.forward (model.py:176-196): weights (num_items,hidden), bias (num_items) or NULL;
+ * logits[b,i] = weights[item[b,i]] . SUM_{s kept} weights[seen[b,s]] + bias[item[b,i]].
+ * keep_out and profile_out (batch,hidden: the kept-row sums) are what the backward needs. */
+int rbpr_knn_forward(rbpr_ctx* ctx, const float* weights, int64_t num_items, int32_t hidden,
+                     const float* bias, const int64_t* item, int64_t batch, int64_t n_items,
+                     const int64_t* seen, int64_t width, uint8_t* keep_out, float* profile_out,
+                     float* logits_out, void* stream);
+
+/* Gradient of rbpr_knn_forward w.r.t. weights and bias (what autograd derives for model.py:176-196):
+ * ACCUMULATES into grad_weights (num_items,hidden) and grad_bias (num_items, NULL = no bias). */
+int rbpr_knn_backward(rbpr_ctx* ctx, const float* weights, int64_t num_items, int32_t hidden,
+                      const int64_t* item, int64_t batch, int64_t n_items, const int64_t* seen,
+                      int64_t width, const uint8_t* keep, const float* profile,
+                      const float* grad_logits, float* grad_weights, float* grad_bias, void* stream);
+
+/* FreeItemKNN.forward (model.py:222-248): weights (num_items,num_items);
+ * logits[b,i] = SUM_{s kept} weights[item[b,i], seen[b,s]] + bias[item[b,i]]. */
+int rbpr_freeknn_forward(rbpr_ctx* ctx, const float* weights, int64_t num_items, const float* bias,
+                         const int64_t* item, int64_t batch, int64_t n_items, const int64_t* seen,
+                         int64_t width, uint8_t* keep_out, float* logits_out, void* stream);
+
+/* Gradient of rbpr_freeknn_forward: ACCUMULATES grad_logits[b,i] into
+ * grad_weights[item[b,i], seen[b,s]] for every kept s, and into grad_bias[item[b,i]]. */
+int rbpr_freeknn_backward(rbpr_ctx* ctx, int64_t num_items, const int64_t* item, int64_t batch,
+                          int64_t n_items, const int64_t* seen, int64_t width, const uint8_t* keep,
+                          const float* grad_logits, float* grad_weights, float* grad_bias,
+                          void* stream);
 
 /* ---- host-side JSONL ingest (no GPU involved; thread-safe; errors via rbpr_ingest_last_error) ---
  * One mmap'ed pass over the reference's on-disk files (bin/datasets/format-repro.sh:56-81); other

@@ -134,6 +134,64 @@ class Context:
             out["items"] = items
         return out
 
+    # ---- item-neighbourhood logits models (reference model.py:156-251) ---------------------------
+    def _knn_ids(self, item: torch.Tensor, seen: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        if item.dim() != 2 or seen.dim() != 2 or item.size(0) != seen.size(0):
+            raise IndexError("item must be (batch, num items) and seen_items (batch, seen items)")
+        return (item.to(self.device, torch.int64).contiguous(), seen.to(self.device, torch.int64).contiguous())
+
+    def _knn_table(self, weights: torch.Tensor, bias: torch.Tensor | None) -> None:
+        for t in (weights,) + (() if bias is None else (bias,)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("weights / bias must be contiguous float32 CUDA tensors")
+        if weights.dim() != 2 or (bias is not None and bias.shape != weights.shape[:1]):
+            raise ValueError("weights must be (num items, width) and bias (num items,)")
+
+    def knn_forward(self, weights: torch.Tensor, bias: torch.Tensor | None, item: torch.Tensor,
+                    seen: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """ItemKNN logits (B,n) plus what the backward needs: kept-row sums (B,H), keep flags (B,S)."""
+        self._knn_table(weights, bias)
+        item, seen = self._knn_ids(item, seen)
+        B, n = item.shape
+        I, H = weights.shape
+        keep = torch.empty(seen.shape, dtype=torch.uint8, device=self.device)
+        profile = torch.empty((B, H), dtype=torch.float32, device=self.device)
+        logits = torch.empty((B, n), dtype=torch.float32, device=self.device)
+        self._check(self.lib.rbpr_knn_forward(self.ctx, _ptr(weights), I, H, _ptr(bias), _ptr(item), B, n,
+                                              _ptr(seen), seen.size(1), _ptr(keep), _ptr(profile), _ptr(logits),
+                                              _stream()))
+        return logits, profile, keep
+
+    def knn_backward(self, weights: torch.Tensor, item: torch.Tensor, seen: torch.Tensor, keep: torch.Tensor,
+                     profile: torch.Tensor, grad_logits: torch.Tensor, grad_weights: torch.Tensor,
+                     grad_bias: torch.Tensor | None) -> None:
+        item, seen = self._knn_ids(item, seen)
+        I, H = weights.shape
+        self._check(self.lib.rbpr_knn_backward(self.ctx, _ptr(weights), I, H, _ptr(item), item.size(0), item.size(1),
+                                               _ptr(seen), seen.size(1), _ptr(keep), _ptr(profile),
+                                               _ptr(grad_logits), _ptr(grad_weights), _ptr(grad_bias), _stream()))
+
+    def freeknn_forward(self, weights: torch.Tensor, bias: torch.Tensor | None, item: torch.Tensor,
+                        seen: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        self._knn_table(weights, bias)
+        if weights.size(0) != weights.size(1):
+            raise ValueError("FreeItemKNN weights must be (num items, num items)")
+        item, seen = self._knn_ids(item, seen)
+        B, n = item.shape
+        keep = torch.empty(seen.shape, dtype=torch.uint8, device=self.device)
+        logits = torch.empty((B, n), dtype=torch.float32, device=self.device)
+        self._check(self.lib.rbpr_freeknn_forward(self.ctx, _ptr(weights), weights.size(0), _ptr(bias), _ptr(item), B,
+                                                  n, _ptr(seen), seen.size(1), _ptr(keep), _ptr(logits), _stream()))
+        return logits, keep
+
+    def freeknn_backward(self, num_items: int, item: torch.Tensor, seen: torch.Tensor, keep: torch.Tensor,
+                         grad_logits: torch.Tensor, grad_weights: torch.Tensor,
+                         grad_bias: torch.Tensor | None) -> None:
+        item, seen = self._knn_ids(item, seen)
+        self._check(self.lib.rbpr_freeknn_backward(self.ctx, num_items, _ptr(item), item.size(0), item.size(1),
+                                                   _ptr(seen), seen.size(1), _ptr(keep), _ptr(grad_logits),
+                                                   _ptr(grad_weights), _ptr(grad_bias), _stream()))
+
 
 class Engine(Context):
     def __init__(self, user_emb: torch.Tensor, item_emb: torch.Tensor,

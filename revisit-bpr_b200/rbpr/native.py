@@ -11,7 +11,7 @@ OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
@@ -22,6 +22,7 @@ SYMBOLS = (
     "rbpr_item_grad_buffer", "rbpr_apply_item_grads", "rbpr_flush_lazy", "rbpr_score_topk",
     "rbpr_score_dense", "rbpr_train_step_triples", "rbpr_pair_logits", "rbpr_sample_negatives_padded",
     "rbpr_topk_metrics_dense", "rbpr_mask_seen_padded", "rbpr_auc_dense",
+    "rbpr_knn_forward", "rbpr_knn_backward", "rbpr_freeknn_forward", "rbpr_freeknn_backward",
     "rbpr_comm_unique_id", "rbpr_comm_init", "rbpr_comm_allreduce_item_grads", "rbpr_collective_count",
     "rbpr_ingest_pairs", "rbpr_ingest_lists", "rbpr_ingest_free", "rbpr_ingest_last_error",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
@@ -89,6 +90,10 @@ def load() -> C.CDLL:
                                               vp, vp, vp, vp, i32, vp, vp]),
         "rbpr_mask_seen_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, vp]),
         "rbpr_auc_dense": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
+        "rbpr_knn_forward": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, i64, vp, i64, vp, vp, vp, vp]),
+        "rbpr_knn_backward": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
+        "rbpr_freeknn_forward": (C.c_int, [vp, vp, i64, vp, vp, i64, i64, vp, i64, vp, vp, vp]),
+        "rbpr_freeknn_backward": (C.c_int, [vp, i64, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]),
         "rbpr_comm_unique_id": (C.c_int, [vp, vp]),
         "rbpr_comm_init": (C.c_int, [vp, i32, i32, vp]),
         "rbpr_comm_allreduce_item_grads": (C.c_int, [vp, vp]),

@@ -138,6 +138,8 @@ class Model(torch.nn.Module):
         from its param_groups at every step, so LR schedulers keep working; Adam moments live in
         `optimizer.state`, so `optimizer.state_dict()` stays meaningful)."""
         opt = getattr(optimizer, "optimizer", optimizer)  # accelerate's AcceleratedOptimizer wrapper
+        if not isinstance(self.logits_model, MF):
+            return  # ItemKNN / FreeItemKNN: kernel-backed autograd, the optimizer does its own step
         if len(opt.param_groups) != 1:
             raise NotImplementedError("the fused BPR step supports a single param group")
         g = opt.param_groups[0]
@@ -253,7 +255,7 @@ class Model(torch.nn.Module):
     def forward(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
         lm = self.logits_model
         if not isinstance(lm, MF):
-            raise NotImplementedError("the CUDA BPR path implements the MF logits model only")
+            return self._forward_unfused(inputs)
         if not self.training:
             self.flush()
             return {"logits": lm(inputs["user"], inputs["item"], inputs, mask=inputs.get("mask"))}
@@ -284,6 +286,31 @@ class Model(torch.nn.Module):
         bpr_loss, l2_reg = stats32[0], stats32[1]
         return {"logits_pos": pos, "logits_neg": ng, "logits": pos - ng, "bpr_loss": bpr_loss,
                 "l2_reg": l2_reg, "loss": _AppliedStep.apply(self._anchor, bpr_loss + l2_reg)}
+
+    def _forward_unfused(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        """Logits models other than MF (ItemKNN, FreeItemKNN — reference model.py:156-251): their
+        forward/backward are CUDA kernels behind autograd, the loss and L2 terms of model.py:43-68 are
+        elementwise torch on (B,1) tensors, and the caller's `loss.backward()` / `optimizer.step()`
+        do the update, as in the reference."""
+        lm = self.logits_model
+        user, item = inputs["user"], inputs["item"]
+        if not self.training:
+            logits = lm(user, item, inputs)
+            if (mask := inputs.get("mask")) is not None:
+                logits = logits.masked_fill(mask.to(logits.device) == 0, -1e13)
+            return {"logits": logits}
+        neg = inputs["neg"]
+        if self._fuse_forward:
+            width = item.size(-1)
+            both = lm(user, torch.cat((item, neg), dim=-1), inputs)
+            pos, ng = both[:, :width], both[:, width:]
+        else:
+            pos, ng = lm(user, item, inputs), lm(user, neg, inputs)
+        out = {"logits_pos": pos, "logits_neg": ng, "logits": pos - ng}
+        out["bpr_loss"] = self._loss(out["logits"]).sum()
+        out["l2_reg"] = self._l2_rows(inputs).sum()
+        out["loss"] = out["bpr_loss"] + out["l2_reg"]
+        return out
 
     # ---- fast path: whole runs of steps from triple ids (our extension, not in the reference) -----
     def bind_interactions(self, indptr: torch.Tensor, indices: torch.Tensor, sampler: int = native.SAMPLER_UNIFORM,
@@ -325,10 +352,15 @@ class Model(torch.nn.Module):
         return {"bpr_loss": bpr_loss, "l2_reg": l2_reg, "loss": _AppliedStep.apply(self._anchor, bpr_loss + l2_reg),
                 "logits": (st[:, 2].sum() / st[:, 3].sum()).reshape(1, 1), "steps": steps, "step_stats": stats}
 
-    @torch.no_grad()
     def regularization(self, inputs: dict[str, torch.Tensor]) -> torch.Tensor:
         """Per-row L2 term (B,) of the reference (model.py:70-93) for callers that want it on its
-        own; the training path computes it inside the fused kernel."""
+        own; the MF training path computes it inside the fused kernel (so no graph is kept there)."""
+        if isinstance(self.logits_model, MF):
+            with torch.no_grad():
+                return self._l2_rows(inputs)
+        return self._l2_rows(inputs)
+
+    def _l2_rows(self, inputs: dict[str, torch.Tensor]) -> torch.Tensor:
         from rbpr.engine import resolve_reg
         feats = self.logits_model.get_features()
         if not feats or all(self._reg_alphas.get(k) is None for k in ("all", "user", "item", "neg")):
@@ -339,3 +371,11 @@ class Model(torch.nn.Module):
         if feats.get("user") is not None:
             term = term + ru * feats["user"][inputs["user"]].pow(2).flatten(1).sum(1)
         return term / 2
+
+
+def __getattr__(name: str) -> Any:
+    # the reference defines ItemKNN / FreeItemKNN in this module (model.py:156-251); ours live in knn.py
+    if name in ("ItemKNN", "FreeItemKNN"):
+        from revisit_bpr.models.bpr import knn
+        return getattr(knn, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -68,7 +68,7 @@ def test_signatures_equal_reference():
     ref_model = types.ModuleType("revisit_bpr_ref_model")
     exec(compile(src, "ref_model", "exec"), ref_model.__dict__)  # noqa: S102
     del stub
-    for cls in ("Model", "MF"):
+    for cls in ("Model", "MF", "ItemKNN", "FreeItemKNN"):
         ours, ref = getattr(bpr, cls), getattr(ref_model, cls)
         po, pr = inspect.signature(ours.__init__).parameters, inspect.signature(ref.__init__).parameters
         assert [(n, q.default, q.kind) for n, q in po.items()] == [(n, q.default, q.kind) for n, q in pr.items()], cls
@@ -83,6 +83,57 @@ def test_signatures_equal_reference():
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     assert set(a.logits_model.get_features()) == set(b.logits_model.get_features())
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree only exists in the build container")
+def test_knn_models_init_like_reference():
+    """Same parameter names, state_dict keys and initial values under the same seed as the reference's
+    ItemKNN / FreeItemKNN (model.py:156-174, 202-222)."""
+    _, bpr, _, _ = _ours()
+    sys.modules["revisit_bpr_ref_loss"] = _load_ref("revisit_bpr/models/bpr/loss.py", "revisit_bpr_ref_loss")
+    src = (REF / "revisit_bpr/models/bpr/model.py").read_text().replace(
+        "from revisit_bpr.models.bpr.loss import Loss", "from revisit_bpr_ref_loss import Loss")
+    ref_model = types.ModuleType("revisit_bpr_ref_model2")
+    exec(compile(src, "ref_model", "exec"), ref_model.__dict__)  # noqa: S102
+    for make in (lambda m: m.ItemKNN(21, 6, bias=True), lambda m: m.ItemKNN(21, 6, padding_idx=3),
+                 lambda m: m.FreeItemKNN(17, bias=True), lambda m: m.FreeItemKNN(17)):
+        torch.manual_seed(5)
+        a = make(bpr)
+        torch.manual_seed(5)
+        b = make(ref_model)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), k
+        assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()]
+        fa, fb = a.get_features(), b.get_features()
+        assert set(fa) == set(fb) and (fa["bias"] is None) == (fb["bias"] is None)
+
+
+def test_knn_models_surface_and_cpu_failure():
+    from rbpr import native
+    models, bpr, _, _ = _ours()
+    from revisit_bpr.models.bpr import model as model_module
+    assert model_module.ItemKNN is bpr.ItemKNN and model_module.FreeItemKNN is bpr.FreeItemKNN
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]  # noqa: E731
+    assert sig(bpr.ItemKNN) == ["num_items", "hidden_dim", "padding_idx", "bias"]
+    assert sig(bpr.FreeItemKNN) == ["num_items", "padding_idx", "bias"]
+    knn = bpr.ItemKNN(11, 4, bias=True)
+    assert knn._weights.shape == (11, 4) and knn._weights[0].abs().sum() == 0 and knn._bias.abs().sum() == 0
+    assert 0 < knn._weights[1:].min() and knn._weights.max() < 1
+    free = bpr.FreeItemKNN(9)
+    assert free._weights.shape == (9, 9) and free._bias is None and "_bias" not in free.state_dict()
+    batch = {"user": torch.tensor([1, 2]), "item": torch.tensor([[1], [2]]), "neg": torch.tensor([[3], [4]]),
+             "seen_items": torch.tensor([[1, 5], [2, 0]])}
+    for lm in (knn, free):
+        model = models.BPR(lm, reg_alphas={"item": 0.1})
+        model.bind_optimizer(torch.optim.Adagrad(model.parameters(), lr=0.1))  # any optimizer: not fused
+        with pytest.raises(native.NativeError):  # CPU tensors: no fallback
+            model(batch)
+    with pytest.raises(ValueError, match="seen_items should be present"):
+        free(None, batch["item"], {})
+    with pytest.raises(KeyError):
+        knn(None, batch["item"], {})
 
 
 def test_mf_init_rule_and_features():
