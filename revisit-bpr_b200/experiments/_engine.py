@@ -82,6 +82,8 @@ class Engine:
         self.state_dict_user_keys: list[str] = []
         self.should_terminate = False
         self.should_interrupt = False
+        self.should_terminate_epoch = False
+        self._iter: Any = None
 
     # ---- events ----
     def register_events(self, *events: Any, event_to_attr: dict[Any, str] | None = None) -> None:
@@ -106,16 +108,22 @@ class Engine:
             return fn
         return deco
 
-    def fire_event(self, event: Any) -> None:
+    def fire_event(self, event: Any, *event_args: Any) -> None:
+        """Handlers are called as handler(engine, *event_args, *args, **kwargs), like ignite's."""
         for handler, args, kwargs, every in list(self._handlers.get(event, [])):
+            args = tuple(event_args) + tuple(args)
             if every is not None:
                 count = self.state.get_event_attrib_value(event) if event in self.state.event_to_attr else 0
                 if count % every != 0:
                     continue
             try:  # ignite lets a handler omit the leading `engine` argument
                 inspect.signature(handler).bind(self, *args, **kwargs)
-                handler(self, *args, **kwargs)
+                takes_engine = True
             except TypeError:
+                takes_engine = False
+            if takes_engine:
+                handler(self, *args, **kwargs)
+            else:
                 handler(*args, **kwargs)
 
     # ---- control ----
@@ -124,6 +132,14 @@ class Engine:
 
     def interrupt(self) -> None:
         self.should_interrupt = True
+
+    def terminate_epoch(self) -> None:
+        self.should_terminate_epoch = True
+
+    def set_data(self, data: Iterable) -> None:
+        """Replace the data of a running engine; the next batch comes from the new iterable."""
+        self.state.dataloader = data
+        self._iter = iter(data)
 
     def state_dict(self) -> dict[str, Any]:
         d = {"epoch_length": self.state.epoch_length, "max_epochs": self.state.max_epochs,
@@ -154,21 +170,27 @@ class Engine:
         if st.epoch >= st.max_epochs:  # a finished engine restarts from scratch (ignite semantics)
             st.epoch, st.iteration = 0, 0
         self.should_terminate = self.should_interrupt = False
+        # a state restored in the middle of an epoch (load_state_dict) resumes inside that epoch:
+        # only the remaining iterations run (handlers on STARTED may swap in a loader that skips
+        # the batches already consumed, ignite semantics)
+        resume_at = st.iteration % st.epoch_length if (st.epoch_length and st.iteration > 0) else 0
         try:
             self.fire_event(Events.STARTED)
             while st.epoch < st.max_epochs and not self.should_terminate:
                 st.epoch += 1
                 self.fire_event(Events.EPOCH_STARTED)
-                it, n_in_epoch = iter(data), 0
-                while (st.epoch_length is None or n_in_epoch < st.epoch_length) and not self.should_terminate:
+                self._iter, n_in_epoch, resume_at = iter(st.dataloader), resume_at, 0
+                self.should_terminate_epoch = False
+                while ((st.epoch_length is None or n_in_epoch < st.epoch_length) and not self.should_terminate
+                       and not self.should_terminate_epoch):
                     self.fire_event(Events.GET_BATCH_STARTED)
                     try:
-                        st.batch = next(it)
+                        st.batch = next(self._iter)
                     except StopIteration:
                         if st.epoch_length is None or n_in_epoch == 0:
                             break
-                        it = iter(data)
-                        st.batch = next(it)
+                        self._iter = iter(st.dataloader)
+                        st.batch = next(self._iter)
                     st.iteration += 1
                     n_in_epoch += 1
                     self.fire_event(Events.GET_BATCH_COMPLETED)
@@ -180,8 +202,8 @@ class Engine:
                         return st
                 self.fire_event(Events.EPOCH_COMPLETED)
             self.fire_event(Events.COMPLETED)
-        except BaseException:
+        except BaseException as exc:
             if self._handlers.get(Events.EXCEPTION_RAISED):
-                self.fire_event(Events.EXCEPTION_RAISED)
+                self.fire_event(Events.EXCEPTION_RAISED, exc)
             raise
         return st

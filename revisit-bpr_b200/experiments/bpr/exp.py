@@ -11,21 +11,29 @@ configs' `experiment:` block instantiates unchanged:
     the configured metrics (`attach_metrics`).
 
 Model, optimizer and loaders are built from the config with `instantiate` (hydra's when installed).
-Trackers, checkpoint rotation, progress bars and S3 sync of the reference are control plane and are
-not reproduced; the corresponding constructor arguments are accepted and ignored.
+With `dir` set, a checkpoint is written after every eval pass under `<dir>/checkpoints/`
+(`n_checkpoints` kept, the best one copied to `<dir>/best_iteration/`) and a run started on a `dir`
+that already holds checkpoints resumes from the newest loadable one (exp.py:249-272,
+options.py:88-146); the hot path's own counters (optimizer step, sampler stream position) travel
+with it.  Trackers, progress bars, output savers and S3 sync of the reference are control plane and
+are not reproduced; the corresponding constructor arguments are accepted and ignored.
 """
 from __future__ import annotations
 
 import json
 import math
 import random
+import re
+import shutil
+import warnings
 from pathlib import Path
 from typing import Any, Callable, Literal
 
 import numpy as np
 import torch
 
-from experiments.options import attach_early_stopping, attach_metrics
+from experiments.options import (CHECKPOINTS_DIR, attach_checkpoint_loader, attach_checkpointer,
+                                 attach_early_stopping, attach_metrics, attach_preemptible)
 from experiments.trainer import Events, ModelEvents, Trainer
 from rbpr import native
 from rbpr.engine import Context
@@ -38,8 +46,42 @@ except ImportError:
 
 try:
     from accelerate import Accelerator
+    from accelerate.utils import ProjectConfiguration
 except ImportError:
-    from experiments._accel import Accelerator
+    from experiments._accel import Accelerator, ProjectConfiguration
+
+
+class _HotPathCounters:
+    """What a resumed run needs beyond model / optimizer / engine state: the fused step's optimizer
+    step number (plain SGD keeps no state that carries it) and the position of the counter-based
+    negative sampler's stream.  Registered with `accelerator.register_for_checkpointing`."""
+
+    def __init__(self, exp: "BPRExperiment") -> None:
+        self._exp = exp
+
+    def _generators(self) -> dict[str, torch.Generator]:
+        """The loaders' own shuffle generators (exp.py:111-115 hands each DataLoader one): they are not
+        part of the global RNG state, and the next epoch's permutation comes from them."""
+        out = {}
+        for key, loader in self._exp._datasets.items():
+            if isinstance(g := getattr(loader, "generator", None), torch.Generator):
+                out[key] = g
+        return out
+
+    def state_dict(self) -> dict[str, Any]:
+        e = self._exp
+        return {"opt_step": int(getattr(e._model, "_opt_step", 0)), "neg_seed": int(e._neg_seed),
+                "neg_calls": int(e._neg_calls),
+                "loader_rng": {k: g.get_state() for k, g in self._generators().items()}}
+
+    def load_state_dict(self, d: dict[str, Any]) -> None:
+        e = self._exp
+        e._neg_seed, e._neg_calls = int(d["neg_seed"]), int(d["neg_calls"])
+        if hasattr(e._model, "restore_step"):
+            e._model.restore_step(int(d["opt_step"]))
+        for k, g in self._generators().items():
+            if k in d.get("loader_rng", {}):
+                g.set_state(d["loader_rng"][k].cpu())
 
 
 class BPRExperiment:
@@ -66,7 +108,8 @@ class BPRExperiment:
         adaptive_sampling_prob: float | None = None,
     ) -> None:
         self._config = exp_config if isinstance(exp_config, dict) else exp_config()
-        self._dir = dir
+        self._dir = Path(dir) if dir is not None else None
+        self._n_checkpoints = n_checkpoints
         self._seed = seed
         self._debug = debug
         self._skip_seen = skip_seen
@@ -79,7 +122,7 @@ class BPRExperiment:
         self._adaptive_sampling_prob = adaptive_sampling_prob
         if mixed_precision not in (None, "no"):
             raise NotImplementedError("the CUDA BPR path is fp32 only (the reference configs use no mixed precision)")
-        del n_checkpoints, trackers_params, save_logits, save_user_metrics, log_momentum  # control plane
+        del trackers_params, save_logits, save_user_metrics, log_momentum  # control plane
         # popularity weights count^alpha (exp.py:85-91); all ones = uniform
         self._item_counts = torch.ones(self._config["num_items"], dtype=torch.float32)
         self._weighted = False
@@ -99,13 +142,11 @@ class BPRExperiment:
 
     # ---- run -------------------------------------------------------------------------------------
     def run(self) -> Any:
-        self._accelerator = Accelerator()
-        self._seed_everything()
-        for m in self._metrics.values():
-            m.set_accelerator(self._accelerator)
+        self._accelerator = self._get_accelerator()
         dev = self._accelerator.device
-        self._model = self._accelerator.prepare(instantiate(self._config["model"]))
+        self._model = instantiate(self._config["model"])
         self._optimizer = instantiate(self._config["optimizer"])(self._model.parameters())
+        self._model, self._optimizer = self._accelerator.prepare(self._model, self._optimizer)
         loaders_cfg = self._config[self._datasets_key]
         max_iters = {k: d.pop("max_iters", None) for k, d in loaders_cfg.items()}
         self._datasets = {key: instantiate(cfg, generator=torch.Generator().manual_seed(self._seed))
@@ -125,11 +166,46 @@ class BPRExperiment:
         self._sampler_ctx = Context(dev)
         if self._weighted:
             self._sampler_ctx.bind_item_weights(self._item_counts)
+        self._load_checkpoint_if_needed()
         if self._adaptive and not self._fast:
             self._update_adaptive_stats()
         self._state = self.trainer.run(self._datasets, max_iters=max_iters, epochs=self._config["epochs"])
         self._accelerator.wait_for_everyone()
+        self._accelerator.end_training()
         return self._state
+
+    def _get_accelerator(self) -> Any:
+        accelerator = Accelerator()
+        if self._dir is not None:
+            accelerator.project_configuration = ProjectConfiguration(
+                project_dir=str(self._dir), automatic_checkpoint_naming=True, total_limit=self._n_checkpoints)
+        self._seed_everything()
+        for m in self._metrics.values():
+            m.set_accelerator(accelerator)
+        return accelerator
+
+    def _load_checkpoint_if_needed(self) -> None:
+        """Resume from the newest checkpoint under `<dir>/checkpoints` that loads; one that does not
+        (a save cut short) is deleted and the one before it is tried (exp.py:249-272)."""
+        if self._dir is None or not (root := self._dir / CHECKPOINTS_DIR).is_dir():
+            return
+        numbered = sorted((int(m.group(1)), d) for d in root.iterdir()
+                          if d.is_dir() and (m := re.search(r"(\d+)$", d.name)))
+        while numbered:
+            num, folder = numbered.pop()
+            try:
+                self._accelerator.load_state()
+            except Exception as exc:  # noqa: BLE001
+                warnings.warn(f"checkpoint {folder} does not load ({exc!r}): removed, trying the one before",
+                              stacklevel=2)
+                shutil.rmtree(folder, ignore_errors=True)
+                continue
+            self._accelerator.project_configuration.iteration = num + 1  # accelerate does not restore it
+            return
+
+    def clean(self) -> None:
+        self._accelerator.free_memory()
+        del self._accelerator, self.trainer
 
     def _enable_fast_train(self, dev: torch.device) -> None:
         from experiments.bpr.dataset import EpochChunks, SparseSamplingInMemoryWithCollator
@@ -171,12 +247,19 @@ class BPRExperiment:
             trainer.add_event("train", Events.GET_BATCH_COMPLETED, self._train_batch)
         if self._skip_seen:
             trainer.add_event("eval", ModelEvents.FORWARD_COMPLETED, self._remove_seen_items)
+        early_stopping = None
         if self._early_stopping_metric is not None:
-            attach_early_stopping(trainer, metric_name=self._early_stopping_metric,
-                                  patience=self._early_stopping_patience, direction=self._early_stopping_direction)
+            early_stopping = attach_early_stopping(trainer, metric_name=self._early_stopping_metric,
+                                                   patience=self._early_stopping_patience,
+                                                   direction=self._early_stopping_direction)
+        attach_preemptible(trainer, self._accelerator)
         if self._debug:
             trainer.add_event("train", Events.ITERATION_COMPLETED(every=2000), lambda e: e.terminate())
         attach_metrics(trainer, self._accelerator, self._metrics)
+        if self._dir is not None:
+            attach_checkpointer(trainer, self._accelerator, early_stopping=early_stopping,
+                                checkpoint_objects=[*self._metrics.values(), _HotPathCounters(self)])
+            attach_checkpoint_loader(trainer, self._accelerator, datasets)
         for key, handlers in self._events.items():
             for event, handler in handlers:
                 trainer.add_event(key, event, handler, accelerator=self._accelerator)

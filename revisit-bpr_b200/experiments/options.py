@@ -1,11 +1,18 @@
-"""Handlers of the reference's experiments/options.py that sit on the BPR scoring path:
+"""Handlers of the reference's experiments/options.py around the BPR path:
 `attach_metrics` (options.py:31-85: reset / update / reduce handlers feeding every configured
-metric with `(output["logits"], batch["target"])`) and `attach_early_stopping` (options.py:166-185).
-Checkpointing, trackers, progress bars and output savers are control-plane glue and out of scope
-(SURVEY.md §2 #8)."""
+metric with `(output["logits"], batch["target"])`), `attach_early_stopping` (options.py:166-185)
+and the checkpoint / resume glue — `attach_checkpointer` (options.py:88-113: a checkpoint after
+every eval pass, copied to `best_iteration/` when the early-stopping counter is 0),
+`attach_checkpoint_loader` (options.py:116-146: skip the batches a resumed engine already
+consumed) and `attach_preemptible` (options.py:188-219: mark the engines interrupted and save on
+INTERRUPT / an exception).  Trackers, progress bars and output savers are control plane and out of
+scope."""
 from __future__ import annotations
 
-from typing import Any, Callable
+import shutil
+import time
+from pathlib import Path
+from typing import Any, Callable, Iterable
 
 import torch
 
@@ -91,3 +98,76 @@ def attach_early_stopping(trainer: Trainer, metric_name: str, patience: int, dir
     handler = EarlyStopping(patience, score, trainer.engines["train"])
     trainer.add_event("eval", Events.COMPLETED, handler)
     return handler
+
+
+# ---- checkpoint / resume -------------------------------------------------------------------------
+CHECKPOINTS_DIR = "checkpoints"      # reference experiments/settings.py:2-3
+BEST_ITERATION_PATH = "best_iteration"
+
+
+def _save(accelerator: Any) -> str:
+    """accelerator.save_state() under automatic naming; a folder that already carries the next
+    number (an aborted save) is stepped over instead of failing the run."""
+    folder = Path(accelerator.project_dir) / CHECKPOINTS_DIR / f"checkpoint_{accelerator.save_iteration}"
+    if folder.exists():
+        accelerator.project_configuration.iteration += 1
+    return accelerator.save_state()
+
+
+def attach_checkpointer(trainer: Trainer, accelerator: Any, early_stopping: Any = None,
+                        checkpoint_objects: Iterable[Any] | None = None) -> None:
+    """Everything a resumed run needs goes through `accelerator.save_state`: model and optimizer
+    (prepared), the engines' states, the early-stopping counters and `checkpoint_objects` (metrics,
+    the hot path's step / sampler counters)."""
+    for obj in ([] if early_stopping is None else [early_stopping]) + list(trainer.engines.values()) \
+            + list(checkpoint_objects or []):
+        accelerator.register_for_checkpointing(obj)
+
+    def after_eval(engine: Any) -> None:
+        engine.state.save_location = _save(accelerator)
+        improved = early_stopping is None or early_stopping.counter == 0
+        if improved and accelerator.is_local_main_process:
+            shutil.copytree(engine.state.save_location, Path(accelerator.project_dir) / BEST_ITERATION_PATH,
+                            dirs_exist_ok=True)
+
+    trainer.add_event("eval", Events.COMPLETED, after_eval)
+
+
+def attach_checkpoint_loader(trainer: Trainer, accelerator: Any, datasets: dict[str, Any]) -> None:
+    def on_started(engine: Any) -> None:
+        st = engine.state
+        for k, v in st.metrics.items():  # restored from a checkpoint written on another device
+            if torch.is_tensor(v):
+                st.metrics[k] = v.to(accelerator.device)
+        if st.was_interrupted:
+            done = st.iteration % st.epoch_length if st.epoch_length else st.iteration
+            st.dataloader = accelerator.skip_first_batches(datasets[st.name], done)
+
+    def on_epoch_completed(engine: Any) -> None:
+        if engine.state.was_interrupted:  # the shortened first epoch is over: back to the full loader
+            engine.set_data(datasets[engine.state.name])
+            engine.state.was_interrupted = False
+
+    for name in trainer.engines:
+        trainer.add_event(name, Events.STARTED, on_started)
+        trainer.add_event(name, Events.EPOCH_COMPLETED, on_epoch_completed)
+
+
+def attach_preemptible(trainer: Trainer, accelerator: Any, min_seconds_between_saves: int = 10) -> None:
+    def on_stop(engine: Any) -> None:
+        engine.state.was_interrupted = True
+        if accelerator.project_dir is None:
+            return
+        last = Path(accelerator.project_dir) / CHECKPOINTS_DIR / f"checkpoint_{accelerator.save_iteration - 1}"
+        if last.exists() and time.time() - last.stat().st_mtime < min_seconds_between_saves:
+            return  # the regular checkpoint was written a moment ago
+        _save(accelerator)
+
+    def on_exception(engine: Any, exc: BaseException | None = None) -> None:
+        on_stop(engine)
+        if exc is not None:
+            raise exc
+
+    for name in trainer.engines:
+        trainer.add_event(name, Events.INTERRUPT, on_stop)
+        trainer.add_event(name, Events.EXCEPTION_RAISED, on_exception)

@@ -161,11 +161,25 @@ class Model(torch.nn.Module):
             raise NotImplementedError(f"{type(opt).__name__} is not implemented in the fused BPR step "
                                       "(supported: torch.optim.SGD [momentum, nesterov], Adam, RMSprop [momentum=0])")
         self._optimizer = opt
-        self._adam_last = None
-        steps = [int(s["step"]) for s in opt.state.values() if "step" in s]
-        self._opt_step = max(steps) if steps else 0
+        self._resync_step()
         if hasattr(opt, "register_state_dict_pre_hook"):
             opt.register_state_dict_pre_hook(lambda _opt: self.flush())
+        if hasattr(opt, "register_load_state_dict_post_hook"):
+            # optimizer.load_state_dict AFTER binding (accelerate.load_state on a built trainer): the
+            # state tensors were replaced and every row is again consistent with the loaded step
+            opt.register_load_state_dict_post_hook(lambda _opt: self._resync_step())
+
+    def _resync_step(self) -> None:
+        steps = [int(s["step"]) for s in self._optimizer.state.values() if "step" in s]
+        self._opt_step = max(steps) if steps else 0
+        self._adam_last = None
+
+    def restore_step(self, step: int) -> None:
+        """Set the number of optimizer steps already applied (checkpoint resume: plain SGD keeps no
+        state that carries it; it numbers the fast path's sampler stream and Adam's bias correction)."""
+        if self._adam_last is not None and step != self._opt_step:
+            raise RuntimeError("restore_step after training started with lazily updated rows in flight")
+        self._opt_step = int(step)
 
     def _adam_state(self, eng: Engine) -> dict[str, torch.Tensor]:
         opt = self._optimizer

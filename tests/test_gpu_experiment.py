@@ -262,3 +262,50 @@ def test_fast_train_extension_runs_whole_chunks_inside_the_library(tmp_path, ada
     np.testing.assert_allclose(exp.metrics["ndcg@10"].item(), ref_bpr.ndcg_at_k(logits, target, 10).mean().item(), atol=1e-4)
     np.testing.assert_allclose(exp.metrics["recall@20"].item(), ref_bpr.recall_at_k(logits, target, 20).mean().item(), atol=1e-4)
     assert exp.metrics["auc"].item() > 0.5
+
+
+@pytest.mark.parametrize("optimizer,lr,fast", [("torch.optim.SGD", 0.05, False), ("torch.optim.Adam", 0.01, False),
+                                               ("torch.optim.Adam", 0.01, True)])
+def test_experiment_checkpoints_and_resumes_from_dir(tmp_path, optimizer, lr, fast):
+    """`dir` set: a checkpoint after every eval pass under <dir>/checkpoints (n_checkpoints kept,
+    best copied to <dir>/best_iteration), and a second run on the same dir continues where the first
+    stopped (reference exp.py:249-272, options.py:88-146): 2 epochs + resume to 4 == 4 epochs in one go
+    (tables, optimizer step, sampler stream, shuffle order, early-stopping counters)."""
+    from experiments._instantiate import instantiate
+    data = tmp_path / "data"
+    data.mkdir()
+    inter, train_rows, _ = _write_dataset(data)
+
+    def run(where, epochs):
+        cfg = _render(data, num_users=inter.num_users - 1, num_items=inter.num_items - 1, epochs=epochs, adaptive=False,
+                      train_batch_size=64, embedding_dim=16, optimizer=optimizer, lr=lr, item_bias="true")
+        if fast:
+            cfg["fast_train"], cfg["fast_steps_per_chunk"] = True, 3
+        exp_cfg = cfg.pop("experiment")
+        exp = instantiate(exp_cfg, exp_config=lambda: cfg, dir=where, n_checkpoints=2, debug=False, seed=13,
+                          trackers_params={})
+        exp.run()
+        return exp
+
+    full = run(tmp_path / "a", 4)
+    ckpts = sorted(p.name for p in (tmp_path / "a" / "checkpoints").iterdir())
+    assert ckpts == ["checkpoint_3", "checkpoint_4"]  # 5 eval passes (4 epoch starts + completion), 2 kept
+    assert sorted(p.name for p in (tmp_path / "a" / "checkpoints" / "checkpoint_4").iterdir())[:3] == [
+        "custom_checkpoint_0.pkl", "custom_checkpoint_1.pkl", "custom_checkpoint_2.pkl"]
+    assert (tmp_path / "a" / "best_iteration" / "pytorch_model.bin").exists()
+
+    first = run(tmp_path / "b", 2)
+    it_per_epoch = first.trainer.engines["train"].state.epoch_length
+    assert first.trainer.engines["train"].state.iteration == 2 * it_per_epoch
+    rest = run(tmp_path / "b", 4)
+    tr = rest.trainer.engines["train"].state
+    assert tr.epoch == 4 and tr.iteration == 4 * it_per_epoch
+    assert rest._model._opt_step == full._model._opt_step > 0
+    assert rest._neg_calls == full._neg_calls
+    a, b = full._model.state_dict(), rest._model.state_dict()
+    for k in a:
+        np.testing.assert_allclose(b[k].cpu().numpy(), a[k].cpu().numpy(), rtol=1e-4, atol=2e-5, err_msg=k)
+    for k in ("ndcg@10", "recall@20", "precision@5", "auc"):
+        np.testing.assert_allclose(float(rest.metrics[k]), float(full.metrics[k]), atol=2e-3, err_msg=k)
+    np.testing.assert_allclose(tr.metrics["loss"].item(), full.trainer.engines["train"].state.metrics["loss"].item(),
+                               rtol=1e-4)
