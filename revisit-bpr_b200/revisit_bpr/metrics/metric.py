@@ -39,6 +39,23 @@ def validate_metric_inputs(output: torch.Tensor, target: torch.Tensor) -> None:
                          f"output - {output.size()}, target - {target.size()}.")
 
 
+def prepare_target(output: torch.Tensor, target: torch.Tensor, topk: int | None = None) -> torch.Tensor:
+    """`target` re-ordered by descending `output` (reference metric.py:110-113), cut at `topk`.
+
+    The metric classes never call this — ranking and metric arithmetic are one kernel
+    (`topk_metrics`) — it exists for callers of the reference's helper.  The ranks come from the same
+    top-k kernel, so at most RBPR_MAX_TOPK (128) columns can be returned: pass `topk` (the reference's
+    callers all slice `[:, :topk]` right away) when the catalog is wider."""
+    validate_metric_inputs(output, target)
+    width = output.size(-1)
+    k = width if topk is None else min(int(topk), width)
+    if k > native.MAX_TOPK:
+        raise NotImplementedError(f"prepare_target returns at most {native.MAX_TOPK} ranked columns: pass topk")
+    ctx = _context(output.device)
+    ranked = ctx.topk_metrics_dense(output, torch.zeros_like(output, dtype=torch.float32), [k], want_items=True)
+    return torch.gather(target, -1, ranked["items"][:, :k].long())
+
+
 def topk_metrics(output: torch.Tensor, target: torch.Tensor, topk: int, linear_gain: bool = False,
                  validate: bool = False, map_normalized: bool = True) -> dict[str, torch.Tensor]:
     """{'ndcg','recall','precision','map'} -> (B,) at cut-off min(topk, I)."""

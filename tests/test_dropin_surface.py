@@ -171,6 +171,9 @@ def test_cpu_calls_fail_loudly_and_optimizer_binding_rules():
         model({"user": torch.tensor([1]), "item": torch.tensor([[1, 2]])})
     with pytest.raises(native.NativeError):
         metrics.Recall(3).compute(torch.zeros(2, 5), torch.zeros(2, 5))
+    from revisit_bpr.metrics.metric import prepare_target
+    with pytest.raises(native.NativeError):
+        prepare_target(torch.zeros(2, 5), torch.zeros(2, 5))
     with pytest.raises(native.NativeError):
         modules.UniformSampler(7, torch.Generator().manual_seed(1)).sample(
             {"item": torch.zeros(1, 1, dtype=torch.long), "seen_items": torch.zeros(1, 3, dtype=torch.long)})

@@ -296,3 +296,25 @@ def test_checkpoint_resume_reproduces_reference_trajectory(name, tmp_path):
     np.testing.assert_allclose(sd["logits_model._item_emb.weight"].cpu().numpy(), case["final_item"], atol=1e-5, rtol=1e-4)
     if case["opt"] == "Adam":
         assert all(float(v["step"]) == steps for v in opt2.state_dict()["state"].values())
+
+
+def test_prepare_target_helper_matches_argsort_gather():
+    """revisit_bpr.metrics.metric.prepare_target (reference metric.py:110-113): target re-ordered by
+    descending output; ours ranks with the top-k kernel (at most 128 columns)."""
+    from revisit_bpr.metrics.metric import prepare_target
+    g = torch.Generator().manual_seed(4)
+    out = torch.randn(7, 90, generator=g)
+    tgt = (torch.rand(7, 90, generator=g) < 0.2).float()
+    want = torch.gather(tgt, -1, torch.argsort(-out, dim=-1))
+    got = prepare_target(out.to(DEV), tgt.to(DEV))
+    assert got.shape == (7, 90) and torch.equal(got.cpu(), want)
+    wide_out = torch.randn(5, 700, generator=g)
+    wide_tgt = torch.rand(5, 700, generator=g)  # not binary: the helper only re-orders
+    got = prepare_target(wide_out.to(DEV), wide_tgt.to(DEV), topk=25)
+    assert torch.equal(got.cpu(), torch.gather(wide_tgt, -1, torch.argsort(-wide_out, dim=-1))[:, :25])
+    with pytest.raises(NotImplementedError):
+        prepare_target(wide_out.to(DEV), wide_tgt.to(DEV))
+    with pytest.raises(IndexError):
+        prepare_target(out.to(DEV), tgt[:, :5].to(DEV))
+    from revisit_bpr.metrics.metric import _context
+    _context(torch.device(DEV)).sync_check()  # the non-binary target raised no device flag
