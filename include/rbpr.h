@@ -337,7 +337,10 @@ int rbpr_freeknn_backward(rbpr_ctx* ctx, int64_t num_items, const int64_t* item,
 
 /* ---- host-side JSONL ingest (no GPU involved; thread-safe; errors via rbpr_ingest_last_error) ---
  * One mmap'ed pass over the reference's on-disk files (bin/datasets/format-repro.sh:56-81); other
- * keys on a line are skipped.  Outputs are malloc'ed int64 arrays released with rbpr_ingest_free.
+ * keys on a line are skipped (their values are stepped over structurally — strings, nested arrays
+ * and objects — without being validated, and bytes after the closing brace of a line are ignored:
+ * every file json.loads accepts yields the same values, some files it rejects are accepted).
+ * Outputs are malloc'ed int64 arrays released with rbpr_ingest_free.
  * Replaces the per-line json.loads loops of experiments/bpr/dataset.py:16-24,183-190.
  *   pairs: {"<key_a>": int, "<key_b>": int}            -> a[n], b[n]
  *   lists: {"<key_a>": int, "<key_list>": [int, ...]}  -> a[rows], offsets[rows+1], values[...]   */

@@ -80,3 +80,115 @@ def test_pairs_to_csr_and_throughput(tmp_path):
     with pytest.raises(IndexError):
         ingest.pairs_to_csr(uu, ii, 100, 2000)
     print(f"ingest: native {n / native_s / 1e6:.1f} M lines/s vs json {n / json_s / 1e6:.2f} M lines/s")
+
+
+def _random_json_value(rng, depth=0):
+    kind = rng.randint(0, 7 if depth < 2 else 4)
+    if kind == 0:
+        return rng.randint(-10**6, 10**12)
+    if kind == 1:
+        alphabet = ["a", " ", '"', "\\", "{", "}", "[", "]", ":", ",", "é", "\n", "\t", "user", "item", "/", "0"]
+        return "".join(rng.choice(alphabet) for _ in range(rng.randint(0, 8)))
+    if kind == 2:
+        return rng.choice([None, True, False])
+    if kind == 3:
+        return rng.random() * rng.choice([1, 1e10, 1e-10, -1])
+    if kind == 4:
+        return rng.randint(0, 9)
+    if kind == 5:
+        return [_random_json_value(rng, depth + 1) for _ in range(rng.randint(0, 3))]
+    return {str(_random_json_value(rng, 3)): _random_json_value(rng, depth + 1) for _ in range(rng.randint(0, 3))}
+
+
+def _dump_with_random_layout(rng, obj):
+    ws = lambda: "".join(rng.choice([" ", "", "", "\t"]) for _ in range(rng.randint(0, 2)))  # noqa: E731
+    if isinstance(obj, dict):
+        body = ("," + ws()).join(json.dumps(k, ensure_ascii=rng.random() < 0.5) + ws() + ":" + ws()
+                                 + _dump_with_random_layout(rng, v) for k, v in obj.items())
+        return "{" + ws() + body + ws() + "}"
+    if isinstance(obj, list):
+        return "[" + ws() + ("," + ws()).join(_dump_with_random_layout(rng, v) for v in obj) + ws() + "]"
+    return json.dumps(obj, ensure_ascii=rng.random() < 0.5)
+
+
+def test_scanner_agrees_with_json_on_randomised_valid_files(tmp_path):
+    """Key order, whitespace, CRLF, blank lines, missing final newline, and arbitrary OTHER keys whose
+    values nest objects / arrays / strings full of quotes, escapes and braces: same values as json.loads."""
+    import random
+    from rbpr import ingest
+    rng = random.Random(20241)
+    for trial in range(250):
+        mode = rng.choice(["pairs", "lists"])
+        lines, users, second = [], [], []
+        for _ in range(rng.randint(0, 10)):
+            extra = {str(_random_json_value(rng, 3)): _random_json_value(rng) for _ in range(rng.randint(0, 3))}
+            fields = [(k, v) for k, v in extra.items() if k not in ("user", "item", "seen_items")]
+            u = rng.randint(0, 10**9)
+            val = rng.randint(0, 10**9) if mode == "pairs" else [rng.randint(0, 10**6) for _ in range(rng.randint(0, 5))]
+            fields += [("user", u), ("item" if mode == "pairs" else "seen_items", val)]
+            rng.shuffle(fields)
+            users.append(u)
+            second.append(val)
+            lines.append(_dump_with_random_layout(rng, dict(fields)))
+        sep = rng.choice(["\n", "\r\n"])
+        text = sep.join(lines) + (sep if rng.random() < 0.7 else "")
+        if lines and rng.random() < 0.2:
+            text = text.replace(sep, sep + sep, 1)
+        path = tmp_path / f"f{trial}.jsonl"
+        path.write_bytes(text.encode("utf-8"))
+        if mode == "pairs":
+            a, b = ingest.read_pairs(path)
+            assert a.tolist() == users and b.tolist() == second, text
+        else:
+            a, off, vals = ingest.read_lists(path)
+            assert a.tolist() == users, text
+            assert [vals[off[k]:off[k + 1]].tolist() for k in range(len(a))] == second, text
+
+
+def test_scanner_survives_corrupted_files(tmp_path):
+    """Random deletions / insertions / substitutions / truncations: either a ValueError or arrays that
+    are consistent with each other — and whenever json.loads also accepts the file, the same values."""
+    import random
+    from rbpr import ingest
+    rng = random.Random(977)
+    base = {"pairs": '{"user": 12, "item": 7, "ts": 1.5e3, "tag": "a\\"b{}", "x": [1, {"y": null}]}\n{"item": 3, "user": 4}\n',
+            "lists": '{"user": 1, "seen_items": [1, 2, 3], "z": {"a": [true, false]}}\n{"seen_items": [], "user": 9}\n'}
+    chars = list('{}[]",:\\ \n\r\t0123456789-+.eEuseritm') + ["é", "\x00", "\x7f"]
+    accepted = rejected = 0
+    for trial in range(1500):
+        mode = rng.choice(["pairs", "lists"])
+        t = list(base[mode])
+        for _ in range(rng.randint(1, 5)):
+            op, pos = rng.randint(0, 3), rng.randint(0, max(0, len(t) - 1))
+            if op == 0 and t:
+                del t[pos]
+            elif op == 1:
+                t.insert(pos, rng.choice(chars))
+            elif op == 2 and t:
+                t[pos] = rng.choice(chars)
+            else:
+                t = t[:pos]
+        text = "".join(t)
+        path = tmp_path / "c.jsonl"
+        path.write_bytes(text.encode("utf-8"))
+        try:
+            if mode == "pairs":
+                a, b = ingest.read_pairs(path)
+                assert len(a) == len(b)
+                got = (a.tolist(), b.tolist())
+            else:
+                a, off, vals = ingest.read_lists(path)
+                assert len(off) == len(a) + 1 and off[-1] == len(vals) and (np.diff(off) >= 0).all()
+                got = (a.tolist(), [vals[off[k]:off[k + 1]].tolist() for k in range(len(a))])
+        except ValueError:
+            rejected += 1
+            continue
+        accepted += 1
+        try:
+            recs = [json.loads(line) for line in text.splitlines() if line.strip()]
+            want = ([r["user"] for r in recs], [r["item" if mode == "pairs" else "seen_items"] for r in recs])
+        except Exception:  # noqa: BLE001  (the scanner does not validate the values it skips)
+            continue
+        if all(isinstance(v, int) and not isinstance(v, bool) for v in want[0]):
+            assert got == want, text
+    assert accepted > 50 and rejected > 500
