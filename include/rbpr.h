@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 5
+#define RBPR_ABI_VERSION 6
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -264,6 +264,33 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
                     const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
                     const int32_t* ks, int32_t n_ks, int32_t* topk_items, float* topk_scores,
                     float* ndcg_out, float* recall_out, void* stream);
+
+/* Every ranking metric the reference configs attach, for ALL cut-offs, from ONE scoring + ranking
+ * pass over a block of users (what attach_metrics' update_handler, experiments/options.py:42-51,
+ * obtains by calling up to 14 metric objects, each of which re-sorts the (B,I) logits:
+ * revisit_bpr/metrics/{ndcg,recall,precision,map,fbeta}.py).  Arguments as rbpr_score_topk; every
+ * output is device float (n_users, n_ks) or NULL:
+ *   ndcg        gain 2^t-1, discount 1/log2(rank+2)  (ndcg.py:8-13,69-78)
+ *   ndcg_linear gain t,     discount 1/(rank+1)      (ndcg.py:16-24)
+ *   recall, precision                                 (recall.py:44-51, precision.py:44-51)
+ *   map         average precision, denominator min(n_pos,k) if map_normalized else hits (map.py:45-64)
+ *   topk_items  device int32 (n_users,k_max) or NULL */
+typedef struct {
+  float* ndcg;
+  float* ndcg_linear;
+  float* recall;
+  float* precision;
+  float* map;
+  int32_t* topk_items;
+  int32_t map_normalized;
+  int32_t reserved0;
+} rbpr_metric_outputs;
+int rbpr_score_metrics(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                       const int64_t* seen_indptr, const int32_t* seen_indices,
+                       const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
+                       const int32_t* ks, int32_t n_ks, const rbpr_metric_outputs* out, void* stream);
+/* Number of launches of the ranking kernel so far (one per <=512 MB block of users per call). */
+int64_t rbpr_topk_launch_count(const rbpr_ctx* ctx);
 
 /* Dense scores for a block of users: out (n_users, I) float, masked like above.
  * The eval-mode Model.forward output `logits` (model.py:43-47) for drop-in callers that

@@ -2,8 +2,8 @@
 
 Each function names the reference lines it restates (paths relative to the reference repo).
 Pinned against the reference itself by tests/golden/make_golden.py -> tests/golden/*.npz
-(tests/test_oracle_golden.py), and — in the build container, where /root/reference exists —
-directly against the imported reference (tests/test_oracle_vs_reference.py).
+(tests/test_oracle_golden.py); tests/golden/make_golden.py re-runs against /root/reference in the
+build container and reproduces every committed fixture bit for bit.
 
 This is also the "port" CPU baseline bench.py times: it performs the same work as the
 reference's own CPU path (materialised (B,I) sampling weights + torch.multinomial, dense

@@ -77,6 +77,7 @@ struct rbpr_ctx {
   int64_t collectives = 0;
   // instrumentation
   int64_t launches = 0;
+  int64_t topk_launches = 0;  // launches of the ranking kernel (tests assert one per eval batch)
   bool timing = false;
   uint64_t timing_tick = 0;
   std::vector<cudaEvent_t> ev;  // pairs

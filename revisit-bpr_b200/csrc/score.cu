@@ -155,6 +155,7 @@ struct TopkParams {
   const float* __restrict__ target;
   int64_t target_ld;
   int linear_gain;  // NDCG gain_function="linear": discount 1/(rank+1) instead of 1/log2(rank+2)
+  float* __restrict__ ndcg_linear_out;  // both gain functions from one pass (fused eval); needs !linear_gain
   int32_t* __restrict__ flag;
 };
 
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   __shared__ uint32_t s_prefix, s_need, s_cnt, s_tie_cnt;
   __shared__ unsigned long long sel[KCAP];
   __shared__ float disc_scan[KCAP], hit_scan[KCAP];
+  __shared__ float disc_lin[KCAP], hit_lin[KCAP];
   __shared__ uint32_t warp_tot[8];
 
   const int tid = threadIdx.x;
@@ -309,6 +311,11 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
     const float disc = p.linear_gain ? 1.0f / ((float)tid + 1.0f) : 1.0f / log2f((float)tid + 2.0f);
     disc_scan[tid] = disc;
     hit_scan[tid] = hit * disc;
+    if (p.ndcg_linear_out != nullptr) {
+      const float dl = 1.0f / ((float)tid + 1.0f);
+      disc_lin[tid] = dl;
+      hit_lin[tid] = hit * dl;
+    }
   }
   __syncthreads();
   // sequential prefix sums in rank order (fp32, like a left-to-right sum) by two threads
@@ -318,6 +325,12 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   } else if (tid == 32) {
     float s = 0.f;
     for (int r = 0; r < KCAP; ++r) { s += hit_scan[r]; hit_scan[r] = s; }
+  } else if (tid == 64 && p.ndcg_linear_out != nullptr) {
+    float s = 0.f;
+    for (int r = 0; r < KCAP; ++r) { s += disc_lin[r]; disc_lin[r] = s; }
+  } else if (tid == 96 && p.ndcg_linear_out != nullptr) {
+    float s = 0.f;
+    for (int r = 0; r < KCAP; ++r) { s += hit_lin[r]; hit_lin[r] = s; }
   }
   // hit counts: reuse ballots
   __shared__ uint32_t hitbits[4];
@@ -328,11 +341,12 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   __syncthreads();
   if (tid < p.n_ks) {
     const int kk = min(min(p.ks[tid], k), KCAP);
-    float ndcg = 0.f, recall = 0.f, precision = 0.f, ap = 0.f;
+    float ndcg = 0.f, ndcg_lin = 0.f, recall = 0.f, precision = 0.f, ap = 0.f;
     if (kk > 0 && n_pos > 0) {
       const float dcg = hit_scan[kk - 1];
       const float idcg = disc_scan[min(kk, n_pos) - 1];
       ndcg = dcg / idcg;
+      if (p.ndcg_linear_out != nullptr) ndcg_lin = hit_lin[kk - 1] / disc_lin[min(kk, n_pos) - 1];
       int hits = 0;
       for (int w = 0; w < 4; ++w) {
         const int lo = w * 32;
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
       }
     }
     if (p.ndcg_out) p.ndcg_out[orow * p.n_ks + tid] = ndcg;
+    if (p.ndcg_linear_out) p.ndcg_linear_out[orow * p.n_ks + tid] = ndcg_lin;
     if (p.recall_out) p.recall_out[orow * p.n_ks + tid] = recall;
     if (p.precision_out) p.precision_out[orow * p.n_ks + tid] = precision;
     if (p.map_out) p.map_out[orow * p.n_ks + tid] = ap;
@@ -399,11 +414,12 @@ int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
                      (cudaStream_t)stream);
 }
 
-int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
-                    const int64_t* seen_indptr, const int32_t* seen_indices,
-                    const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
-                    const int32_t* ks, int32_t n_ks, int32_t* topk_items, float* topk_scores,
-                    float* ndcg_out, float* recall_out, void* stream) {
+// Shared body of rbpr_score_topk / rbpr_score_metrics.
+static int score_topk_impl(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                           const int64_t* seen_indptr, const int32_t* seen_indices,
+                           const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
+                           const int32_t* ks, int32_t n_ks, int32_t* topk_items, float* topk_scores,
+                           const rbpr_metric_outputs* mo, void* stream) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!ctx->user_emb || !ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
   if (n_users == 0) return 0;
@@ -420,7 +436,8 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_topk: seen CSR must be both set or both NULL");
   if ((held_indptr == nullptr) != (held_indices == nullptr))
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_topk: held-out CSR must be both set or both NULL");
-  if ((ndcg_out || recall_out) && (!held_indptr || n_ks == 0))
+  const bool any_metric = mo && (mo->ndcg || mo->ndcg_linear || mo->recall || mo->precision || mo->map);
+  if (any_metric && (!held_indptr || n_ks == 0))
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_topk: metrics need the held-out CSR and cut-offs");
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -450,8 +467,14 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
   for (int q = 0; q < n_ks; ++q) tp.ks[q] = ks[q];
   tp.topk_items = topk_items;
   tp.topk_scores = topk_scores;
-  tp.ndcg_out = ndcg_out;
-  tp.recall_out = recall_out;
+  if (mo) {
+    tp.ndcg_out = mo->ndcg;
+    tp.ndcg_linear_out = mo->ndcg_linear;
+    tp.recall_out = mo->recall;
+    tp.precision_out = mo->precision;
+    tp.map_out = mo->map;
+    tp.map_normalized = mo->map_normalized;
+  }
   for (int64_t r0 = 0; r0 < n_users; r0 += blk) {
     const int nb = (int)((n_users - r0) < blk ? (n_users - r0) : blk);
     int rc = score_block(ctx, users + r0, nb, seen_indptr, seen_indices, r0, ctx->score_buf, ld, st);
@@ -459,10 +482,35 @@ int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
     tp.row0 = r0;
     topk_metrics<<<nb, 256, 0, st>>>(tp);
     ctx->launches++;
+    ctx->topk_launches++;
     RBPR_CUDA(ctx, cudaGetLastError());
   }
   return 0;
 }
+
+int rbpr_score_topk(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                    const int64_t* seen_indptr, const int32_t* seen_indices,
+                    const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
+                    const int32_t* ks, int32_t n_ks, int32_t* topk_items, float* topk_scores,
+                    float* ndcg_out, float* recall_out, void* stream) {
+  rbpr_metric_outputs mo;
+  memset(&mo, 0, sizeof(mo));
+  mo.ndcg = ndcg_out;
+  mo.recall = recall_out;
+  return score_topk_impl(ctx, users, n_users, seen_indptr, seen_indices, held_indptr, held_indices, k_max, ks,
+                         n_ks, topk_items, topk_scores, &mo, stream);
+}
+
+int rbpr_score_metrics(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
+                       const int64_t* seen_indptr, const int32_t* seen_indices,
+                       const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
+                       const int32_t* ks, int32_t n_ks, const rbpr_metric_outputs* out, void* stream) {
+  if (ctx && !out) RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_metrics: null outputs");
+  return score_topk_impl(ctx, users, n_users, seen_indptr, seen_indices, held_indptr, held_indices, k_max, ks,
+                         n_ks, out ? out->topk_items : nullptr, nullptr, out, stream);
+}
+
+int64_t rbpr_topk_launch_count(const rbpr_ctx* ctx) { return ctx ? ctx->topk_launches : 0; }
 
 int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
                             int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,
@@ -504,6 +552,7 @@ int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* tar
     tp.row0 = r0;
     topk_metrics<<<nb, 256, 0, (cudaStream_t)stream>>>(tp);
     ctx->launches++;
+    ctx->topk_launches++;
   }
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;

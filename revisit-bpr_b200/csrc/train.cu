@@ -3,8 +3,8 @@
 //
 // A call is cut into WAVES of whole steps.  Per wave, on the context's auxiliary stream:
 //   P1  count_users + bpr_sample — per-step occurrence count of every user (one atomic per
-//       triple into an L2-resident counter table; no sort), then a group of 8 lanes per slot
-//       draws the negative (Philox4x32-10, CSR rejection) and emits a 16-byte record
+//       triple into an L2-resident counter table; no sort), then a group of kSampleLanes (2) lanes
+//       per slot draws the negative (Philox4x32-10, Bloom filter + CSR rejection) and emits a 16-byte record
 //       {u, i+, i-, flags} where the flags say whether the user occurs once in its step.  The
 //       static samplers depend on (seed, step, triple, CSR) only, so wave w+1 is prepared while
 //       wave w trains.
@@ -69,23 +69,6 @@ __global__ void expand_rows(const int64_t* __restrict__ indptr, int64_t U, int64
     atomicOr(bloom + row * 8 + (h1 >> 5), 1u << (h1 & 31u));
     atomicOr(bloom + row * 8 + (h2 >> 5), 1u << (h2 & 31u));
   }
-}
-
-// Standalone sampler: one group of 8 lanes per triple.
-__global__ void sample_only(const TrainParams p, const int64_t* __restrict__ triple_idx,
-                            int64_t n64, int64_t* __restrict__ out) {
-  const Group<8> g;
-  int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
-  if (k >= n64) return;  // whole group exits together
-  int64_t t = triple_idx[k];
-  int32_t uu = p.coo_user[t];
-  uint32_t lo = (uint32_t)p.indptr[uu], hi = (uint32_t)p.indptr[uu + 1];
-  int32_t j = draw_negative<8>(p, (uint32_t)t, uu, lo, hi, g);
-  if (j < 0) {
-    if (g.gl == 0) atomicExch(p.flag, 1);
-    j = 1;
-  }
-  if (g.gl == 0) out[k] = (int64_t)j;
 }
 
 int check_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
@@ -422,6 +405,14 @@ int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void
 // defined in comm.cu
 int rbpr_internal_allreduce_item_grads(rbpr_ctx* ctx, cudaStream_t st);
 
+// The step's one exchange on stream st: dense item gradient summed over ranks, then the (dense,
+// identical on every rank) item update.
+int rbpr_internal_exchange_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
+  int rc = rbpr_internal_allreduce_item_grads(ctx, st);
+  if (rc) return rc;
+  return run_apply(ctx, step, hp, 1, 1, nullptr, 0, st);
+}
+
 // ---- helpers shared with dropin.cu ---------------------------------------------------------------
 int rbpr_internal_check_ready_tables(rbpr_ctx* ctx, const rbpr_hparams* hp) {
   return check_tables(ctx, hp);
@@ -438,6 +429,7 @@ int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int
                                 uint64_t step, float2* logit_out, const int32_t* step_pos,
                                 double* stats_out, cudaStream_t st) {
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, RBPR_STATS_PER_STEP * sizeof(double), st));
+  const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
   if (n > 0) {
     int lanes, nv, blocks = 1;
     rbpr_geometry(ctx->D, &lanes, &nv);
@@ -457,8 +449,15 @@ int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int
     int nb = 0;
     rc = run_phase_a(ctx, p, hp, records, reinterpret_cast<float4*>(ctx->partials[0]), blocks, st, &nb);
     if (rc) return rc;
-    rc = run_apply(ctx, step, hp, 0, 1, records, n, st, reinterpret_cast<const float4*>(ctx->partials[0]),
+    // data-parallel: users (owned by this rank) now, items after the exchange below
+    rc = run_apply(ctx, step, hp, 0, multi ? 0 : 1, records, n, st, reinterpret_cast<const float4*>(ctx->partials[0]),
                    nb * (kPhaseAThreads / 32), ctx->stats);
+    if (rc) return rc;
+  }
+  if (multi) {  // every rank takes part in the step's one exchange, with or without local triples
+    int rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, st);
+    if (rc) return rc;
+    rc = rbpr_internal_exchange_apply(ctx, step, hp, st);
     if (rc) return rc;
   }
   if (stats_out)
@@ -523,11 +522,13 @@ int rbpr_sample_negatives(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, u
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   TrainParams p;
   fill_train_params(ctx, p, seed, &hp);
-  p.step = step;
-  const int64_t threads = n * 8;
-  sample_only<<<(int)((threads + 255) / 256), 256, 0, st>>>(p, triple_idx, n, neg_out);
-  ctx->launches++;
-  RBPR_CUDA(ctx, cudaGetLastError());
+  if (n >= (1ll << 31)) RBPR_FAIL(ctx, RBPR_ERR_ARG, "sample: n must be < 2^31 per call");
+  // the wave sampler with one "step" of n slots and no records: only neg_out is written
+  p.triple_idx = triple_idx;
+  p.batch = n;
+  p.neg_out = neg_out;
+  int rc2 = run_sample(ctx, p, nullptr, n, step, st);
+  if (rc2) return rc2;
   return check_flag(ctx, st);
 }
 
@@ -673,9 +674,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
                        step_stats);
         if (rc) return rc;
         RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_users, ctx->aux2));
-        rc = rbpr_internal_allreduce_item_grads(ctx, st);
-        if (rc) return rc;
-        rc = run_apply(ctx, p.step, hp, 1, 1, nullptr, 0, st);
+        rc = rbpr_internal_exchange_apply(ctx, p.step, hp, st);
         if (rc) return rc;
         RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_users, 0));
       } else {

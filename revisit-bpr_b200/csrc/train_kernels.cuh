@@ -251,8 +251,8 @@ __host__ __device__ constexpr bool opt_has_s2(int opt) { return opt == RBPR_OPT_
 
 constexpr int kPhaseAThreads = 128;
 
-// P1 — negative sampling for every step of a WAVE in one launch.  A group of 8 lanes per slot
-// resolves (user, item), draws the negative with a cooperative 9-ary CSR probe, and emits a
+// P1 — negative sampling for every step of a WAVE in one launch.  A group of kSampleLanes lanes per slot
+// resolves (user, item), draws the negative with a cooperative (lanes+1)-ary CSR probe, and emits a
 // 16-byte record {u, i+, i-, flags} in input order.  The run flags come from the per-step user
 // occurrence counts built by count_users (train.cu): kRecSingle if the user occurs once in the
 // step, kRecMultiHead for ONE designated slot (arrival rank 0) of a user that occurs several times.
@@ -281,11 +281,14 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
   const uint64_t k = sl * (uint64_t)p.batch + local;
   if (k >= n_slots) return;
   int64_t t64 = __ldg(p.triple_idx + k);
-  if (t64 < 0 || t64 >= p.nnz) t64 = 0;  // flagged by count_users
+  if (t64 < 0 || t64 >= p.nnz) {
+    if (g.gl == 0) atomicExch(p.flag, 2);
+    t64 = 0;
+  }
   const uint32_t t = (uint32_t)t64;
   const int32_t uu = __ldg(p.coo_user + t);
   const int32_t i = __ldg(p.indices + t);
-  const int32_t flags = slot_flags(p, k, sl, uu);
+  const int32_t flags = (records != nullptr) ? slot_flags(p, k, sl, uu) : 0;  // sampler-only calls keep no counts
   int32_t j;
   if (p.sampler == RBPR_SAMPLER_INJECTED) {
     j = (int32_t)__ldg(p.neg_in + k);

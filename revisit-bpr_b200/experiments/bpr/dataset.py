@@ -73,6 +73,8 @@ class SparseSamplingInMemoryWithCollator(Dataset):
         su, soff, svals = ingest.read_lists(seen_items_path, "user", "seen_items")
         if su.size and (su.min() < 0 or su.max() >= num_users):
             raise IndexError("user id outside num_users in the seen-items file")
+        if svals.size and (svals.min() < 0 or svals.max() >= num_items):
+            raise IndexError("item id outside num_items in the seen-items file")
         lens = np.diff(soff)
         width = max(1, int(lens.max()) if lens.size else 1)
         dense = np.full((num_users, width), padding_value, dtype=np.int64)
@@ -103,6 +105,57 @@ class SparseSamplingInMemoryWithCollator(Dataset):
         return self._indptr, self._indices
 
 
+def _lists_to_csr(rows: list[Any]) -> tuple[torch.Tensor, torch.Tensor]:
+    """(indptr (n+1,) int64, indices int32 ascending per row, duplicates dropped) of a list of id lists."""
+    arrs = [np.unique(np.asarray(r, dtype=np.int64).reshape(-1)) for r in rows]
+    indptr = np.zeros(len(arrs) + 1, dtype=np.int64)
+    np.cumsum([a.size for a in arrs], out=indptr[1:])
+    flat = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.int64)
+    return torch.from_numpy(indptr), torch.from_numpy(flat.astype(np.int32))
+
+
+class AllItemsBatch(dict):
+    """The batch `AllItemsCollator` returns.  Same keys and tensors as the reference's
+    (experiments/bpr/dataset.py:274-296) — `user` (B,), `item` (B,I) = arange, `target` (B,I)
+    multi-hot, `seen_items` (B,S) 0-padded — but the three wide ones are only built when read: the
+    fused eval path (Model.forward -> AllItemsEval -> rbpr_score_metrics) works from the compact forms
+    `target_csr` / `seen_csr` and the `all_items` marker, so a (B,I) int64 + a (B,I) float matrix per
+    batch (30 MB at ML-20M, batch 128) never cross PCIe."""
+
+    _LAZY = ("item", "target", "seen_items")
+
+    def __init__(self, users: torch.Tensor, num_items: int, positives: list[Any], seen: list[Any],
+                 padding_value: float) -> None:
+        super().__init__(user=users, all_items=True, target_csr=_lists_to_csr(positives), seen_csr=_lists_to_csr(seen))
+        self._num_items, self._positives, self._seen_lists, self._pad = num_items, positives, seen, padding_value
+
+    def __missing__(self, key: str) -> torch.Tensor:
+        n, dev = self["user"].numel(), self["user"].device
+        if key == "item":
+            val = torch.arange(self._num_items, dtype=torch.long, device=dev).unsqueeze(0).repeat(n, 1)
+        elif key == "target":
+            indptr, indices = self["target_csr"]
+            val = torch.zeros(n, self._num_items, device=dev)
+            rows = torch.repeat_interleave(torch.arange(n), indptr[1:] - indptr[:-1])
+            val[rows.to(dev), indices.long().to(dev)] = 1.0
+        elif key == "seen_items":
+            val = pad_sequence([torch.as_tensor(s) for s in self._seen_lists], batch_first=True,
+                               padding_value=self._pad).to(dev)
+        else:
+            raise KeyError(key)
+        self[key] = val
+        return val
+
+    def __contains__(self, key: object) -> bool:
+        return key in self._LAZY or dict.__contains__(self, key)
+
+    def get(self, key: str, default: Any = None) -> Any:
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
 class AllItemsCollator:
     """Eval batches: every item scored for every user, multi-hot target, padded seen items."""
 
@@ -115,17 +168,8 @@ class AllItemsCollator:
         for inst in instances:
             for k, v in inst.items():
                 cols[k].append(v)
-        n = len(instances)
-        target = torch.zeros(n, self._num_items)
-        for r, pos in enumerate(cols["item"]):
-            target[r, torch.as_tensor(pos, dtype=torch.long)] = 1.0
-        return {
-            "user": torch.as_tensor(cols["user"]),
-            "item": torch.arange(self._num_items, dtype=torch.long).unsqueeze(0).repeat(n, 1),
-            "target": target,
-            "seen_items": pad_sequence([torch.as_tensor(s) for s in cols["seen_items"]], batch_first=True,
-                                       padding_value=self._padding_value),
-        }
+        return AllItemsBatch(torch.as_tensor(cols["user"]), self._num_items, cols["item"], cols["seen_items"],
+                             self._padding_value)
 
 
 class OnePosCollator:
@@ -162,20 +206,33 @@ class EpochChunks:
     `DataLoader(shuffle=True, generator=g)` would draw (reference exp.py:111-115)."""
 
     def __init__(self, dataset: SparseSamplingInMemoryWithCollator, batch_size: int, steps_per_chunk: int = 64,
-                 generator: torch.Generator | None = None, device: torch.device | str | None = None) -> None:
+                 generator: torch.Generator | None = None, device: torch.device | str | None = None,
+                 owned: tuple[int, int] | None = None, world: int = 1) -> None:
         self.dataset, self.batch_size, self.steps_per_chunk = dataset, int(batch_size), int(steps_per_chunk)
         self.generator, self.device = generator, device
         self.total_batch_size = self.batch_size
+        # data parallel: this rank permutes only the triples [lo, hi) of its own users, and every rank
+        # runs ceil(nnz / (B * world)) steps per epoch (each step ends in a collective)
+        self.owned, self.world = owned, int(world)
 
     @property
     def steps_per_epoch(self) -> int:
-        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+        per = self.batch_size * self.world
+        return (len(self.dataset) + per - 1) // per
 
     def __len__(self) -> int:
         return (self.steps_per_epoch + self.steps_per_chunk - 1) // self.steps_per_chunk
 
     def __iter__(self) -> Iterator[dict[str, Any]]:
-        perm = torch.randperm(len(self.dataset), generator=self.generator)
+        if self.owned is None:
+            perm = torch.randperm(len(self.dataset), generator=self.generator)
+        else:
+            lo, hi = self.owned
+            need = self.steps_per_epoch * self.batch_size
+            perm = torch.randperm(hi - lo, generator=self.generator) + lo
+            if 0 < perm.numel() < need:
+                perm = perm.repeat((need + perm.numel() - 1) // perm.numel())
+            perm = perm[:need]
         if self.device is not None:
             perm = perm.to(self.device)
         chunk = self.batch_size * self.steps_per_chunk

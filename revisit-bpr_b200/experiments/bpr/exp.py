@@ -157,11 +157,15 @@ class BPRExperiment:
         # Our extension: `fast_train: true` at the top level of the config replaces the B-sized train
         # batches by whole chunks of steps run inside the library (device sampling included).
         self._fast = bool(self._config.get("fast_train", False))
+        self._world, self._rank = self._process_group()
+        if self._world > 1:
+            self._enable_data_parallel()
         if self._fast:
             self._enable_fast_train(dev)
         self.trainer = self._get_trainer(self._model, self._optimizer, self._datasets)
         # counter-based device sampler: seed + iteration, like the reference's reseeded generator
-        self._neg_seed = self._seed + self.trainer.engines["train"].state.iteration
+        # (ranks draw from disjoint streams)
+        self._neg_seed = self._seed + self.trainer.engines["train"].state.iteration + 1000003 * self._rank
         self._neg_calls = 0
         self._sampler_ctx = Context(dev)
         if self._weighted:
@@ -207,6 +211,40 @@ class BPRExperiment:
         self._accelerator.free_memory()
         del self._accelerator, self.trainer
 
+    @staticmethod
+    def _process_group() -> tuple[int, int]:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+        return 1, 0
+
+    def _enable_data_parallel(self) -> None:
+        """One process per GPU (torchrun, or the reference's Distributed(...) + launcher.DDP,
+        experiments/decorator.py:30-54, launcher.py:35-73): users are sharded by owner, so this rank's
+        train loader only yields triples of ITS users (same number of batches on every rank), the
+        model joins the library's communicator (one all-reduce of the dense item gradient per step),
+        eval loaders hand every world-th batch to this rank, and the owner-sharded user rows are
+        gathered before every eval pass / checkpoint."""
+        from experiments.bpr.dataset import SparseSamplingInMemoryWithCollator
+        from rbpr.parallel import OwnerBatchSampler, RoundRobinBatches, shard_bounds
+        loader = self._datasets["train"]
+        ds = loader.dataset
+        if not isinstance(ds, SparseSamplingInMemoryWithCollator):
+            raise NotImplementedError("data-parallel BPR needs the SparseSamplingInMemoryWithCollator train dataset "
+                                      "(its CSR defines the owner blocks)")
+        indptr, _ = ds.csr()
+        self._user_cuts = shard_bounds(indptr, self._world)
+        self._model.enable_data_parallel(self._user_cuts)
+        if not self._fast:
+            sampler = OwnerBatchSampler(indptr, self._world, self._rank, loader.batch_size,
+                                        generator=torch.Generator().manual_seed(self._seed + self._rank))
+            sharded = torch.utils.data.DataLoader(ds, batch_sampler=sampler, collate_fn=ds.collate_fn,
+                                                  num_workers=loader.num_workers)
+            sharded.total_batch_size = loader.batch_size
+            self._datasets["train"] = sharded
+        for key in [k for k in self._datasets if k != "train"]:
+            self._datasets[key] = RoundRobinBatches(self._datasets[key], self._world, self._rank)
+
     def _enable_fast_train(self, dev: torch.device) -> None:
         from experiments.bpr.dataset import EpochChunks, SparseSamplingInMemoryWithCollator
         loader = self._datasets["train"]
@@ -224,8 +262,13 @@ class BPRExperiment:
         self._model.bind_interactions(torch.from_numpy(indptr), torch.from_numpy(indices), sampler=kind,
                                       seed=self._seed, item_weights=self._item_counts if self._weighted else None,
                                       adaptive_prob=self._adaptive_sampling_prob, adaptive_every=every)
+        owned = None
+        if self._world > 1:
+            from rbpr.parallel import owned_triples
+            owned = owned_triples(indptr, self._world, self._rank)
         self._datasets["train"] = EpochChunks(ds, bs, steps_per_chunk=int(self._config.get("fast_steps_per_chunk", 64)),
-                                              generator=torch.Generator().manual_seed(self._seed), device=dev)
+                                              generator=torch.Generator().manual_seed(self._seed + self._rank),
+                                              device=dev, owned=owned, world=self._world)
 
     def interrupt(self) -> None:
         for e in self.trainer.engines.values():
@@ -247,6 +290,14 @@ class BPRExperiment:
             trainer.add_event("train", Events.GET_BATCH_COMPLETED, self._train_batch)
         if self._skip_seen:
             trainer.add_event("eval", ModelEvents.FORWARD_COMPLETED, self._remove_seen_items)
+        for name in trainer.engines:
+            if name != "train" and getattr(self, "_world", 1) > 1:
+                trainer.add_event(name, Events.STARTED, self._sync_user_shards)
+            # kernels neutralise bad ids / an exhausted sampler and raise a device flag instead of
+            # failing in place: poll it after the first batch, at every epoch end and before eval
+            trainer.add_event(name, Events.ITERATION_COMPLETED, self._poll_after_first_batch)
+            trainer.add_event(name, Events.EPOCH_COMPLETED, self._poll_device_errors)
+        trainer.add_event("eval", Events.STARTED, self._poll_device_errors)
         early_stopping = None
         if self._early_stopping_metric is not None:
             early_stopping = attach_early_stopping(trainer, metric_name=self._early_stopping_metric,
@@ -301,9 +352,32 @@ class BPRExperiment:
     @torch.no_grad()
     def _remove_seen_items(self, engine: Any) -> None:
         batch, output = engine.state.batch, engine.state.output
-        if (seen := batch.get("seen_items")) is not None:
+        if getattr(output, "fused", False) and dict.__contains__(batch, "seen_csr"):
+            output.mask_seen(batch["seen_csr"])  # all-items batch: masking happens inside the scoring call
+        elif (seen := batch.get("seen_items")) is not None:
             self._sampler_ctx.mask_seen_padded(output["logits"], seen)
         self._to_device(batch)  # metrics read batch["target"] on the device next
+
+    def _sync_user_shards(self) -> None:
+        self._model.sync_user_shards()
+
+    def _poll_after_first_batch(self, engine: Any) -> None:
+        polled = self.__dict__.setdefault("_polled_engines", set())
+        if engine.state.name not in polled:
+            polled.add(engine.state.name)
+            self._poll_device_errors()
+
+    def _poll_device_errors(self, *_: Any) -> None:
+        """Raise (RuntimeError) what the kernels flagged since the last poll: out-of-range user / item
+        / triple ids, a user without any negative left, a metric target outside {0,1}."""
+        lm = getattr(self._model, "logits_model", None)
+        eng = getattr(lm, "_engine", None)
+        if eng is not None:
+            eng.sync_check()
+        self._sampler_ctx.sync_check()
+        from revisit_bpr.metrics import metric as _metric_mod
+        for ctx in _metric_mod._contexts.values():
+            ctx.sync_check()
 
     def _reset_metrics(self, engine: Any) -> None:
         if engine.state.was_interrupted:

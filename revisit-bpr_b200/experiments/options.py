@@ -35,7 +35,8 @@ def attach_metrics(trainer: Trainer, accelerator: Any, metrics: dict[str, Metric
         state = engine.state
         if state.skip_metrics or "target" not in state.batch:
             return
-        for key, m in metrics.items():
+        rest = _fused_update(state, metrics)
+        for key, m in rest.items():
             kwargs = {"mask": state.batch.get("mask")} if isinstance(m, MaskedMetric) else {}
             m(state.output["logits"], state.batch["target"], **kwargs)
             state.metrics[key] = m.get_metric()
@@ -45,8 +46,7 @@ def attach_metrics(trainer: Trainer, accelerator: Any, metrics: dict[str, Metric
 
         def reduce_handler(engine: Any) -> None:
             if not done["v"]:
-                engine.state.metrics = {k: accelerator.reduce(v, reduction="mean") if torch.is_tensor(v) else v
-                                        for k, v in engine.state.metrics.items()}
+                engine.state.metrics = _reduce_metrics(engine.state.metrics, metrics, accelerator)
             done["v"] = True
 
         def rearm() -> None:
@@ -62,6 +62,72 @@ def attach_metrics(trainer: Trainer, accelerator: Any, metrics: dict[str, Metric
         trainer.add_event(name, Events.EPOCH_STARTED, reset_handler)
         trainer.add_event(name, Events.ITERATION_COMPLETED, update_handler)
         trainer.add_event(name, Events.EPOCH_COMPLETED | Events.INTERRUPT, reduce_handler)
+
+
+def _reduce_metrics(values: dict[str, Any], metrics: dict[str, Metric], accelerator: Any) -> dict[str, Any]:
+    """Cross-rank reduction of an engine's metric dict (reference options.py:53-59 takes the mean of
+    the per-rank means).  Ranking metrics are reduced exactly instead — every rank contributes its
+    (sum of per-user values, number of users) and ONE all-reduce carries all of them; other tensor
+    entries (running losses) ride along as (value, 1), i.e. the mean over ranks."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return {k: accelerator.reduce(v, reduction="mean") if torch.is_tensor(v) else v for k, v in values.items()}
+    from rbpr.parallel import reduce_sum_count
+    keys = [k for k, v in values.items() if torch.is_tensor(v)]
+    if not keys:
+        return values
+    dev = accelerator.device
+    pairs = []
+    for k in keys:
+        m = metrics.get(k)
+        total = getattr(m, "_total", getattr(m, "_total_auc", None)) if m is not None else None
+        count = getattr(m, "_total_count", None) if m is not None else None
+        if torch.is_tensor(total) and torch.is_tensor(count):
+            pairs.append(torch.stack([total.to(dev, torch.float64), count.to(dev, torch.float64)]))
+        else:
+            pairs.append(torch.stack([values[k].detach().to(dev, torch.float64).reshape(()),
+                                      torch.ones((), dtype=torch.float64, device=dev)]))
+    means = reduce_sum_count(torch.stack(pairs))
+    out = dict(values)
+    for k, v in zip(keys, means):
+        out[k] = v.to(values[k].dtype)
+    return out
+
+
+def _fused_update(state: Any, metrics: dict[str, Metric]) -> dict[str, Metric]:
+    """Feed every metric that can be derived from ONE scoring + ranking pass (rbpr_score_metrics:
+    NDCG, Recall, Precision, MAP, FBeta at all their cut-offs) when the eval output is the lazy
+    all-items object; returns the metrics still to be updated the reference's way (from dense logits)."""
+    out, batch = state.output, state.batch
+    fused = getattr(out, "fused", False) and getattr(out, "masked", False) and dict.__contains__(batch, "target_csr")
+    if not fused:
+        return metrics
+    eng = out._model.logits_model.engine()
+    rest: dict[str, Metric] = {}
+    groups: dict[bool, list[tuple[str, Metric, tuple[str, ...]]]] = {}
+    for key, m in metrics.items():
+        req = m.fused_request() if hasattr(m, "fused_request") else None
+        if req is None:
+            rest[key] = m
+        else:  # one MAP normalisation per call: metrics asking for the other one form a second group
+            groups.setdefault(bool(getattr(m, "_normalized", True)), []).append((key, m, req))
+    if len(groups) == 2:  # fold the group without a MAP into the other one
+        for flag in (True, False):
+            if not any("map" in req for _, _, req in groups[flag]):
+                groups[not flag].extend(groups.pop(flag))
+                break
+    for normalized, members in groups.items():
+        ks = sorted({min(m._topk, eng.I) for _, m, _ in members})
+        want = tuple(sorted({name for _, _, req in members for name in req}))
+        for a in range(0, len(ks), 16):  # the kernel takes 16 cut-offs per pass
+            part = ks[a:a + 16]
+            res = out.ranking_metrics(batch["target_csr"], part, want, map_normalized=normalized)
+            for key, m, _ in members:
+                k = min(m._topk, eng.I)
+                if k in part:
+                    m.accumulate(m.fused_value(res, part.index(k)))
+                    state.metrics[key] = m.get_metric()
+    return rest
 
 
 class EarlyStopping:

@@ -72,6 +72,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.rbpr_launch_count(self.ctx))
 
+    def topk_launch_count(self) -> int:
+        """Launches of the ranking kernel by this context (one per eval batch on the fused path)."""
+        return int(self.lib.rbpr_topk_launch_count(self.ctx))
+
     def bind_item_weights(self, weights: torch.Tensor) -> None:
         """Popularity weights (I,) -> Walker alias table (weights[0] is forced to 0)."""
         w = weights.detach().double().cpu().numpy().copy()
@@ -479,6 +483,35 @@ class Engine(Context):
                                              _ptr(held_p), _ptr(held_i), k_max, ks_arr, len(ks),
                                              _ptr(items), _ptr(scores), _ptr(ndcg), _ptr(recall),
                                              _stream()))
+        return out
+
+    def score_metrics(self, users: torch.Tensor, seen: tuple[torch.Tensor, torch.Tensor] | None,
+                      held: tuple[torch.Tensor, torch.Tensor], ks: Sequence[int], want: Sequence[str] = ("ndcg", "recall"),
+                      map_normalized: bool = True, want_items: bool = False) -> dict[str, torch.Tensor]:
+        """ONE scoring + ranking pass: every requested metric family (`want` from ndcg, ndcg_linear,
+        recall, precision, map) at every cut-off of `ks` -> {name: (n_users, len(ks)) float32}."""
+        dev = self.device
+        users = users.to(dev, torch.int64).contiguous()
+        n = users.numel()
+        ks = [int(k) for k in ks]
+        k_max = max(ks)
+        if k_max > native.MAX_TOPK:
+            raise ValueError(f"topk={k_max} exceeds the kernel limit {native.MAX_TOPK}")
+        seen_p = seen_i = None
+        if seen is not None:
+            seen_p, seen_i = seen[0].to(dev, torch.int64).contiguous(), seen[1].to(dev, torch.int32).contiguous()
+        held_p, held_i = held[0].to(dev, torch.int64).contiguous(), held[1].to(dev, torch.int32).contiguous()
+        out = {name: torch.empty((n, len(ks)), dtype=torch.float32, device=dev) for name in want}
+        mo = native.MetricOutputs()
+        for name in ("ndcg", "ndcg_linear", "recall", "precision", "map"):
+            setattr(mo, name, out[name].data_ptr() if name in out else None)
+        if want_items:
+            out["items"] = torch.empty((n, k_max), dtype=torch.int32, device=dev)
+            mo.topk_items = out["items"].data_ptr()
+        mo.map_normalized = int(map_normalized)
+        ks_arr = (C.c_int32 * len(ks))(*ks)
+        self._check(self.lib.rbpr_score_metrics(self.ctx, _ptr(users), n, _ptr(seen_p), _ptr(seen_i), _ptr(held_p),
+                                                _ptr(held_i), k_max, ks_arr, len(ks), C.byref(mo), _stream()))
         return out
 
     def score_dense(self, users: torch.Tensor,

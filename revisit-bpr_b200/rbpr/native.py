@@ -11,7 +11,7 @@ OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
@@ -26,6 +26,7 @@ SYMBOLS = (
     "rbpr_comm_unique_id", "rbpr_comm_init", "rbpr_comm_allreduce_item_grads", "rbpr_collective_count",
     "rbpr_ingest_pairs", "rbpr_ingest_lists", "rbpr_ingest_free", "rbpr_ingest_last_error",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
+    "rbpr_score_metrics", "rbpr_topk_launch_count",
 )
 
 
@@ -35,6 +36,13 @@ class HParams(C.Structure):
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("reg_user", C.c_float), ("reg_item", C.c_float), ("reg_neg", C.c_float),
         ("adaptive_prob", C.c_float), ("adaptive_every", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
+class MetricOutputs(C.Structure):
+    _fields_ = [
+        ("ndcg", C.c_void_p), ("ndcg_linear", C.c_void_p), ("recall", C.c_void_p), ("precision", C.c_void_p),
+        ("map", C.c_void_p), ("topk_items", C.c_void_p), ("map_normalized", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -83,6 +91,9 @@ def load() -> C.CDLL:
         "rbpr_score_topk": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
                                       vp, vp, vp, vp, vp]),
         "rbpr_score_dense": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "rbpr_score_metrics": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
+                                         C.POINTER(MetricOutputs), vp]),
+        "rbpr_topk_launch_count": (i64, [vp]),
         "rbpr_train_step_triples": (C.c_int, [vp, vp, vp, vp, i64, u64, hp, vp, vp, vp]),
         "rbpr_pair_logits": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),

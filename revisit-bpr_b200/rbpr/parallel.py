@@ -58,3 +58,73 @@ class DataParallelTrainer:
             stats = stats.clone()
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
         return stats
+
+
+class OwnerBatchSampler:
+    """Index batches of ONE rank for `DataLoader(batch_sampler=...)`: a fresh permutation of the
+    triples owned by this rank every epoch, cut into `batch_size` batches.  Every rank yields the same
+    number of batches — ceil(nnz / (batch_size * world)) — because each step ends in a collective:
+    a shard a little shorter than that wraps around, a longer one drops its tail (owner blocks are
+    balanced by interaction count, so the difference is less than one user's row)."""
+
+    def __init__(self, indptr: np.ndarray, world: int, rank: int, batch_size: int,
+                 generator: torch.Generator | None = None) -> None:
+        self.lo, self.hi = owned_triples(indptr, world, rank)
+        self.batch_size, self.generator = int(batch_size), generator
+        nnz = int(indptr[-1])
+        self.steps = (nnz + self.batch_size * world - 1) // (self.batch_size * world)
+
+    def __len__(self) -> int:
+        return self.steps
+
+    def __iter__(self):
+        n = self.hi - self.lo
+        need = self.steps * self.batch_size
+        perm = torch.randperm(n, generator=self.generator) + self.lo
+        if 0 < n < need:
+            perm = perm.repeat((need + n - 1) // n)
+        perm = perm[:need].tolist()
+        for a in range(0, need, self.batch_size):
+            yield perm[a:a + self.batch_size]
+
+
+class RoundRobinBatches:
+    """Eval loader of one rank: every world-th batch of the underlying loader (what
+    accelerate.prepare_data_loader does to the reference's loaders, experiments/bpr/exp.py:110),
+    without padding the tail — per-rank (sum, count) pairs are reduced instead of means."""
+
+    def __init__(self, loader, world: int, rank: int) -> None:
+        self._loader, self._world, self._rank = loader, int(world), int(rank)
+
+    def __iter__(self):
+        for i, batch in enumerate(self._loader):
+            if i % self._world == self._rank:
+                yield batch
+
+    def __len__(self) -> int:
+        n = len(self._loader)
+        return n // self._world + (1 if self._rank < n % self._world else 0)
+
+    def __getattr__(self, name: str):
+        return getattr(self._loader, name)
+
+
+def reduce_sum_count(pairs: torch.Tensor, group: dist.ProcessGroup | None = None) -> torch.Tensor:
+    """ONE all-reduce of stacked (sum, count) pairs (n, 2) -> per-entry global mean (n,)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        pairs = pairs.clone()
+        dist.all_reduce(pairs, op=dist.ReduceOp.SUM, group=group)
+    return pairs[:, 0] / pairs[:, 1]
+
+
+def sync_row_shards(tensors: list[torch.Tensor], cuts: np.ndarray, group: dist.ProcessGroup | None = None) -> None:
+    """Make every rank hold every owner's rows: rows [cuts[r], cuts[r+1]) of each tensor are broadcast
+    from rank r (user rows and their optimizer state live only on their owner between eval passes)."""
+    world = dist.get_world_size(group)
+    for r in range(world):
+        a, b = int(cuts[r]), int(cuts[r + 1])
+        if b <= a:
+            continue
+        src = dist.get_global_rank(group, r) if group is not None else r
+        for t in tensors:
+            dist.broadcast(t[a:b], src=src, group=group)

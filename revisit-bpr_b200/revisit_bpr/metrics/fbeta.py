@@ -23,6 +23,15 @@ class FBeta(_TopkMean):
         num = (1.0 + b2) * both["precision"] * both["recall"]
         return num / (b2 * both["precision"] + both["recall"] + 1e-13)
 
+    def fused_request(self) -> tuple[str, ...] | None:
+        from rbpr import native
+        return None if self._topk > native.MAX_TOPK else ("precision", "recall")
+
+    def fused_value(self, res: dict[str, torch.Tensor], col: int) -> torch.Tensor:
+        b2 = self._beta * self._beta
+        pr, rc = res["precision"][:, col], res["recall"][:, col]
+        return (1.0 + b2) * pr * rc / (b2 * pr + rc + 1e-13)
+
     # The reference keeps (never updated) Precision / Recall sub-metrics in its state; their entries
     # are reproduced so that checkpoints written by either implementation load in the other.
     def state_dict(self) -> dict[str, Any]:

@@ -11,6 +11,7 @@ class MAP(_TopkMean):
     def __init__(self, topk: int, normalized: bool = True) -> None:
         super().__init__(topk)
         self._normalized = normalized
+        self._fused_family = "map"  # one normalisation per ranking pass: attach_metrics groups by it
 
     def compute(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         return topk_metrics(output, target, self._topk, validate=True, map_normalized=self._normalized)["map"]

@@ -146,6 +146,24 @@ class _TopkMean(Metric):
         self._total_count += torch.tensor(target.size(0), device=output.device)
         self._total += self.compute(output, target).sum()
 
+    # ---- fused evaluation (experiments.options.attach_metrics): one ranking pass feeds every metric --
+    _fused_family: str | None = None  # which output of rbpr_score_metrics this metric reads
+
+    def fused_request(self) -> tuple[str, ...] | None:
+        """Names of the rbpr_score_metrics outputs this metric is computed from at cut-off `_topk`
+        (None: not computable from the shared ranking pass)."""
+        if self._fused_family is None or self._topk > native.MAX_TOPK:
+            return None
+        return (self._fused_family,)
+
+    def fused_value(self, res: dict[str, torch.Tensor], col: int) -> torch.Tensor:
+        return res[self._fused_family][:, col]
+
+    def accumulate(self, values: torch.Tensor) -> None:
+        """Add per-user values (B,) computed elsewhere (same bookkeeping as __call__)."""
+        self._total_count += torch.tensor(float(values.size(0)), device=values.device)
+        self._total += values.sum()
+
     def get_metric(self, reset: bool = False) -> torch.Tensor:
         metric = self._total / self._total_count
         if reset:

@@ -12,6 +12,7 @@ class NDCG(_TopkMean):
         assert gain_function in ("exp", "linear"), f"Invalid gain_function value: {gain_function}"
         super().__init__(topk)
         self._linear = gain_function == "linear"
+        self._fused_family = "ndcg_linear" if self._linear else "ndcg"
 
     def compute(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         return topk_metrics(output, target, self._topk, linear_gain=self._linear)["ndcg"]

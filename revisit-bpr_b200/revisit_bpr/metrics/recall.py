@@ -7,6 +7,7 @@ from revisit_bpr.metrics.metric import _TopkMean, topk_metrics
 
 class Recall(_TopkMean):
     _key = "recall"
+    _fused_family = "recall"
 
     def compute(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         return topk_metrics(output, target, self._topk, validate=True)["recall"]

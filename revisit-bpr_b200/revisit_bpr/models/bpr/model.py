@@ -28,6 +28,11 @@ from rbpr.engine import Engine
 from revisit_bpr.models.bpr.loss import Loss
 
 
+def _f32(x: float) -> float:
+    import ctypes
+    return ctypes.c_float(float(x)).value
+
+
 class BaseLogitModel(torch.nn.Module):
     def get_features(self) -> dict[str, torch.Tensor]:
         return {}
@@ -79,8 +84,12 @@ class MF(BaseLogitModel):
                 "revisit_bpr.models.bpr.MF runs on a B200 only (librbpr.so, sm_100a): move the model "
                 "to CUDA; there is no CPU fallback")
         for emb in (self._user_emb, self._item_emb):
-            if emb.padding_idx not in (None, 0):
-                raise NotImplementedError("only padding_idx in (None, 0) is supported")
+            if emb.padding_idx != 0:
+                # the kernels hard-wire row 0 as the padding row (never sampled, never updated, always
+                # masked), which is what every reference config sets; with padding_idx=None the
+                # reference would TRAIN row 0 — refusing beats silently freezing it
+                raise NotImplementedError("the CUDA BPR path needs nn.Embedding(..., padding_idx=0) on both tables "
+                                          f"(got padding_idx={emb.padding_idx})")
         key = (uw.data_ptr(), iw.data_ptr(), None if ib is None else ib.data_ptr(), tuple(uw.shape),
                tuple(iw.shape))
         if self._engine is None or self._engine_key != key:
@@ -97,6 +106,61 @@ class MF(BaseLogitModel):
         eng = self.engine()
         ub = None if self._user_bias is None else self._user_bias.data
         return eng.pair_logits(user, item, mask, ub)
+
+
+class AllItemsEval(dict):
+    """Eval-mode output of `Model.forward` for a batch that scores EVERY item for each user (the
+    `AllItemsCollator` batches of the reference, experiments/bpr/dataset.py:274-296).
+
+    It behaves like the reference's `{"logits": (B, I)}` dict, but the matrix is only built when
+    somebody reads `["logits"]` (one fp32 scoring kernel, rbpr_score_dense).  The metric hook of
+    `experiments.options.attach_metrics` does not: it asks `ranking_metrics` for NDCG / Recall /
+    Precision / MAP at every cut-off in ONE fused scoring + ranking call (rbpr_score_metrics), which is
+    what replaces reference model.py:43-47 + exp.py:369-374 + one full sort per metric object."""
+
+    def __init__(self, model: "Model", users: torch.Tensor) -> None:
+        super().__init__()
+        self._model, self._users = model, users
+        self._seen: tuple[torch.Tensor, torch.Tensor] | None = None
+        self.masked = False
+
+    @property
+    def fused(self) -> bool:
+        """True until the dense logits have been materialised (after that they are authoritative:
+        a handler may have edited them in place)."""
+        return not dict.__contains__(self, "logits")
+
+    def mask_seen(self, seen_csr: tuple[torch.Tensor, torch.Tensor]) -> None:
+        """`_remove_seen_items` (reference exp.py:369-374) for the fused path: remember the rows to
+        push to -1e13 (plus column 0) instead of editing a matrix."""
+        self._seen, self.masked = seen_csr, True
+
+    def ranking_metrics(self, held_csr: tuple[torch.Tensor, torch.Tensor], ks: list[int], want: tuple[str, ...],
+                        map_normalized: bool = True) -> dict[str, torch.Tensor]:
+        eng = self._model.logits_model.engine()
+        return eng.score_metrics(self._users, self._seen, held_csr, ks, want=want, map_normalized=map_normalized)
+
+    def __missing__(self, key: str) -> torch.Tensor:
+        if key != "logits":
+            raise KeyError(key)
+        lm = self._model.logits_model
+        eng = lm.engine()
+        if self.masked:
+            logits = eng.score_dense(self._users, self._seen)
+        else:  # nothing masked (skip_seen=False): column 0 keeps its real score, as in the reference
+            items = torch.arange(eng.I, device=eng.device).unsqueeze(0).expand(self._users.numel(), -1)
+            logits = lm(self._users.to(eng.device), items.contiguous())
+        self["logits"] = logits
+        return logits
+
+    def __contains__(self, key: object) -> bool:
+        return key == "logits" or dict.__contains__(self, key)
+
+    def get(self, key: str, default: Any = None) -> Any:
+        try:
+            return self[key]
+        except KeyError:
+            return default
 
 
 class _AppliedStep(torch.autograd.Function):
@@ -237,6 +301,12 @@ class Model(torch.nn.Module):
         if self._opt_kind == native.OPT_SGD:
             eng.set_sgd(float(g["lr"]))
         elif self._opt_kind == native.OPT_SGDM:
+            # the zero-gradient catch-up of lazily updated user rows replays the missed steps with the
+            # learning rate in force NOW (only Adam keeps a per-step table): when a scheduler moved lr,
+            # bring every row up to date with the old value first
+            if self._adam_last is not None and eng.hp.optimizer == native.OPT_SGDM and eng.hp.lr != 0.0 \
+                    and eng.hp.lr != _f32(g["lr"]):
+                eng.flush_lazy(self._opt_step)
             eng.set_sgd_momentum(float(g["lr"]), float(g["momentum"]), bool(g.get("nesterov", False)),
                                  state=self._state1(eng, "momentum_buffer", with_step=False))
         elif self._opt_kind == native.OPT_RMSPROP:
@@ -265,6 +335,37 @@ class Model(torch.nn.Module):
         self.flush()
         return super().state_dict(*args, **kwargs)
 
+    # ---- data parallel (one process per GPU) ------------------------------------------------------
+    def enable_data_parallel(self, user_cuts: Any, group: Any = None) -> None:
+        """Join the library's NCCL communicator: from now on every training step of this model ends in
+        ONE all-reduce of the dense item gradient (rbpr_train_steps / rbpr_train_step_triples), so all
+        ranks must run the same number of steps.  `user_cuts` (world+1,) are the owner blocks of user
+        rows (rbpr.parallel.shard_bounds): each rank must only be fed triples of its own users.
+        Replaces Distributed(...) + launcher.DDP + accelerator.prepare of the reference
+        (experiments/decorator.py:30-54, launcher.py:35-73, bpr/exp.py:101-105)."""
+        import numpy as np
+        eng = self.logits_model.engine()
+        if getattr(eng, "world", 1) <= 1:
+            eng.init_comm(group)
+        self._dp = {"cuts": np.asarray(user_cuts, dtype=np.int64), "group": group}
+
+    @torch.no_grad()
+    def sync_user_shards(self) -> None:
+        """All-gather the owner-sharded user rows (and their optimizer state) so that every rank can
+        evaluate any user and rank 0 can write a complete checkpoint."""
+        dp = getattr(self, "_dp", None)
+        if dp is None:
+            return
+        from rbpr.parallel import sync_row_shards
+        self.flush()
+        feats = self.logits_model.get_features()
+        tensors = [feats["user"].data]
+        if self._optimizer is not None:
+            st = self._optimizer.state.get(feats["user"], {})
+            tensors += [st[k] for k in ("exp_avg", "exp_avg_sq", "momentum_buffer", "square_avg")
+                        if torch.is_tensor(st.get(k))]
+        sync_row_shards(tensors, dp["cuts"], dp["group"])
+
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
         lm = self.logits_model
@@ -272,6 +373,8 @@ class Model(torch.nn.Module):
             return self._forward_unfused(inputs)
         if not self.training:
             self.flush()
+            if inputs.get("all_items") is True and lm._user_bias is None and inputs.get("mask") is None:
+                return AllItemsEval(self, inputs["user"])
             return {"logits": lm(inputs["user"], inputs["item"], inputs, mask=inputs.get("mask"))}
         if "triple_idx" in inputs:
             return self._forward_triple_ids(inputs)

@@ -17,10 +17,29 @@ def pytest_configure(config):
     # the C-ABI library is a build artefact (git-ignored): a fresh checkout builds it once, in-tree,
     # exactly as __graft_entry__.build() does (nvcc cross-compiles without a GPU)
     if not (PKG / "librbpr.so").exists():
-        import shutil
-        import subprocess
-        if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
-            subprocess.run(["bash", str(PKG / "csrc" / "build.sh")], check=True, capture_output=True)
+        _build_library_once()
+
+
+def _build_library_once() -> None:
+    """Build under a file lock (xdist workers race otherwise); a failed build must not abort the
+    host-only tests: the compiler log is shown as a warning and GPU / native tests fail on load."""
+    import fcntl
+    import os
+    import shutil
+    import subprocess
+    import warnings
+    nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if Path("/usr/local/cuda/bin/nvcc").exists() else None)
+    if nvcc is None:
+        return
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if (PKG / "librbpr.so").exists():
+            return
+        r = subprocess.run(["bash", str(PKG / "csrc" / "build.sh")], capture_output=True, text=True,
+                           env={**os.environ, "NVCC": nvcc})
+        if r.returncode != 0:
+            warnings.warn("building librbpr.so failed (native and GPU tests will fail to load it):\n"
+                          + (r.stdout + r.stderr)[-4000:], stacklevel=1)
 
 
 @pytest.fixture(scope="session")

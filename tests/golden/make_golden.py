@@ -186,6 +186,12 @@ def main():
     train_case("adam_bias_ui", Model, MF, UniformSampler, opt="Adam",
                opt_kw={"lr": 5e-3, "betas": (0.8, 0.99)}, reg={"user": 0.01, "item": 0.02}, bias=True,
                **{**common, "steps": 9})
+    train_case("sgdm_nesterov", Model, MF, UniformSampler, opt="SGD",
+               opt_kw={"lr": 0.02, "momentum": 0.9, "nesterov": True},
+               reg={"user": 0.0016, "item": 0.0001, "neg": 0.00375}, bias=True, **{**common, "steps": 8})
+    train_case("rmsprop", Model, MF, UniformSampler, opt="RMSprop",
+               opt_kw={"lr": 0.005, "alpha": 0.9, "momentum": 0.0}, reg={"all": 0.001}, bias=True,
+               **{**common, "steps": 8})
     metrics_case(NDCG, Recall)
     sampler_case(UniformSampler)
     adaptive_case(Model, MF)

@@ -309,3 +309,130 @@ def test_experiment_checkpoints_and_resumes_from_dir(tmp_path, optimizer, lr, fa
         np.testing.assert_allclose(float(rest.metrics[k]), float(full.metrics[k]), atol=2e-3, err_msg=k)
     np.testing.assert_allclose(tr.metrics["loss"].item(), full.trainer.engines["train"].state.metrics["loss"].item(),
                                rtol=1e-4)
+
+
+STOCK_METRICS = """
+    ndcg@100: {_target_: revisit_bpr.metrics.NDCG, topk: 100}
+    recall@100: {_target_: revisit_bpr.metrics.Recall, topk: 100}
+    ndcg@10: {_target_: revisit_bpr.metrics.NDCG, topk: 10}
+    recall@10: {_target_: revisit_bpr.metrics.Recall, topk: 10}
+    auc: {_target_: revisit_bpr.metrics.RocAucManySlow}
+    ndcg@5: {_target_: revisit_bpr.metrics.NDCG, topk: 5}
+    recall@5: {_target_: revisit_bpr.metrics.Recall, topk: 5}
+    recall@20: {_target_: revisit_bpr.metrics.Recall, topk: 20}
+    ndcg@50: {_target_: revisit_bpr.metrics.NDCG, topk: 50}
+    recall@50: {_target_: revisit_bpr.metrics.Recall, topk: 50}
+    precision@5: {_target_: revisit_bpr.metrics.Precision, topk: 5}
+    precision@10: {_target_: revisit_bpr.metrics.Precision, topk: 10}
+    precision@50: {_target_: revisit_bpr.metrics.Precision, topk: 50}
+    precision@100: {_target_: revisit_bpr.metrics.Precision, topk: 100}
+"""
+
+
+def test_eval_ranks_once_per_batch_for_the_stock_metric_set(tmp_path):
+    """The 14 metrics every RQ2 config attaches (configs/RQ2/neg-sampling/ada-sampling-ml-20m.yaml.j2:13-55):
+    the 13 ranking metrics come from ONE scoring + ranking call per eval batch (rbpr_score_metrics),
+    only the AUC reads dense logits; values equal those of the metric classes fed dense tensors."""
+    import jinja2
+    from experiments._instantiate import instantiate
+    from revisit_bpr import metrics as M
+    inter, train_rows, test_rows = _write_dataset(tmp_path, n_users=150, n_items=260, seed=9)
+    text = CONFIG[:CONFIG.index("  metrics:")] + "  metrics:" + STOCK_METRICS + CONFIG[CONFIG.index("datasets:"):]
+    cfg = yaml.safe_load(jinja2.Template(text, undefined=jinja2.StrictUndefined).render(
+        dataset=str(tmp_path), num_users=inter.num_users - 1, num_items=inter.num_items - 1, epochs=1, adaptive=False,
+        train_batch_size=64, embedding_dim=16, optimizer="torch.optim.SGD", lr=0.05, item_bias="true"))
+    # extra families in the same pass: MAP (both normalisations -> two passes), FBeta, linear-gain NDCG
+    exp_cfg = cfg.pop("experiment")
+    exp = instantiate(exp_cfg, exp_config=lambda: cfg, dir=None, debug=False, seed=13, trackers_params={})
+    counts = {}
+    orig_run = type(exp)._get_trainer
+
+    def spy(self, *a, **k):
+        tr = orig_run(self, *a, **k)
+        eng = self._model.logits_model.engine()
+        from experiments.trainer import Events
+        tr.add_event("eval", Events.STARTED, lambda: counts.__setitem__("t0", eng.topk_launch_count()))
+        tr.add_event("eval", Events.COMPLETED, lambda e: counts.__setitem__("last", (eng.topk_launch_count() - counts["t0"],
+                                                                                    e.state.iteration)))
+        return tr
+
+    type(exp)._get_trainer = spy
+    try:
+        exp.run()
+    finally:
+        type(exp)._get_trainer = orig_run
+    launches, batches = counts["last"]
+    n_eval_users = len(test_rows)
+    assert batches % ((n_eval_users + 31) // 32) == 0  # iteration counts accumulate over eval passes
+    assert launches == (n_eval_users + 31) // 32, (launches, batches)  # ONE ranking launch per eval batch
+    # same numbers as the metric classes on dense tensors (the reference's calling convention)
+    dev = torch.device("cuda:0")
+    model = exp._model
+    model.eval()
+    users = sorted(test_rows)
+    eng = model.logits_model.engine()
+    seen = torch.nn.utils.rnn.pad_sequence([torch.as_tensor(train_rows[u]) for u in users], batch_first=True)
+    items = torch.arange(inter.num_items).unsqueeze(0).repeat(len(users), 1)
+    with torch.no_grad():
+        logits = model({"user": torch.as_tensor(users).to(dev), "item": items.to(dev)})["logits"]
+    exp._sampler_ctx.mask_seen_padded(logits, seen)
+    target = torch.zeros(len(users), inter.num_items)
+    for r, u in enumerate(users):
+        target[r, torch.as_tensor(test_rows[u])] = 1.0
+    target = target.to(dev)
+    for key, m in (("ndcg@100", M.NDCG(100)), ("recall@20", M.Recall(20)), ("precision@50", M.Precision(50)),
+                   ("ndcg@5", M.NDCG(5)), ("recall@100", M.Recall(100))):
+        np.testing.assert_allclose(exp.metrics[key].item(), m.compute(logits, target).mean().item(), atol=1e-6, err_msg=key)
+    del eng
+
+
+def test_fused_eval_output_families_match_dense_metric_classes():
+    """rbpr_score_metrics vs the metric classes on the dense matrix, all families and both MAP
+    normalisations, linear-gain NDCG and FBeta, through the update handler's grouping."""
+    from types import SimpleNamespace
+    from experiments.bpr.dataset import AllItemsCollator
+    from experiments.options import _fused_update
+    from revisit_bpr import metrics as M
+    from revisit_bpr.models.bpr import MF, Model
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    U, I, D = 90, 333, 24
+    model = Model(MF(torch.nn.Embedding(U, D, padding_idx=0), torch.nn.Embedding(I, D, padding_idx=0), item_bias=True)).to(dev)
+    with torch.no_grad():
+        model.logits_model._item_bias.normal_(0, 0.01)
+    model.eval()
+    rng = np.random.default_rng(2)
+    insts = []
+    for u in range(1, 60):
+        row = rng.permutation(np.arange(1, I))[: rng.integers(3, 40)]
+        k = max(1, row.size // 4)
+        insts.append({"user": u, "item": sorted(row[:k].tolist()), "seen_items": sorted(row[k:].tolist())})
+    insts[5]["item"] = []  # a user without positives scores 0 and still counts
+    batch = AllItemsCollator(I)(insts)
+    for k, v in list(batch.items()):
+        if torch.is_tensor(v):
+            batch[k] = v.to(dev)
+    out = model(batch)
+    assert out.fused
+    out.mask_seen(batch["seen_csr"])
+    mk = lambda: {"ndcg@10": M.NDCG(10), "ndcgl@20": M.NDCG(20, "linear"), "recall@20": M.Recall(20),  # noqa: E731
+                  "precision@7": M.Precision(7), "map@30": M.MAP(30), "mapu@30": M.MAP(30, normalized=False),
+                  "f@15": M.FBeta(15, beta=0.5), "ndcg@500": M.NDCG(500), "auc": M.RocAucManySlow()}
+    fused, dense = mk(), mk()
+    for m in list(fused.values()) + list(dense.values()):
+        m.reset()
+    eng = model.logits_model.engine()
+    t0 = eng.topk_launch_count()
+    state = SimpleNamespace(output=out, batch=batch, metrics={})
+    rest = _fused_update(state, fused)
+    assert set(rest) == {"ndcg@500", "auc"}          # k > 128 and AUC need the dense matrix
+    assert eng.topk_launch_count() - t0 == 2          # two MAP normalisations -> two passes, nothing more
+    assert out.fused                                   # ... and no (B, I) matrix was built for them
+    logits, target = out["logits"], batch["target"]
+    assert not out.fused and logits.shape == (len(insts), I) and target.shape == logits.shape
+    for key, m in dense.items():
+        if key in rest:
+            continue
+        m(logits, target)
+        np.testing.assert_allclose(fused[key].get_metric().item(), m.get_metric().item(), atol=1e-6, err_msg=key)
+        assert float(fused[key]._total_count) == len(insts)
