@@ -51,6 +51,7 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
+  cudaFree(ctx->stamp);
   cudaFree(ctx->ord);
   cudaFree(ctx->cnt);
   cudaFree(ctx->stats);
@@ -100,6 +101,8 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
+  cudaFree(ctx->stamp);
+  ctx->stamp = nullptr;
   ctx->item_grad = nullptr;
   ctx->user_grad = nullptr;
   ctx->touched = nullptr;

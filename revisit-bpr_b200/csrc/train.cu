@@ -405,6 +405,11 @@ int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void
 // defined in comm.cu
 int rbpr_internal_allreduce_item_grads(rbpr_ctx* ctx, cudaStream_t st);
 
+// defined in train_small.cu
+bool rbpr_small_batch_eligible(const rbpr_ctx* ctx, int64_t batch);
+int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* records, int64_t n, int n_steps,
+                            double* stats, cudaStream_t st);
+
 // The step's one exchange on stream st: dense item gradient summed over ranks, then the (dense,
 // identical on every rank) item update.
 int rbpr_internal_exchange_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
@@ -596,6 +601,9 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
   TrainParams p;
   fill_train_params(ctx, p, seed, hp);
   const bool piped = nwaves > 1 && !adaptive;
+  // small batches (the reference configs' own 256): a persistent cluster kernel runs whole waves
+  const bool small = hp->optimizer == RBPR_OPT_SGD && !adaptive && !(ctx->comm != nullptr && ctx->world > 1) &&
+                     rbpr_small_batch_eligible(ctx, batch) && getenv("RBPR_NO_SMALL_BATCH") == nullptr;
   cudaStream_t prep_st = piped ? ctx->aux : st;
   if (piped) {
     RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, st));
@@ -654,7 +662,15 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
     const int64_t wsteps = wave_steps(w);
     if (piped) RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
-    for (int64_t s = 0; s < wsteps; ++s) {
+    if (small) {
+      // all steps of the wave in ONE launch of one thread-block cluster (train_small.cu)
+      p.batch = batch;
+      p.step = step0 + (uint64_t)wave_step0(w);
+      rc = rbpr_launch_small_steps(ctx, p, reinterpret_cast<const int4*>(ctx->records[b]), nw, (int)wsteps,
+                                   ctx->stats + wave_step0(w) * RBPR_STATS_PER_STEP, st);
+      if (rc) return rc;
+    }
+    for (int64_t s = 0; s < wsteps && !small; ++s) {
       const int64_t soff = s * batch;
       p.n = (int)((nw - soff) < batch ? (nw - soff) : batch);
       p.step = step0 + (uint64_t)(wave_step0(w) + s);

@@ -1,0 +1,299 @@
+// Small-batch training path for sm_100a: MANY consecutive steps in ONE launch of ONE thread-block
+// cluster (8 CTAs x 512 threads), hardware cluster barriers between the halves of a step.
+//
+// Why: at the reference configs' own batch size (train_batch_size 256, README.md:305) a step moves
+// 0.8 MB — a fraction of a microsecond of memory time — and the two dependent launches of the
+// large-batch path (bpr_phase_a, bpr_apply) cost 10.6 us per step.  A grid-wide cooperative kernel
+// was tried in round 1 and lost (two grid.sync per step cost more than two launches:
+// profiles/r02d_coop_experiment.txt).  A cluster barrier is a hardware barrier among <= 8 SMs
+// (~0.2 us), and 4096 threads are exactly one 16-lane group per triple at B=256, D=128.
+//
+// One step (exact synchronous-minibatch semantics, same arithmetic as train_kernels.cuh):
+//   A  every lane group takes triples of the step: the three rows are read with ld.global.cg
+//      (L2: another CTA of the cluster may have written them in the previous step, L1 is not
+//      coherent), dot / softplus / gradients as in bpr_phase_a; item gradients go to the dense
+//      accumulator with red.global.add.v4.f32, a user occurring once is updated in place, a user
+//      occurring several times accumulates into the user-gradient buffer;
+//   -- barrier.cluster (release/acquire, after a device-scope fence) --
+//   B  the same groups walk the same records again: the first group to reach an item row this step
+//      (atomicExch on a per-item epoch stamp) applies its accumulated gradient and clears it; the
+//      designated triple of a repeated user applies the user row.  No scan over the catalogue, no
+//      touched-flag pass: the work of a step is proportional to its batch.
+//   -- barrier.cluster --
+// Plain SGD only (a stateful optimizer moves every item row every step — dense torch.optim
+// semantics — which is a sweep over the table, not a small-batch operation); everything else takes
+// the large-batch path.  Reference call sites replaced: as rbpr_train_steps (include/rbpr.h).
+#include "train_kernels.cuh"
+
+using namespace rbpr_dev;
+
+namespace {
+
+constexpr int kSmallThreads = 512;
+constexpr int kSmallCluster = 8;
+
+struct SmallParams {
+  TrainParams t;        // tables, accumulators, hyper-parameters (t.batch = triples per step)
+  float* item_emb_w;    // the item table, writable
+  float* item_bias_w;   // or null
+  uint32_t* stamp;      // (I) epoch in which each item row was last applied
+  uint32_t epoch0;      // stamp value of the first step of this launch (unique per executed step)
+  const int4* records;  // the wave's records {u, i+, i-, flags}
+  int64_t n;            // triples in the wave
+  int n_steps;
+  double* stats;        // (n_steps, RBPR_STATS_PER_STEP), zeroed by the caller
+};
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void cluster_barrier() {
+  __threadfence();  // reds / stores of this thread are performed at L2 before the barrier releases
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallParams sp) {
+  const TrainParams& p = sp.t;
+  const Group<LANES> g;
+  const int D = p.D;
+  __shared__ float4 s_part[kSmallThreads / 32];
+  const uint32_t groups_total = (gridDim.x * kSmallThreads) / LANES;
+  const uint32_t gid = (blockIdx.x * kSmallThreads + threadIdx.x) / LANES;
+  const float lr = p.lr;
+  bool colok[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
+
+  for (int s = 0; s < sp.n_steps; ++s) {
+    const int64_t off = (int64_t)s * p.batch;
+    const int64_t left = sp.n - off;
+    const uint32_t n = (uint32_t)(left < p.batch ? left : p.batch);
+    const int4* recs = sp.records + off;
+    const uint32_t tag = sp.epoch0 + (uint32_t)s;
+    float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
+
+    // ---- A: gather, loss, gradients ---------------------------------------------------------------
+    for (uint32_t k = gid; k < n; k += groups_total) {
+      const int4 rec = __ldg(recs + k);
+      const int32_t uu = rec.x, i = rec.y, j = rec.z;
+      const bool single = (rec.w & kRecSingle) != 0;
+      const float* urow = p.user_emb + (size_t)uu * D;
+      const float* irow = p.item_emb + (size_t)i * D;
+      const float* jrow = p.item_emb + (size_t)j * D;
+      float4 u[NV], vi[NV], vj[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = 4 * (g.gl + LANES * v);
+        u[v] = colok[v] ? ldcg4(urow + c) : f4zero();
+        vi[v] = colok[v] ? ldcg4(irow + c) : f4zero();
+        vj[v] = colok[v] ? ldcg4(jrow + c) : f4zero();
+      }
+      float pp = 0.f, pn = 0.f, sq = 0.f, usq = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        pp += dot4(u[v], vi[v]);
+        pn += dot4(u[v], vj[v]);
+        sq += p.reg_item * dot4(vi[v], vi[v]) + p.reg_neg * dot4(vj[v], vj[v]);
+        usq += dot4(u[v], u[v]);
+      }
+      float x = g.sum(pp - pn);
+      if (p.item_bias != nullptr) x += __ldcg(p.item_bias + i) - __ldcg(p.item_bias + j);
+      const float e = __expf(-fabsf(x));
+      const float spl = fmaxf(-x, 0.f) + __logf(1.0f + e);
+      const float inv = __fdividef(1.0f, 1.0f + e);
+      const float c = (x >= 0.f) ? e * inv : inv;
+      l2_acc += 0.5f * (sq + p.reg_user * usq);
+      if (g.gl == 0) {
+        loss_acc += spl;
+        absx_acc += fabsf(x);
+        cnt_acc += 1.f;
+        if (p.bias_grad != nullptr) {
+          atomicAdd(p.bias_grad + i, -c);
+          atomicAdd(p.bias_grad + j, c);
+        }
+      }
+      float* gi = (i != 0) ? p.item_grad + (size_t)i * D : nullptr;
+      float* gj = (j != 0) ? p.item_grad + (size_t)j * D : nullptr;
+      float* gurow = p.user_grad + (size_t)uu * D;
+      float* uout = p.user_emb + (size_t)uu * D;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!colok[v]) continue;
+        const int cidx = 4 * (g.gl + LANES * v);
+        const float4 cu = make_float4(c * u[v].x, c * u[v].y, c * u[v].z, c * u[v].w);
+        float4 a, b, gu;
+        a.x = p.reg_item * vi[v].x - cu.x;
+        a.y = p.reg_item * vi[v].y - cu.y;
+        a.z = p.reg_item * vi[v].z - cu.z;
+        a.w = p.reg_item * vi[v].w - cu.w;
+        b.x = p.reg_neg * vj[v].x + cu.x;
+        b.y = p.reg_neg * vj[v].y + cu.y;
+        b.z = p.reg_neg * vj[v].z + cu.z;
+        b.w = p.reg_neg * vj[v].w + cu.w;
+        if (gi != nullptr) red4(gi + cidx, a);
+        if (gj != nullptr) red4(gj + cidx, b);
+        gu.x = p.reg_user * u[v].x - c * (vi[v].x - vj[v].x);
+        gu.y = p.reg_user * u[v].y - c * (vi[v].y - vj[v].y);
+        gu.z = p.reg_user * u[v].z - c * (vi[v].z - vj[v].z);
+        gu.w = p.reg_user * u[v].w - c * (vi[v].w - vj[v].w);
+        if (uu == 0) continue;
+        if (!single) {
+          red4(gurow + cidx, gu);
+        } else {
+          float4 o;
+          o.x = u[v].x - lr * gu.x;
+          o.y = u[v].y - lr * gu.y;
+          o.z = u[v].z - lr * gu.z;
+          o.w = u[v].w - lr * gu.w;
+          st4(uout + cidx, o);
+        }
+      }
+    }
+    {  // per-warp statistics partial of the step
+      float a = loss_acc, b = l2_acc, cabs = absx_acc, d = cnt_acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        cabs += __shfl_xor_sync(0xffffffffu, cabs, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+      if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = make_float4(a, b, cabs, d);
+    }
+    cluster_barrier();
+
+    if (threadIdx.x < 32 && sp.stats != nullptr) {  // one atomic per statistic per CTA
+      const float4 v = (threadIdx.x < kSmallThreads / 32) ? s_part[threadIdx.x] : f4zero();
+      double a = v.x, b = v.y, c2 = v.z, d = v.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+      if (threadIdx.x == 0) {
+        double* out = sp.stats + (size_t)s * RBPR_STATS_PER_STEP;
+        atomicAdd(out + 0, a);
+        atomicAdd(out + 1, b);
+        atomicAdd(out + 2, c2);
+        atomicAdd(out + 3, d);
+      }
+    }
+
+    // ---- B: apply the step's gradients, driven by the step's own records ----------------------------
+    for (uint32_t k = gid; k < n; k += groups_total) {
+      const int4 rec = __ldg(recs + k);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int32_t q = side == 0 ? rec.y : rec.z;
+        uint32_t first = 0u;
+        if (g.gl == 0 && q != 0) first = (atomicExch(sp.stamp + q, tag) != tag) ? 1u : 0u;
+        first = __shfl_sync(g.mask, first, g.shift);
+        if (first == 0u) continue;
+        float* grow = p.item_grad + (size_t)q * D;
+        float* prow = sp.item_emb_w + (size_t)q * D;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!colok[v]) continue;
+          const int c = 4 * (g.gl + LANES * v);
+          const float4 gr = ldcg4(grow + c);
+          float4 pv = ldcg4(prow + c);
+          pv.x -= lr * gr.x;
+          pv.y -= lr * gr.y;
+          pv.z -= lr * gr.z;
+          pv.w -= lr * gr.w;
+          st4(prow + c, pv);
+          st4(grow + c, f4zero());
+        }
+        if (g.gl == 0 && p.bias_grad != nullptr) {
+          const float gb = __ldcg(p.bias_grad + q);
+          sp.item_bias_w[q] = __ldcg(sp.item_bias_w + q) - lr * gb;
+          p.bias_grad[q] = 0.f;
+        }
+      }
+      if ((rec.w & kRecMultiHead) != 0 && rec.x != 0) {
+        const size_t r = (size_t)rec.x;
+        float* grow = p.user_grad + r * D;
+        float* prow = p.user_emb + r * D;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!colok[v]) continue;
+          const int c = 4 * (g.gl + LANES * v);
+          const float4 gr = ldcg4(grow + c);
+          float4 pv = ldcg4(prow + c);
+          pv.x -= lr * gr.x;
+          pv.y -= lr * gr.y;
+          pv.z -= lr * gr.z;
+          pv.w -= lr * gr.w;
+          st4(prow + c, pv);
+          st4(grow + c, f4zero());
+        }
+      }
+    }
+    cluster_barrier();
+  }
+}
+
+}  // namespace
+
+// Can this call take the small-batch path?  (plain SGD, single GPU, static sampler — checked by the
+// caller — and at most 4 triples per lane group per step)
+bool rbpr_small_batch_eligible(const rbpr_ctx* ctx, int64_t batch) {
+  int lanes, nv;
+  rbpr_geometry(ctx->D, &lanes, &nv);
+  const int64_t groups = (int64_t)kSmallCluster * kSmallThreads / lanes;
+  return batch <= 4 * groups;
+}
+
+// `n_steps` consecutive steps over prepared records in one cluster launch on stream st.
+int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* records, int64_t n,
+                            int n_steps, double* stats, cudaStream_t st) {
+  if (!ctx->stamp) {
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->stamp, (size_t)ctx->I * sizeof(uint32_t)));
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stamp, 0, (size_t)ctx->I * sizeof(uint32_t), st));
+    ctx->stamp_epoch = 1;
+  }
+  if ((uint64_t)ctx->stamp_epoch + (uint64_t)n_steps >= 0xFFFFFFF0ull) {  // 32-bit stamps wrapped: start over
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stamp, 0, (size_t)ctx->I * sizeof(uint32_t), st));
+    ctx->stamp_epoch = 1;
+  }
+  SmallParams sp;
+  sp.t = p;
+  sp.item_emb_w = ctx->item_emb;
+  sp.item_bias_w = ctx->item_bias;
+  sp.stamp = ctx->stamp;
+  sp.epoch0 = ctx->stamp_epoch;
+  sp.records = records;
+  sp.n = n;
+  sp.n_steps = n_steps;
+  sp.stats = stats;
+  ctx->stamp_epoch += (uint32_t)n_steps;
+  if (stats)
+    RBPR_CUDA(ctx, cudaMemsetAsync(stats, 0, (size_t)n_steps * RBPR_STATS_PER_STEP * sizeof(double), st));
+  int lanes, nv;
+  rbpr_geometry(ctx->D, &lanes, &nv);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kSmallCluster);
+  cfg.blockDim = dim3(kSmallThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kSmallCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define X(L, V)                                                                   \
+  if (lanes == L && nv == V) {                                                    \
+    RBPR_CUDA(ctx, cudaLaunchKernelEx(&cfg, bpr_small_steps<L, V>, sp));          \
+    ctx->launches++;                                                              \
+    ctx->small_launches++;                                                        \
+    return 0;                                                                     \
+  }
+  RBPR_FOR_EACH_GEOMETRY(X)
+#undef X
+  RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
+}

@@ -419,8 +419,6 @@ def test_fused_eval_output_families_match_dense_metric_classes():
                   "precision@7": M.Precision(7), "map@30": M.MAP(30), "mapu@30": M.MAP(30, normalized=False),
                   "f@15": M.FBeta(15, beta=0.5), "ndcg@500": M.NDCG(500), "auc": M.RocAucManySlow()}
     fused, dense = mk(), mk()
-    for m in list(fused.values()) + list(dense.values()):
-        m.reset()
     eng = model.logits_model.engine()
     t0 = eng.topk_launch_count()
     state = SimpleNamespace(output=out, batch=batch, metrics={})

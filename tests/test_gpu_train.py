@@ -7,6 +7,8 @@ import torch
 
 from helpers import TRAIN_CASES, load_train_case, oracle_run
 
+REG = {"user": 0.0016, "item": 0.0001, "neg": 0.00375}
+
 pytestmark = pytest.mark.gpu
 
 
@@ -275,3 +277,60 @@ def test_error_paths():
         eng.train_steps(torch.tensor([0], device=dev), 1, 0, 0)
     with pytest.raises(native.NativeError):
         Engine(torch.zeros(5, 6, device=dev), torch.zeros(4, 6, device=dev))  # dim % 4 != 0
+
+
+@pytest.mark.parametrize("D,B,bias", [(128, 256, False), (64, 256, True), (20, 100, False), (256, 512, False)])
+def test_small_batch_cluster_kernel_matches_large_batch_path_and_oracle(D, B, bias, monkeypatch):
+    """Small batches (the reference configs' train_batch_size 256) run whole waves of steps inside ONE
+    launch of a thread-block cluster (csrc/train_small.cu).  Same negatives, statistics and tables as
+    the two-launches-per-step path, and as the oracle's autograd + SGD, on a problem dense in repeated
+    users and hot items (duplicates inside a step are the hard part of the exact minibatch)."""
+    from oracle import ref_bpr
+    from rbpr import native
+    from rbpr.engine import Engine
+    dev = torch.device("cuda:0")
+    inter, ue, ie, ib = _random_problem(1500, 300, D, 12, 5 + D, dev, bias=bias)
+    steps = min(37, inter.nnz // B)
+    t = torch.randperm(inter.nnz, generator=torch.Generator().manual_seed(1))[:B * steps]
+    assert t.numel() == B * steps
+    runs = []
+    for small in (True, False):
+        if small:
+            monkeypatch.delenv("RBPR_NO_SMALL_BATCH", raising=False)
+        else:
+            monkeypatch.setenv("RBPR_NO_SMALL_BATCH", "1")
+        eng = Engine(ue.to(dev), ie.to(dev), None if ib is None else ib.to(dev))
+        eng.bind_csr(torch.from_numpy(inter.indptr), torch.from_numpy(inter.indices))
+        eng.set_reg(REG)
+        eng.set_sgd(0.05)
+        eng.set_sampler(native.SAMPLER_UNIFORM)
+        l0 = eng.launch_count()
+        stats, negs = eng.train_steps(t.to(dev), B, seed=3, step0=11, want_neg=True)
+        eng.sync_check()
+        runs.append((stats.cpu().numpy(), negs.cpu().numpy(), eng.user_emb.cpu().numpy(), eng.item_emb.cpu().numpy(),
+                     None if ib is None else eng.item_bias.cpu().numpy(), eng.launch_count() - l0))
+        # a second call on the same engine continues correctly (per-item epoch stamps keep advancing)
+        if small:
+            st2, _ = eng.train_steps(t[:B * 3].to(dev), B, seed=3, step0=11 + steps)
+            eng.sync_check()
+            assert np.isfinite(st2.cpu().numpy()).all() and (st2[:, 3] == B).all().item()
+    (s0, n0, u0, i0, b0, l_small), (s1, n1, u1, i1, b1, l_big) = runs
+    assert l_small < 8 and l_big >= 2 * steps  # one cluster launch per wave vs two launches per step
+    assert (n0 == n1).all()
+    np.testing.assert_allclose(s0, s1, rtol=2e-6)
+    np.testing.assert_allclose(u0, u1, atol=2e-6)
+    np.testing.assert_allclose(i0, i1, atol=2e-6)
+    model = ref_bpr.RefModel(ue, ie, ib, REG)
+    opt = ref_bpr.make_optimizer(model, "sgd", lr=0.05)
+    coo, tn = inter.coo_users(), t.numpy()
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        out = ref_bpr.train_step(model, opt, torch.from_numpy(coo[tn[sl]]), torch.from_numpy(inter.indices[tn[sl]].astype(np.int64)),
+                                 torch.from_numpy(n0[sl]))
+        np.testing.assert_allclose(s0[s, 0], out["bpr_loss"].item(), rtol=1e-4)
+        np.testing.assert_allclose(s0[s, 1], out["l2_reg"].item(), rtol=1e-4)
+    np.testing.assert_allclose(u0, model.user_emb.detach().numpy(), atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(i0, model.item_emb.detach().numpy(), atol=1e-5, rtol=1e-4)
+    if bias:
+        np.testing.assert_allclose(b0, model.item_bias.detach().numpy(), atol=1e-5, rtol=1e-4)
+        np.testing.assert_allclose(b0, b1, atol=2e-6)
