@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 6
+#define RBPR_ABI_VERSION 7
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -239,6 +239,22 @@ int rbpr_comm_init(rbpr_ctx* ctx, int32_t world, int32_t rank, const void* id128
 /* The all-reduce alone, for callers driving rbpr_grad_step / rbpr_apply_item_grads themselves. */
 int rbpr_comm_allreduce_item_grads(rbpr_ctx* ctx, void* stream);
 int64_t rbpr_collective_count(const rbpr_ctx* ctx);
+
+/* The exchange as ONE kernel over NVLink peer memory instead of ncclAllReduce + dense apply: every rank
+ * owns a slice of the item rows, sums the ranks' gradients for it straight from their accumulators,
+ * applies the optimizer and stores the updated rows into every replica (csrc/exchange.cu).  The host
+ * shell gathers every rank's export blob (RBPR_IPC_BLOB_BYTES each, cudaIpc handles of the library's
+ * gradient buffers and of the item table / bias storages) and hands all of them to every rank.
+ * After a successful bind rbpr_train_steps / rbpr_train_step_triples use the fused exchange (the
+ * communicator of rbpr_comm_init stays the fallback when this fails: no peer access, no IPC).
+ * With a stateful optimizer the item table's optimizer state is SHARDED: only rows
+ * [I*rank/world, I*(rank+1)/world) of item_m / item_v are kept current on a rank.
+ * rbpr_grad_step / rbpr_item_grad_buffer / rbpr_apply_item_grads are not available once bound. */
+#define RBPR_MAX_PEERS 8
+#define RBPR_IPC_BLOB_BYTES 512
+int rbpr_comm_ipc_export(rbpr_ctx* ctx, void* blob_out);
+int rbpr_comm_ipc_bind(rbpr_ctx* ctx, const void* blobs, int32_t world, int32_t rank, void* stream);
+int64_t rbpr_fused_exchange_count(const rbpr_ctx* ctx);
 
 /* Bring every lazily-updated user row up to `step` optimizer steps (dense-Adam semantics
  * of torch.optim.Adam: rows with zero gradient still move).  Call before reading the user

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 void rbpr_internal_comm_destroy(rbpr_ctx* ctx);  // comm.cu
+void rbpr_internal_fx_destroy(rbpr_ctx* ctx);    // exchange.cu
 
 extern "C" {
 
@@ -45,6 +46,7 @@ int rbpr_create(int device, rbpr_ctx** out) {
 void rbpr_destroy(rbpr_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  rbpr_internal_fx_destroy(ctx);
   rbpr_internal_comm_destroy(ctx);
   cudaFree(ctx->coo_user);
   cudaFree(ctx->bloom);
@@ -89,6 +91,7 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
                      int64_t num_items, int32_t dim, float* item_bias) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!user_emb || !item_emb) RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: null table pointer");
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "bind_tables: peer-memory exchange is bound to the current tables");
   if (num_users < 2 || num_items < 3)
     RBPR_FAIL(ctx, RBPR_ERR_ARG, "bind_tables: need >=2 user rows and >=3 item rows (row 0 pads)");
   if (num_items >= (1ll << 31) || num_users >= (1ll << 31))

@@ -115,6 +115,7 @@ int rbpr_comm_init(rbpr_ctx* ctx, int32_t world, int32_t rank, const void* id128
 int rbpr_comm_allreduce_item_grads(rbpr_ctx* ctx, void* stream) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!ctx->item_grad) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "allreduce_item_grads: not available once the peer-memory exchange is bound");
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   return rbpr_internal_allreduce_item_grads(ctx, (cudaStream_t)stream);
 }

@@ -78,6 +78,19 @@ struct rbpr_ctx {
   void* comm = nullptr;
   int world = 1, rank = 0;
   int64_t collectives = 0;
+  // fused exchange over peer memory (exchange.cu): every rank's two gradient accumulators, item
+  // table and bias mapped through cudaIpc, flag words for the cross-rank barrier
+  bool fx_bound = false;
+  void* fx_sym = nullptr;  // owned: buf[0] | buf[1] | flags
+  float* fx_grad[RBPR_MAX_PEERS][2] = {};
+  float* fx_item[RBPR_MAX_PEERS] = {};
+  float* fx_bias[RBPR_MAX_PEERS] = {};
+  uint32_t** fx_flags_dev = nullptr;  // device array of every rank's flag words
+  std::vector<void*> fx_opened;       // cudaIpcOpenMemHandle mappings to close
+  int fx_par = 0;                     // accumulator the current step uses
+  uint32_t fx_epoch = 0;
+  float* fx_item_grad_owned = nullptr;  // the library's own accumulator while the shared ones are in use
+  int64_t fused_exchanges = 0;
   // instrumentation
   int64_t launches = 0;
   int64_t topk_launches = 0;  // launches of the ranking kernel (tests assert one per eval batch)

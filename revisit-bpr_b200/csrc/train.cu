@@ -390,6 +390,7 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
       case 7: RBPR_FAIL(ctx, RBPR_ERR_ARG, "user id outside [0,num_users)");
       case 8: RBPR_FAIL(ctx, RBPR_ERR_ARG, "item id outside [0,num_items)");
       case 9: RBPR_FAIL(ctx, RBPR_ERR_DATA, "metric target contains values outside of 0 and 1");
+      case 10: RBPR_FAIL(ctx, RBPR_ERR_COMM, "cross-rank barrier timed out: the ranks are out of step");
       default: RBPR_FAIL(ctx, RBPR_ERR_DATA, "device error flag %d", f);
     }
   }
@@ -410,9 +411,13 @@ bool rbpr_small_batch_eligible(const rbpr_ctx* ctx, int64_t batch);
 int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* records, int64_t n, int n_steps,
                             double* stats, cudaStream_t st);
 
+// defined in exchange.cu
+int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st);
+
 // The step's one exchange on stream st: dense item gradient summed over ranks, then the (dense,
 // identical on every rank) item update.
 int rbpr_internal_exchange_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
+  if (ctx->fx_bound) return rbpr_internal_fused_exchange(ctx, step, hp, st);  // one kernel over peer memory
   int rc = rbpr_internal_allreduce_item_grads(ctx, st);
   if (rc) return rc;
   return run_apply(ctx, step, hp, 1, 1, nullptr, 0, st);
@@ -674,6 +679,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       const int64_t soff = s * batch;
       p.n = (int)((nw - soff) < batch ? (nw - soff) : batch);
       p.step = step0 + (uint64_t)(wave_step0(w) + s);
+      p.item_grad = ctx->item_grad;  // alternates between two buffers under the fused exchange
+      p.bias_grad = ctx->item_bias ? ctx->item_grad + ctx->I * ctx->D : nullptr;
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
       float4* parts = reinterpret_cast<float4*>(ctx->partials[b]) + s * stride;
       int nb = 0;
@@ -760,6 +767,7 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
                    double* stats_out, void* stream) {
   int rc = check_ready(ctx, hp);
   if (rc) return rc;
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "grad_step: not available once the peer-memory exchange is bound");
   if (n < 0 || n >= (1ll << 31)) RBPR_FAIL(ctx, RBPR_ERR_ARG, "grad_step: bad n");
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -812,6 +820,7 @@ int rbpr_grad_step(rbpr_ctx* ctx, const int64_t* triple_idx, int64_t n, uint64_t
 int rbpr_item_grad_buffer(rbpr_ctx* ctx, float** ptr, int64_t* numel) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!ctx->item_grad) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "item_grad_buffer: not available once the peer-memory exchange is bound");
   if (ptr) *ptr = ctx->item_grad;
   if (numel) *numel = ctx->I * ctx->D + (ctx->item_bias ? ctx->I : 0);
   return 0;
@@ -820,6 +829,7 @@ int rbpr_item_grad_buffer(rbpr_ctx* ctx, float** ptr, int64_t* numel) {
 int rbpr_apply_item_grads(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, void* stream) {
   int rc = check_ready(ctx, hp);
   if (rc) return rc;
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "apply_item_grads: not available once the peer-memory exchange is bound");
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, (cudaStream_t)stream);
   if (rc) return rc;

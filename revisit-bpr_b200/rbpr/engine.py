@@ -429,6 +429,65 @@ class Engine(Context):
         self._check(self.lib.rbpr_comm_init(self.ctx, world, rank, C.c_void_p(uid.data_ptr())))
         self.world, self.rank = world, rank
 
+    def init_fused_exchange(self, group=None, strict: bool = False) -> bool:
+        """Replace the per-step all-reduce + dense apply by the fused reduce + update + broadcast kernel
+        over NVLink peer memory (csrc/exchange.cu).  Every rank exports cudaIpc handles of its gradient
+        buffers and of the item table / bias storages; the blobs travel through torch.distributed.
+        Returns False (and keeps the NCCL path) when peer memory cannot be shared, unless `strict`.
+        With a stateful optimizer the item table's optimizer state becomes SHARDED by row block
+        (`item_cuts`); call `gather_item_state` before reading it (checkpoints)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > native.MAX_PEERS:
+            if strict:
+                raise native.NativeError(f"the fused exchange needs 2..{native.MAX_PEERS} ranks on one node")
+            return False
+        blob = torch.zeros(native.IPC_BLOB_BYTES, dtype=torch.uint8)
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        err = ""
+        try:
+            self._check(self.lib.rbpr_comm_ipc_export(self.ctx, C.c_void_p(blob.data_ptr())))
+        except native.NativeError as e:
+            ok.zero_()
+            err = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            if strict:
+                raise native.NativeError(f"fused exchange unavailable: {err or 'a peer could not export its memory'}")
+            return False
+        gathered = [torch.zeros(native.IPC_BLOB_BYTES, dtype=torch.uint8, device=self.device) for _ in range(world)]
+        dist.all_gather(gathered, blob.to(self.device), group=group)
+        blobs = torch.cat(gathered).cpu().contiguous()
+        try:
+            self._check(self.lib.rbpr_comm_ipc_bind(self.ctx, C.c_void_p(blobs.data_ptr()), world, rank, _stream()))
+        except native.NativeError as e:
+            ok.zero_()
+            err = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            raise native.NativeError(f"fused exchange: binding peer memory failed on some rank ({err}); the ranks are "
+                                     "now inconsistent, restart without it (RBPR_FUSED_EXCHANGE=0)")
+        self.world, self.rank, self.fused_exchange = world, rank, True
+        return True
+
+    def item_cuts(self) -> list[int]:
+        """Row blocks of the item table owned by each rank under the fused exchange."""
+        w = getattr(self, "world", 1)
+        return [self.I * r // w for r in range(w + 1)]
+
+    def gather_item_state(self, group=None) -> None:
+        """Fused exchange + stateful optimizer: make every rank hold the whole optimizer state of the
+        item table again (each rank only keeps its own row block current)."""
+        if not getattr(self, "fused_exchange", False) or self.hp.optimizer == native.OPT_SGD:
+            return
+        from rbpr.parallel import sync_row_shards
+        state = self.adam_state if self.hp.optimizer == native.OPT_ADAM else self.opt_state
+        names = ("item_m", "item_v", "bias_m", "bias_v") if self.hp.optimizer == native.OPT_ADAM else ("item_s", "bias_s")
+        sync_row_shards([state[k] for k in names if state.get(k) is not None], self.item_cuts(), group)
+
+    def fused_exchange_count(self) -> int:
+        return int(self.lib.rbpr_fused_exchange_count(self.ctx))
+
     def collective_count(self) -> int:
         return int(self.lib.rbpr_collective_count(self.ctx))
 

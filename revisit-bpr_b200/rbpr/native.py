@@ -11,7 +11,9 @@ OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 6
+ABI_VERSION = 7
+IPC_BLOB_BYTES = 512
+MAX_PEERS = 8
 
 # Every symbol include/rbpr.h declares (tests check the library exports all of them).
 SYMBOLS = (
@@ -27,6 +29,7 @@ SYMBOLS = (
     "rbpr_ingest_pairs", "rbpr_ingest_lists", "rbpr_ingest_free", "rbpr_ingest_last_error",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
     "rbpr_score_metrics", "rbpr_topk_launch_count",
+    "rbpr_comm_ipc_export", "rbpr_comm_ipc_bind", "rbpr_fused_exchange_count",
 )
 
 
@@ -94,6 +97,9 @@ def load() -> C.CDLL:
         "rbpr_score_metrics": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
                                          C.POINTER(MetricOutputs), vp]),
         "rbpr_topk_launch_count": (i64, [vp]),
+        "rbpr_comm_ipc_export": (C.c_int, [vp, vp]),
+        "rbpr_comm_ipc_bind": (C.c_int, [vp, vp, i32, i32, vp]),
+        "rbpr_fused_exchange_count": (i64, [vp]),
         "rbpr_train_step_triples": (C.c_int, [vp, vp, vp, vp, i64, u64, hp, vp, vp, vp]),
         "rbpr_pair_logits": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),

@@ -347,6 +347,10 @@ class Model(torch.nn.Module):
         eng = self.logits_model.engine()
         if getattr(eng, "world", 1) <= 1:
             eng.init_comm(group)
+            import os
+            if os.environ.get("RBPR_FUSED_EXCHANGE", "1") != "0":
+                # the exchange as one kernel over NVLink peer memory; NCCL stays when IPC is unavailable
+                eng.init_fused_exchange(group)
         self._dp = {"cuts": np.asarray(user_cuts, dtype=np.int64), "group": group}
 
     @torch.no_grad()
@@ -365,6 +369,10 @@ class Model(torch.nn.Module):
             tensors += [st[k] for k in ("exp_avg", "exp_avg_sq", "momentum_buffer", "square_avg")
                         if torch.is_tensor(st.get(k))]
         sync_row_shards(tensors, dp["cuts"], dp["group"])
+        lm = self.logits_model
+        if lm._engine is not None and self._optimizer is not None and self._opt_kind not in (None, native.OPT_SGD):
+            # fused exchange: the item table's optimizer state is sharded by row block between eval passes
+            lm._engine.gather_item_state(dp["group"])
 
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, inputs: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
