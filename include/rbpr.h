@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 7
+#define RBPR_ABI_VERSION 8
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -305,8 +305,11 @@ int rbpr_score_metrics(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
                        const int64_t* seen_indptr, const int32_t* seen_indices,
                        const int64_t* held_indptr, const int32_t* held_indices, int32_t k_max,
                        const int32_t* ks, int32_t n_ks, const rbpr_metric_outputs* out, void* stream);
-/* Number of launches of the ranking kernel so far (one per <=512 MB block of users per call). */
+/* Number of ranking passes so far (one per block of users per call). */
 int64_t rbpr_topk_launch_count(const rbpr_ctx* ctx);
+/* Which scoring path ran: blocks of users that went through the tensor-core candidate filter
+ * (csrc/score_tc.cu), and users it handed back to the dense fp32 path (candidate overflow). */
+int rbpr_score_path_counts(const rbpr_ctx* ctx, int64_t* tensor_passes, int64_t* overflow_users);
 
 /* Dense scores for a block of users: out (n_users, I) float, masked like above.
  * The eval-mode Model.forward output `logits` (model.py:43-47) for drop-in callers that

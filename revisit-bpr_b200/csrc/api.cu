@@ -72,6 +72,13 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->stage_idx);
   cudaFree(ctx->stage_neg);
   cudaFree(ctx->score_buf);
+  cudaFree(ctx->tc_items);
+  cudaFree(ctx->tc_users);
+  cudaFree(ctx->tc_gmax);
+  cudaFree(ctx->tc_mask);
+  cudaFree(ctx->tc_small);
+  cudaFree(ctx->tc_cand);
+  cudaFree(ctx->tc_ovf_users);
   cudaFree(ctx->adam_tab);
   cudaFree(ctx->ad_snap);
   cudaFree(ctx->ad_keys);

@@ -70,6 +70,15 @@ struct rbpr_ctx {
   // score scratch
   float* score_buf = nullptr;
   size_t score_buf_bytes = 0;
+  // tensor-core scoring path (score_tc.cu): K-padded panels, seen bitmask, group maxima, candidates
+  float *tc_items = nullptr, *tc_users = nullptr, *tc_gmax = nullptr;
+  void *tc_mask = nullptr, *tc_small = nullptr;
+  int32_t *tc_cand = nullptr, *tc_overflow_rows = nullptr;  // (tc_overflow_rows points into tc_small)
+  size_t tc_items_bytes = 0, tc_users_bytes = 0, tc_gmax_bytes = 0, tc_mask_bytes = 0, tc_small_bytes = 0,
+         tc_cand_bytes = 0;
+  int64_t* tc_ovf_users = nullptr;  // (cap) users handed to the dense path
+  size_t tc_ovf_users_bytes = 0;
+  int64_t tc_passes = 0, tc_overflow_users = 0;
   // per-step Adam scalars {lr_s/(1-b1^s), sqrt(1-b2^s)}, index = 1-based optimizer step
   std::vector<float2> adam_host;
   float2* adam_tab = nullptr;

@@ -8,11 +8,10 @@
 //                  gather of the top-k, bitonic sort by (score desc, item asc), hit flags against
 //                  the user's held-out row, NDCG@k / Recall@k for every requested cut-off.
 // Reference call sites replaced: see include/rbpr.h (rbpr_score_topk / rbpr_score_dense).
-#include "common.cuh"
+#include "score_common.cuh"
 
 namespace {
 
-constexpr float kMasked = -1e13f;
 constexpr int BM = 128, BN = 128, BK = 8;
 
 __global__ void __launch_bounds__(256)
@@ -116,55 +115,23 @@ score_gemm(const float* __restrict__ user_emb, const float* __restrict__ item_em
 }
 
 __global__ void mask_seen(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                          int64_t row0, int n_users, int I, float* __restrict__ S, int64_t ld) {
+                          int64_t row0, const int32_t* __restrict__ row_map, int n_users, int I, float* __restrict__ S,
+                          int64_t ld) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_users) return;
-  const int64_t lo = indptr[row0 + w], hi = indptr[row0 + w + 1];
+  const int64_t r = row0 + (row_map != nullptr ? (int64_t)row_map[w] : w);
+  const int64_t lo = indptr[r], hi = indptr[r + 1];
   for (int64_t q = lo + lane; q < hi; q += 32) {
     const int32_t it = indices[q];
     if (it >= 0 && it < I) S[w * ld + it] = kMasked;
   }
 }
 
-__device__ __forceinline__ uint32_t fkey(float x) {
-  uint32_t u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-constexpr int KCAP = RBPR_MAX_TOPK;  // 128
-
-struct TopkParams {
-  const float* __restrict__ S;
-  int64_t ld;
-  int I;
-  int k_max;
-  const int64_t* __restrict__ held_indptr;
-  const int32_t* __restrict__ held_indices;
-  int64_t row0;  // first local row of this block in the held CSR / outputs
-  int n_ks;
-  int ks[16];
-  int32_t* __restrict__ topk_items;
-  float* __restrict__ topk_scores;
-  float* __restrict__ ndcg_out;
-  float* __restrict__ recall_out;
-  float* __restrict__ precision_out;
-  float* __restrict__ map_out;  // average precision @k (MAP.compute, revisit_bpr/metrics/map.py:45-64)
-  int map_normalized;           // denominator min(n_pos, k) instead of hits@k
-  // dense-target mode (revisit_bpr.metrics on (B,I) tensors): positives = target[row, item] > 0
-  const float* __restrict__ target;
-  int64_t target_ld;
-  int linear_gain;  // NDCG gain_function="linear": discount 1/(rank+1) instead of 1/log2(rank+2)
-  float* __restrict__ ndcg_linear_out;  // both gain functions from one pass (fused eval); needs !linear_gain
-  int32_t* __restrict__ flag;
-};
-
 __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_need, s_cnt, s_tie_cnt;
   __shared__ unsigned long long sel[KCAP];
-  __shared__ float disc_scan[KCAP], hit_scan[KCAP];
-  __shared__ float disc_lin[KCAP], hit_lin[KCAP];
   __shared__ uint32_t warp_tot[8];
 
   const int tid = threadIdx.x;
@@ -261,133 +228,20 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
   }
 
   // ---- outputs ----
-  const int64_t orow = p.row0 + urow;
-  int32_t item = -1;
-  float hit = 0.f;
-  int64_t hlo = 0, hhi = 0;
-  if (p.held_indptr != nullptr) {
-    hlo = p.held_indptr[orow];
-    hhi = p.held_indptr[orow + 1];
-  }
-  int n_pos = (int)(hhi - hlo);
-  if (p.target != nullptr) {  // count positives of the dense target row (and check it is binary)
-    __shared__ int s_npos;
-    if (tid == 0) s_npos = 0;
-    __syncthreads();
-    const float* trow = p.target + orow * p.target_ld;
-    int local = 0;
-    bool bad = false;
-    for (int i = tid; i < I; i += 256) {
-      const float t = trow[i];
-      local += (t == 1.0f);
-      bad |= !(t == 0.0f || t == 1.0f);
-    }
-    if (bad) atomicExch(p.flag, 9);
-    atomicAdd(&s_npos, local);
-    __syncthreads();
-    n_pos = s_npos;
-  }
-  if (tid < KCAP) {
-    if (tid < k) {
-      const unsigned long long c = sel[tid];
-      item = (int32_t)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull));
-      if (p.topk_items) p.topk_items[orow * p.k_max + tid] = item;
-      if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = row[item];
-      if (p.target != nullptr) {
-        hit = (p.target[orow * p.target_ld + item] == 1.0f) ? 1.f : 0.f;
-      } else {
-        int64_t lo = hlo, hi = hhi;
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          const int32_t v = p.held_indices[mid];
-          if (v < item) lo = mid + 1; else hi = mid;
-        }
-        if (lo < hhi && p.held_indices[lo] == item) hit = 1.f;
-      }
-    } else if (tid < p.k_max) {
-      if (p.topk_items) p.topk_items[orow * p.k_max + tid] = -1;
-      if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = kMasked;
-    }
-    const float disc = p.linear_gain ? 1.0f / ((float)tid + 1.0f) : 1.0f / log2f((float)tid + 2.0f);
-    disc_scan[tid] = disc;
-    hit_scan[tid] = hit * disc;
-    if (p.ndcg_linear_out != nullptr) {
-      const float dl = 1.0f / ((float)tid + 1.0f);
-      disc_lin[tid] = dl;
-      hit_lin[tid] = hit * dl;
-    }
-  }
   __syncthreads();
-  // sequential prefix sums in rank order (fp32, like a left-to-right sum) by two threads
-  if (tid == 0) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += disc_scan[r]; disc_scan[r] = s; }
-  } else if (tid == 32) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += hit_scan[r]; hit_scan[r] = s; }
-  } else if (tid == 64 && p.ndcg_linear_out != nullptr) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += disc_lin[r]; disc_lin[r] = s; }
-  } else if (tid == 96 && p.ndcg_linear_out != nullptr) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += hit_lin[r]; hit_lin[r] = s; }
-  }
-  // hit counts: reuse ballots
-  __shared__ uint32_t hitbits[4];
-  {
-    const unsigned bal = __ballot_sync(0xffffffffu, hit > 0.f);
-    if (tid < KCAP && (tid & 31) == 0) hitbits[tid >> 5] = bal;
-  }
-  __syncthreads();
-  if (tid < p.n_ks) {
-    const int kk = min(min(p.ks[tid], k), KCAP);
-    float ndcg = 0.f, ndcg_lin = 0.f, recall = 0.f, precision = 0.f, ap = 0.f;
-    if (kk > 0 && n_pos > 0) {
-      const float dcg = hit_scan[kk - 1];
-      const float idcg = disc_scan[min(kk, n_pos) - 1];
-      ndcg = dcg / idcg;
-      if (p.ndcg_linear_out != nullptr) ndcg_lin = hit_lin[kk - 1] / disc_lin[min(kk, n_pos) - 1];
-      int hits = 0;
-      for (int w = 0; w < 4; ++w) {
-        const int lo = w * 32;
-        if (kk <= lo) break;
-        const int take = min(32, kk - lo);
-        const uint32_t m = (take == 32) ? 0xffffffffu : ((1u << take) - 1u);
-        hits += __popc(hitbits[w] & m);
-      }
-      recall = (float)hits / (float)n_pos;
-      precision = (float)hits / (float)kk;
-      if (p.map_out != nullptr) {
-        float acc = 0.f;
-        int cum = 0;
-        for (int r = 0; r < kk; ++r) {
-          if ((hitbits[r >> 5] >> (r & 31)) & 1u) {
-            ++cum;
-            acc += (float)cum / (float)(r + 1);
-          }
-        }
-        const int denom = p.map_normalized ? min(n_pos, kk) : hits;
-        ap = denom > 0 ? acc / (float)denom : 0.f;
-      }
-    }
-    if (p.ndcg_out) p.ndcg_out[orow * p.n_ks + tid] = ndcg;
-    if (p.ndcg_linear_out) p.ndcg_linear_out[orow * p.n_ks + tid] = ndcg_lin;
-    if (p.recall_out) p.recall_out[orow * p.n_ks + tid] = recall;
-    if (p.precision_out) p.precision_out[orow * p.n_ks + tid] = precision;
-    if (p.map_out) p.map_out[orow * p.n_ks + tid] = ap;
-  }
+  topk_emit_outputs(p, urow, sel, k);
 }
 
 int score_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
                 const int32_t* seen_indices, int64_t row0, float* S, int64_t ld,
-                cudaStream_t st) {
+                cudaStream_t st, const int32_t* row_map = nullptr) {
   dim3 grid((unsigned)((ctx->I + BN - 1) / BN), (unsigned)((n_users + BM - 1) / BM));
   score_gemm<<<grid, 256, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, n_users,
                                    (int)ctx->I, ctx->D, S, ld);
   ctx->launches++;
   if (seen_indptr != nullptr) {
     const int64_t threads = (int64_t)n_users * 32;
-    mask_seen<<<(int)((threads + 255) / 256), 256, 0, st>>>(seen_indptr, seen_indices, row0,
+    mask_seen<<<(int)((threads + 255) / 256), 256, 0, st>>>(seen_indptr, seen_indices, row0, row_map,
                                                             n_users, (int)ctx->I, S, ld);
     ctx->launches++;
   }
@@ -412,6 +266,19 @@ int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   return score_block(ctx, users, (int)n_users, seen_indptr, seen_indices, 0, out, ctx->I,
                      (cudaStream_t)stream);
+}
+
+// defined in score_tc.cu
+bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max);
+int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
+                        const int32_t* seen_indices, int64_t row0, const TopkParams& tp_in, int* overflow_host,
+                        cudaStream_t st);
+constexpr int64_t kTcBlock = 16384;  // users per pass of the tensor path (bounds its scratch)
+
+static __global__ void gather_users(const int64_t* __restrict__ users, const int32_t* __restrict__ rows, int n,
+                                    int64_t* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = users[rows[k]];
 }
 
 // Shared body of rbpr_score_topk / rbpr_score_metrics.
@@ -442,8 +309,9 @@ static int score_topk_impl(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
   cudaStream_t st = (cudaStream_t)stream;
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t ld = (ctx->I + 3) & ~3ll;
-  // user block sized so the score buffer stays <= 512 MB
-  int64_t blk = (512ll << 20) / (ld * (int64_t)sizeof(float));
+  const bool tc = rbpr_score_tc_eligible(ctx, k_max);
+  // user block sized so the score buffer stays <= 512 MB (tensor path: only overflow users need it)
+  int64_t blk = ((tc ? 64ll : 512ll) << 20) / (ld * (int64_t)sizeof(float));
   blk = (blk / BM) * BM;
   if (blk < BM) blk = BM;
   if (blk > n_users) blk = n_users;
@@ -474,6 +342,41 @@ static int score_topk_impl(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
     tp.precision_out = mo->precision;
     tp.map_out = mo->map;
     tp.map_normalized = mo->map_normalized;
+  }
+  if (tc) {
+    // tensor-core candidate filter + exact fp32 rescoring (score_tc.cu); users whose candidate list
+    // overflowed (mass ties) are re-done by the dense path below
+    for (int64_t r0 = 0; r0 < n_users; r0 += kTcBlock) {
+      const int nb = (int)((n_users - r0) < kTcBlock ? (n_users - r0) : kTcBlock);
+      int overflow = 0;
+      int rc = rbpr_score_tc_block(ctx, users + r0, nb, seen_indptr, seen_indices, r0, tp, &overflow, st);
+      if (rc) return rc;
+      if (overflow > 0) {
+        ctx->tc_overflow_users += overflow;
+        if ((size_t)overflow * sizeof(int64_t) > ctx->tc_ovf_users_bytes) {
+          cudaFree(ctx->tc_ovf_users);
+          ctx->tc_ovf_users = nullptr;
+          ctx->tc_ovf_users_bytes = 0;
+          RBPR_CUDA(ctx, cudaMalloc(&ctx->tc_ovf_users, (size_t)nb * sizeof(int64_t)));
+          ctx->tc_ovf_users_bytes = (size_t)nb * sizeof(int64_t);
+        }
+        gather_users<<<(overflow + 255) / 256, 256, 0, st>>>(users + r0, ctx->tc_overflow_rows, overflow, ctx->tc_ovf_users);
+        ctx->launches++;
+        for (int o0 = 0; o0 < overflow; o0 += (int)blk) {
+          const int ob = (overflow - o0) < blk ? (overflow - o0) : (int)blk;
+          rc = score_block(ctx, ctx->tc_ovf_users + o0, ob, seen_indptr, seen_indices, r0, ctx->score_buf, ld, st,
+                           ctx->tc_overflow_rows + o0);
+          if (rc) return rc;
+          tp.row0 = r0;
+          tp.row_map = ctx->tc_overflow_rows + o0;
+          topk_metrics<<<ob, 256, 0, st>>>(tp);
+          tp.row_map = nullptr;
+          ctx->launches++;
+          RBPR_CUDA(ctx, cudaGetLastError());
+        }
+      }
+    }
+    return 0;
   }
   for (int64_t r0 = 0; r0 < n_users; r0 += blk) {
     const int nb = (int)((n_users - r0) < blk ? (n_users - r0) : blk);
@@ -511,6 +414,13 @@ int rbpr_score_metrics(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
 }
 
 int64_t rbpr_topk_launch_count(const rbpr_ctx* ctx) { return ctx ? ctx->topk_launches : 0; }
+
+int rbpr_score_path_counts(const rbpr_ctx* ctx, int64_t* tensor_passes, int64_t* overflow_users) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (tensor_passes) *tensor_passes = ctx->tc_passes;
+  if (overflow_users) *overflow_users = ctx->tc_overflow_users;
+  return 0;
+}
 
 int rbpr_topk_metrics_dense(rbpr_ctx* ctx, const float* scores, const float* target, int64_t n_rows,
                             int64_t n_cols, int32_t k_max, const int32_t* ks, int32_t n_ks,

@@ -1,0 +1,616 @@
+// Full-catalog scoring without the (users x items) score matrix: tensor cores FILTER, fp32 decides.
+//
+// The reference scores every item for every eval user, masks the seen ones and sorts the row once per
+// metric object (revisit_bpr/models/bpr/model.py:43-47,131-145, experiments/bpr/exp.py:369-374,
+// revisit_bpr/metrics/metric.py:110-113).  Only the top-k of a row matters, and ranks must be the
+// fp32 ranks.  So:
+//   pack      item rows (and the bias as one extra K column) / gathered user rows into K-padded
+//             fp32 panels, with their norms;
+//   pass A    S~ = U V^T on tcgen05 (kind::tf32, operands by TMA with 128-byte swizzle, fp32
+//             accumulators in TMEM, 128x128 tiles, double-buffered accumulators so the epilogue of a
+//             tile overlaps the MMAs of the next).  The epilogue — one thread per user row, straight
+//             from TMEM — applies the seen bitmask and keeps only the MAX of every 16 consecutive items;
+//   select    tau~ = k-th largest group maximum of the user (k distinct unmasked items score at least
+//             that much, so it bounds the k-th largest score from below);
+//   pass B    the same contraction again (cheaper than storing 200 M scores); the epilogue emits the
+//             items with S~ >= tau~ - 2 eps, where eps = 2^-8 |u| max|v| bounds the TF32 error by
+//             Cauchy-Schwarz: a superset of the exact top-k (ties included), ~1.3 k items per user;
+//   rescore   exact fp32 FMA scores of the candidates (same arithmetic as score_gemm), sort by (score
+//             desc, item asc), hits / NDCG / Recall / Precision / MAP (score_common.cuh).
+// DRAM traffic: the panels, a bitmask of the seen items, 1/16 of the score matrix as group maxima,
+// the candidate lists — against 2 x 800 MB written and ~6 passes re-read by the dense path at 10 k
+// users of the ML-20M shape.  Users whose candidate list overflows (mass ties, e.g. an all-zero
+// user row) and shapes outside the tensor path (tiny catalogues, D + bias > 288) take the dense
+// fp32 path of score.cu; `RBPR_NO_TC_SCORE=1` forces it everywhere.
+#include <cuda.h>
+
+#include "score_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;            // users per tile (UMMA M)
+constexpr int TN = 128;            // items per tile (UMMA N)
+constexpr int KBLK = 32;           // fp32 per 128-byte swizzle row = one K block
+constexpr int KB_MAX = 9;          // K blocks of the resident user panel (D + bias <= 288)
+constexpr int GROUP = 16;          // items per group maximum
+constexpr int NGT = TN / GROUP;    // group maxima per tile and user
+constexpr int CAND_CAP = 512;      // candidate slots per user
+constexpr int kTcThreads = 192;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr uint32_t kStageBytes = TN * KBLK * 4;  // 16 KiB: one K block of a 128-row panel
+constexpr int kMinItems = 8192;    // below this the dense path is used
+
+struct TcParams {
+  int n_users;       // rows of this block of users
+  int n_utiles, n_itiles, KB, stages;
+  int pass;          // 0: group maxima, 1: candidates
+  const uint4* mask;       // (n_users, n_itiles) 128 bits per (user, tile): 1 = masked
+  float* gmax;             // (n_users, n_itiles * NGT)
+  const float* thr;        // (n_users)
+  int32_t* cnt;            // (n_users)
+  int32_t* cand;           // (n_users, CAND_CAP)
+  int32_t* err;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a pipeline bug must end in an error flag, never in a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int32_t* err) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if (spin > 1024) __nanosleep(64);
+  }
+  atomicExch(err, 11);
+  return false;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <- TMEM lane base + i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// Shared-memory matrix descriptor of a K-major panel written by TMA with 128-byte swizzle: rows of
+// 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100), layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+struct Work {  // the CTA's contiguous range of (user tile, item tile) units, user-tile major
+  long long begin, end;
+};
+
+// ---- the contraction + filter kernel --------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1)
+score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // KB x 16 KiB: the user panel of the current user tile
+  uint8_t* sB = smem + (size_t)p.KB * kStageBytes;      // stages x 16 KiB: K blocks of item tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * kStageBytes);
+  uint64_t* full = bars;                 // [stages]  TMA -> MMA
+  uint64_t* empty = bars + p.stages;     // [stages]  MMA -> TMA
+  uint64_t* a_full = empty + p.stages;   // user panel landed
+  uint64_t* a_free = a_full + 1;         // MMAs reading the user panel retired
+  uint64_t* t_full = a_free + 1;         // [2] accumulator ready (MMA -> epilogue)
+  uint64_t* t_empty = t_full + 2;        // [2] accumulator drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_free, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full + s, 1);
+      mbar_init(t_empty + s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // 2 accumulator stages x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long total = (long long)p.n_utiles * p.n_itiles;
+  Work w;
+  w.begin = total * blockIdx.x / gridDim.x;
+  w.end = total * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t q = 0, seg = 0;
+      bool ok = true;
+      for (long long unit = w.begin; unit < w.end && ok;) {
+        const int ut = (int)(unit / p.n_itiles), it0 = (int)(unit % p.n_itiles);
+        const long long left = w.end - unit;
+        const int it1 = (int)((long long)(p.n_itiles - it0) < left ? p.n_itiles : it0 + left);
+        ok = mbar_wait(a_free, (seg & 1u) ^ 1u, p.err);
+        if (!ok) break;
+        mbar_expect_tx(a_full, (uint32_t)p.KB * kStageBytes);
+        for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + (size_t)kb * kStageBytes, &tmA, kb * KBLK, ut * TM, a_full);
+        for (int it = it0; it < it1 && ok; ++it)
+          for (int kb = 0; kb < p.KB; ++kb, ++q) {
+            const uint32_t st = q % (uint32_t)p.stages, ph = (q / (uint32_t)p.stages) & 1u;
+            ok = mbar_wait(empty + st, ph ^ 1u, p.err);
+            if (!ok) break;
+            mbar_expect_tx(full + st, kStageBytes);
+            tma_load_2d(sB + (size_t)st * kStageBytes, &tmB, kb * KBLK, it * TN, full + st);
+          }
+        unit += it1 - it0;
+        ++seg;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t q = 0, seg = 0, t = 0;
+      bool ok = true;
+      for (long long unit = w.begin; unit < w.end && ok;) {
+        const int it0 = (int)(unit % p.n_itiles);
+        const long long left = w.end - unit;
+        const int it1 = (int)((long long)(p.n_itiles - it0) < left ? p.n_itiles : it0 + left);
+        ok = mbar_wait(a_full, seg & 1u, p.err);
+        if (!ok) break;
+        tc_fence_after();
+        for (int it = it0; it < it1 && ok; ++it, ++t) {
+          const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+          ok = mbar_wait(t_empty + acc, aph ^ 1u, p.err);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * (uint32_t)TN;
+          for (int kb = 0; kb < p.KB; ++kb, ++q) {
+            const uint32_t st = q % (uint32_t)p.stages, ph = (q / (uint32_t)p.stages) & 1u;
+            ok = mbar_wait(full + st, ph, p.err);
+            if (!ok) break;
+            tc_fence_after();
+            const uint64_t ad = umma_desc(smem_u32(sA + (size_t)kb * kStageBytes));
+            const uint64_t bd = umma_desc(smem_u32(sB + (size_t)st * kStageBytes));
+#pragma unroll
+            for (int k4 = 0; k4 < KBLK / 8; ++k4)  // UMMA K = 8 fp32 = 32 bytes inside the swizzled row
+              tc_mma_tf32(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), kIdesc, (kb | k4) != 0 ? 1u : 0u);
+            tc_commit(empty + st);  // frees the stage when these MMAs have read it
+          }
+          if (ok) tc_commit(t_full + acc);
+        }
+        if (ok) tc_commit(a_free);
+        unit += it1 - it0;
+        ++seg;
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, thread <-> TMEM lane <-> user row of the tile =====
+    const int quarter = warp & 3;  // the TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    uint32_t t = 0;
+    bool ok = true;
+    for (long long unit = w.begin; unit < w.end && ok;) {
+      const int ut = (int)(unit / p.n_itiles), it0 = (int)(unit % p.n_itiles);
+      const long long left = w.end - unit;
+      const int it1 = (int)((long long)(p.n_itiles - it0) < left ? p.n_itiles : it0 + left);
+      const int u = ut * TM + row;
+      const bool valid = u < p.n_users;
+      const float thr = (p.pass == 1 && valid) ? __ldg(p.thr + u) : 0.f;
+      for (int it = it0; it < it1 && ok; ++it, ++t) {
+        const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+        uint4 mw = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (valid) mw = __ldg(p.mask + (size_t)u * p.n_itiles + it);
+        ok = mbar_wait(t_full + acc, aph, p.err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)TN;
+        const uint32_t words[4] = {mw.x, mw.y, mw.z, mw.w};
+        float gm[NGT];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tc_ld32(taddr + (uint32_t)(c * 32), v);
+          const uint32_t wbits = words[c];
+          if (p.pass == 0) {
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m0 = fmaxf(m0, ((wbits >> j) & 1u) ? -INFINITY : v[j]);
+#pragma unroll
+            for (int j = 16; j < 32; ++j) m1 = fmaxf(m1, ((wbits >> j) & 1u) ? -INFINITY : v[j]);
+            gm[2 * c] = m0;
+            gm[2 * c + 1] = m1;
+          } else {
+            uint32_t pm = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pm |= (v[j] >= thr ? 1u : 0u) << j;
+            pm &= ~wbits;
+            while (pm != 0u) {  // rare: ~1 % of the scores
+              const int j = __ffs(pm) - 1;
+              pm &= pm - 1u;
+              const int pos = atomicAdd(p.cnt + u, 1);
+              if (pos < CAND_CAP) p.cand[(size_t)u * CAND_CAP + pos] = it * TN + c * 32 + j;
+            }
+          }
+        }
+        // accumulator drained: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + acc);
+        if (p.pass == 0 && valid) {
+          float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u * p.n_itiles * NGT + (size_t)it * NGT);
+          dst[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+          dst[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+        }
+      }
+      unit += it1 - it0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- small kernels around it ----------------------------------------------------------------------
+// K-padded fp32 panel of the item table: [v_i, bias_i, 0 ...]; rows >= I are zero.  One warp per row;
+// also the squared norm of the packed row and the maximum norm over rows.
+__global__ void pack_items(const float* __restrict__ item_emb, const float* __restrict__ item_bias, int I, int D,
+                           int Kp, int rows, float* __restrict__ out, uint32_t* __restrict__ vmax_bits) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float sq = 0.f;
+  for (int c = lane; c < Kp; c += 32) {
+    float v = 0.f;
+    if (r < I) {
+      if (c < D) v = item_emb[(int64_t)r * D + c];
+      else if (c == D && item_bias != nullptr) v = item_bias[r];
+    }
+    out[(int64_t)r * Kp + c] = v;
+    sq += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0 && r < I) atomicMax(vmax_bits, __float_as_uint(sqrtf(sq)));  // non-negative floats order as uints
+}
+
+__global__ void pack_users(const float* __restrict__ user_emb, const int64_t* __restrict__ users, int n_users, int D,
+                           int Kp, int rows, int with_bias, int64_t U, float* __restrict__ out,
+                           float* __restrict__ unorm, int32_t* __restrict__ err) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  int64_t u = 0;
+  if (r < n_users) {
+    u = users[r];
+    if (u < 0 || u >= U) {
+      if (lane == 0) atomicExch(err, 7);
+      u = 0;
+    }
+  }
+  float sq = 0.f;
+  for (int c = lane; c < Kp; c += 32) {
+    float v = 0.f;
+    if (r < n_users) {
+      if (c < D) v = user_emb[u * D + c];
+      else if (c == D && with_bias) v = 1.0f;
+    }
+    out[(int64_t)r * Kp + c] = v;
+    sq += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0 && r < n_users) unorm[r] = sqrtf(sq);
+}
+
+// 128 bits per (user, item tile): item 0, the user's seen items and columns >= I are masked.
+__global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
+                           int64_t row0, int n_users, int I, int n_itiles, uint32_t* __restrict__ mask) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_users) return;
+  uint32_t* m = mask + (size_t)r * n_itiles * 4;
+  if (lane == 0) atomicOr(m, 1u);
+  for (int c = I + lane; c < n_itiles * TN; c += 32) atomicOr(m + (c >> 5), 1u << (c & 31));
+  if (seen_indptr != nullptr) {
+    const int64_t lo = seen_indptr[row0 + r], hi = seen_indptr[row0 + r + 1];
+    for (int64_t q = lo + lane; q < hi; q += 32) {
+      const int32_t it = seen_indices[q];
+      if (it >= 0 && it < I) atomicOr(m + (it >> 5), 1u << (it & 31));
+    }
+  }
+}
+
+// tau~ = k-th largest group maximum (8-bit radix select over the float keys), then the pass-B
+// threshold tau~ - 2 eps with eps = 2^-8 |u'| max|v'|.
+__global__ void __launch_bounds__(256)
+select_threshold(const float* __restrict__ gmax, int G, int k, const float* __restrict__ unorm,
+                 const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_need;
+  const int tid = threadIdx.x;
+  const float* row = gmax + (size_t)blockIdx.x * G;
+  uint32_t prefix = 0, prefix_mask = 0, need = (uint32_t)k;
+  bool short_row = false;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < G; i += 256) {
+      const uint32_t key = fkey(row[i]);
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= need) break;
+        acc += hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << shift);
+      s_need = need - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    prefix_mask |= 255u << shift;
+    __syncthreads();
+  }
+  (void)short_row;
+  if (tid == 0) {
+    const float tau = ikey(prefix);  // -inf when fewer than k groups hold an unmasked item
+    const float eps2 = 0.0078125f * unorm[blockIdx.x] * __uint_as_float(*vmax_bits);  // 2 * 2^-8 |u'| max|v'|
+    thr[blockIdx.x] = tau - eps2;
+  }
+}
+
+// Exact fp32 scores of the candidates, ranking, outputs.  One CTA of 128 threads per user.
+__global__ void __launch_bounds__(128)
+rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_emb, const float* __restrict__ item_bias,
+             const int64_t* __restrict__ users, int D, const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand,
+             int32_t* __restrict__ overflow_rows, int32_t* __restrict__ overflow_count, TopkParams p) {
+  __shared__ unsigned long long sel[CAND_CAP];
+  __shared__ __align__(16) float s_u[1024];
+  const int tid = threadIdx.x;
+  const int64_t urow = blockIdx.x;
+  const int n = cnt[urow];
+  if (n > CAND_CAP) {  // mass ties: this user goes through the dense path afterwards
+    if (tid == 0) overflow_rows[atomicAdd(overflow_count, 1)] = (int32_t)urow;
+    return;
+  }
+  const int64_t u = users[urow];
+  for (int c = tid; c < D; c += 128) s_u[c] = user_emb[u * D + c];
+  for (int i = tid; i < CAND_CAP; i += 128) sel[i] = 0ull;
+  __syncthreads();
+  for (int q = tid; q < n; q += 128) {
+    const int32_t it = cand[(size_t)urow * CAND_CAP + q];
+    const float* v = item_emb + (int64_t)it * D;
+    float acc = 0.f;  // k ascending fmaf chain: the arithmetic of score_gemm
+    for (int c = 0; c < D; c += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(v + c);
+      acc = fmaf(s_u[c], x.x, acc);
+      acc = fmaf(s_u[c + 1], x.y, acc);
+      acc = fmaf(s_u[c + 2], x.z, acc);
+      acc = fmaf(s_u[c + 3], x.w, acc);
+    }
+    if (item_bias != nullptr) acc += __ldg(item_bias + it);
+    sel[q] = ((unsigned long long)fkey(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)it);
+  }
+  __syncthreads();
+  // bitonic sort of CAND_CAP composite keys, descending (empty slots are 0 and sink to the end)
+  for (int size = 2; size <= CAND_CAP; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < CAND_CAP / 2; t += 128) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = sel[lo], b = sel[hi];
+        if ((a < b) == desc) {
+          sel[lo] = b;
+          sel[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  topk_emit_outputs(p, urow, sel, min(min(p.k_max, p.I), n));
+}
+
+typedef CUresult (*fn_encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_panel_map(rbpr_ctx* ctx, CUtensorMap* map, float* base, int64_t rows, int Kp) {
+  static fn_encode_tiled fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RBPR_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    if (!sym) RBPR_FAIL(ctx, RBPR_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = (fn_encode_tiled)sym;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) RBPR_FAIL(ctx, RBPR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+int grow(rbpr_ctx* ctx, void** ptr, size_t* have, size_t need) {
+  if (need <= *have) return 0;
+  cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  RBPR_CUDA(ctx, cudaMalloc(ptr, need));
+  *have = need;
+  return 0;
+}
+
+}  // namespace
+
+// Is the tensor path applicable to this context's tables and this request?
+bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max) {
+  if (getenv("RBPR_NO_TC_SCORE") != nullptr) return false;
+  const int kp = ((ctx->D + (ctx->item_bias ? 1 : 0) + KBLK - 1) / KBLK) * KBLK;
+  return ctx->I >= kMinItems && kp / KBLK <= KB_MAX && k_max <= RBPR_MAX_TOPK && ctx->D % 4 == 0 && ctx->D <= 1024;
+}
+
+// One block of users (n_users <= 16384) through the tensor path.  Outputs as TopkParams describes;
+// `overflow_host` receives the number of users left to the dense path (their local rows are in
+// ctx->tc_overflow_rows).  Synchronises the stream once (to read that count).
+int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
+                        const int32_t* seen_indices, int64_t row0, const TopkParams& tp_in, int* overflow_host,
+                        cudaStream_t st) {
+  const int D = ctx->D, I = (int)ctx->I;
+  const int with_bias = ctx->item_bias ? 1 : 0;
+  const int Kp = ((D + with_bias + KBLK - 1) / KBLK) * KBLK, KB = Kp / KBLK;
+  const int n_utiles = (n_users + TM - 1) / TM, n_itiles = (I + TN - 1) / TN;
+  const int urows = n_utiles * TM, irows = n_itiles * TN;
+  const int G = n_itiles * NGT;
+  // scratch
+  int rc = grow(ctx, (void**)&ctx->tc_items, &ctx->tc_items_bytes, (size_t)irows * Kp * sizeof(float));
+  if (rc) return rc;
+  rc = grow(ctx, (void**)&ctx->tc_users, &ctx->tc_users_bytes, (size_t)urows * Kp * sizeof(float));
+  if (rc) return rc;
+  rc = grow(ctx, (void**)&ctx->tc_mask, &ctx->tc_mask_bytes, (size_t)n_users * n_itiles * 16);
+  if (rc) return rc;
+  rc = grow(ctx, (void**)&ctx->tc_gmax, &ctx->tc_gmax_bytes, (size_t)n_users * G * sizeof(float));
+  if (rc) return rc;
+  rc = grow(ctx, (void**)&ctx->tc_cand, &ctx->tc_cand_bytes, (size_t)n_users * CAND_CAP * sizeof(int32_t));
+  if (rc) return rc;
+  // small per-user arrays in one allocation: thr | unorm | cnt | overflow rows | {overflow count, vmax}
+  const size_t small = (size_t)n_users * 4 * sizeof(float) + 256;
+  rc = grow(ctx, (void**)&ctx->tc_small, &ctx->tc_small_bytes, small);
+  if (rc) return rc;
+  float* thr = (float*)ctx->tc_small;
+  float* unorm = thr + n_users;
+  int32_t* cnt = (int32_t*)(unorm + n_users);
+  int32_t* ovf_rows = cnt + n_users;
+  int32_t* ovf_count = ovf_rows + n_users;
+  uint32_t* vmax_bits = (uint32_t*)(ovf_count + 1);
+  ctx->tc_overflow_rows = ovf_rows;
+
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->tc_mask, 0, (size_t)n_users * n_itiles * 16, st));
+  RBPR_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)n_users * sizeof(int32_t), st));
+  RBPR_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, 2 * sizeof(int32_t), st));
+  pack_items<<<(unsigned)(((int64_t)irows * 32 + 255) / 256), 256, 0, st>>>(ctx->item_emb, ctx->item_bias, I, D, Kp, irows,
+                                                                            ctx->tc_items, vmax_bits);
+  pack_users<<<(unsigned)(((int64_t)urows * 32 + 255) / 256), 256, 0, st>>>(ctx->user_emb, users, n_users, D, Kp, urows,
+                                                                            with_bias, ctx->U, ctx->tc_users, unorm, ctx->flag);
+  build_mask<<<(unsigned)(((int64_t)n_users * 32 + 255) / 256), 256, 0, st>>>(seen_indptr, seen_indices, row0, n_users, I,
+                                                                              n_itiles, (uint32_t*)ctx->tc_mask);
+  ctx->launches += 3;
+  CUtensorMap tmA, tmB;
+  rc = make_panel_map(ctx, &tmA, ctx->tc_users, urows, Kp);
+  if (rc) return rc;
+  rc = make_panel_map(ctx, &tmB, ctx->tc_items, irows, Kp);
+  if (rc) return rc;
+  int stages = (int)((200 * 1024 - (size_t)KB * kStageBytes) / kStageBytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_tc: dim too large for the tensor path");
+  const size_t smem = (size_t)(KB + stages) * kStageBytes + (2 * stages + 6) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RBPR_CUDA(ctx, cudaFuncSetAttribute(score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_users = n_users;
+  p.n_utiles = n_utiles;
+  p.n_itiles = n_itiles;
+  p.KB = KB;
+  p.stages = stages;
+  p.mask = (const uint4*)ctx->tc_mask;
+  p.gmax = ctx->tc_gmax;
+  p.thr = thr;
+  p.cnt = cnt;
+  p.cand = ctx->tc_cand;
+  p.err = ctx->flag;
+  const long long units = (long long)n_utiles * n_itiles;
+  const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
+  p.pass = 0;
+  score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+  const int k = tp_in.k_max < I ? tp_in.k_max : I;
+  select_threshold<<<n_users, 256, 0, st>>>(ctx->tc_gmax, G, k, unorm, vmax_bits, thr);
+  p.pass = 1;
+  score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+  TopkParams tp = tp_in;
+  tp.row0 = row0;
+  rescore_rank<<<n_users, 128, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, D, cnt, ctx->tc_cand, ovf_rows,
+                                        ovf_count, tp);
+  ctx->launches += 4;
+  ctx->topk_launches++;
+  ctx->tc_passes++;
+  RBPR_CUDA(ctx, cudaGetLastError());
+  int32_t h = 0;
+  RBPR_CUDA(ctx, cudaMemcpyAsync(&h, ovf_count, sizeof(h), cudaMemcpyDeviceToHost, st));
+  RBPR_CUDA(ctx, cudaStreamSynchronize(st));
+  *overflow_host = (int)h;
+  return 0;
+}

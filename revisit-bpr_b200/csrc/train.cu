@@ -390,6 +390,7 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
       case 7: RBPR_FAIL(ctx, RBPR_ERR_ARG, "user id outside [0,num_users)");
       case 8: RBPR_FAIL(ctx, RBPR_ERR_ARG, "item id outside [0,num_items)");
       case 9: RBPR_FAIL(ctx, RBPR_ERR_DATA, "metric target contains values outside of 0 and 1");
+      case 11: RBPR_FAIL(ctx, RBPR_ERR_CUDA, "scoring pipeline stalled (mbarrier wait timed out): set RBPR_NO_TC_SCORE=1");
       case 10: RBPR_FAIL(ctx, RBPR_ERR_COMM, "cross-rank barrier timed out: the ranks are out of step");
       default: RBPR_FAIL(ctx, RBPR_ERR_DATA, "device error flag %d", f);
     }

@@ -72,6 +72,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.rbpr_launch_count(self.ctx))
 
+    def score_path_counts(self) -> tuple[int, int]:
+        """(blocks of users scored through the tensor-core filter, users it handed to the dense path)."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.rbpr_score_path_counts(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def topk_launch_count(self) -> int:
         """Launches of the ranking kernel by this context (one per eval batch on the fused path)."""
         return int(self.lib.rbpr_topk_launch_count(self.ctx))

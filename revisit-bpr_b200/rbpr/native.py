@@ -11,7 +11,7 @@ OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 7
+ABI_VERSION = 8
 IPC_BLOB_BYTES = 512
 MAX_PEERS = 8
 
@@ -29,7 +29,7 @@ SYMBOLS = (
     "rbpr_ingest_pairs", "rbpr_ingest_lists", "rbpr_ingest_free", "rbpr_ingest_last_error",
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
     "rbpr_score_metrics", "rbpr_topk_launch_count",
-    "rbpr_comm_ipc_export", "rbpr_comm_ipc_bind", "rbpr_fused_exchange_count",
+    "rbpr_score_path_counts", "rbpr_comm_ipc_export", "rbpr_comm_ipc_bind", "rbpr_fused_exchange_count",
 )
 
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "rbpr_score_metrics": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i32, C.POINTER(i32), i32,
                                          C.POINTER(MetricOutputs), vp]),
         "rbpr_topk_launch_count": (i64, [vp]),
+        "rbpr_score_path_counts": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "rbpr_comm_ipc_export": (C.c_int, [vp, vp]),
         "rbpr_comm_ipc_bind": (C.c_int, [vp, vp, i32, i32, vp]),
         "rbpr_fused_exchange_count": (i64, [vp]),
