@@ -137,10 +137,14 @@ int rbpr_adaptive_stats(rbpr_ctx* ctx, const float** factor_std, const int32_t**
  * user row, rank ~ Geometric(sampling_prob) clamped to the number of unseen items, item = that
  * rank among the user's unseen items in the snapshot's factor order (top if u_f > 0 else bottom).
  * Replaces AdaptiveSampler.sample (neg_samplers.py:74-124) / _adaptive_sampling (exp.py:295-342):
- * no (B,I) scatter, no per-row argsort over I.  Counter-based draw of DESIGN.md §3.3. */
+ * no (B,I) scatter, no per-row argsort over I.  Counter-based draw of DESIGN.md §3.3.
+ * hp / opt_step (hp may be NULL): with a stateful optimizer bound, user rows are updated lazily; the
+ * draw then replays, in registers, the zero-gradient steps a row missed up to `opt_step` optimizer
+ * steps, so it sees what dense torch.optim would hold (the reference reads model.get_features()). */
 int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64_t* seen,
                                 int64_t batch, int64_t width, int64_t num, double sampling_prob,
-                                uint64_t seed, uint64_t step, int64_t* neg_out, void* stream);
+                                uint64_t seed, uint64_t step, int64_t* neg_out, uint64_t opt_step,
+                                const rbpr_hparams* hp, void* stream);
 
 /* Negative sampler alone: for each triple id t = triple_idx[k] draw
  * neg_out[k] = f(seed, step, t, CSR) — the counter-based specification in DESIGN.md §3

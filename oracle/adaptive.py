@@ -6,7 +6,7 @@ Two layers:
     and the geometric draw, clamp, choose top/bottom by the sign of u_f, mask seen items and item
     0 to -1e13, argsort descending, take the rank.  Pinned against the real reference by
     tests/golden/adaptive.npz (minted by tests/golden/make_golden.py).
-  * `sample` restates OUR counter-based draws (factor by sequential fp32 inverse CDF from Philox
+  * `sample` restates OUR counter-based draws (factor by a blocked fp32 inverse CDF from Philox
     word 0, geometric rank from word 1 in fp64) and then calls `reference_pick`, so equality with
     the CUDA kernel checks both the stream and the kernel's rank-skip search.
 """
@@ -52,19 +52,34 @@ def sample(user_emb: np.ndarray, snap: np.ndarray, std: np.ndarray, users, seen_
             w = [int(x) for x in philox4x32_10(np.uint32(off & 0xFFFFFFFF), np.uint32((off >> 32) & 0xFFFFFFFF),
                                                np.uint32(slot & 0xFFFFFFFF), np.uint32(slot >> 32), k0, k1)]
             weights = np.abs(urow) * std                  # float32 products
-            total = np.float32(0)
-            for x in weights:
-                total = np.float32(total + x)
+            # blocked fp32 inverse CDF (8 blocks of `blk` consecutive factors): block sums s_l in
+            # sequential order, prefix P_l accumulated in block order, then the first factor whose
+            # running sum fl(fl(P_l + w_a) + w_b ...) exceeds the target
+            D = weights.size
+            blk = ((((D + 7) // 8) + 3) // 4) * 4
+            sums = []
+            for l in range(8):
+                acc = np.float32(0)
+                for x in weights[l * blk:(l + 1) * blk]:
+                    acc = np.float32(acc + x)
+                sums.append(acc)
+            prefix, total = [], np.float32(0)
+            for l in range(8):
+                prefix.append(total)
+                total = np.float32(total + sums[l])
             if not total > 0:
                 raise RuntimeError("invalid multinomial distribution (sum of probabilities <= 0)")
             target = np.float32(np.float32(w[0] >> 8) * np.float32(1.0 / 16777216.0)) * total
-            cum, factor, last_pos = np.float32(0), -1, 0
-            for f, x in enumerate(weights):
-                cum = np.float32(cum + x)
-                if x > 0:
-                    last_pos = f
-                if factor < 0 and cum > target:
-                    factor = f
+            factor, last_pos = -1, 0
+            for l in range(8):
+                cum = prefix[l]
+                for f in range(l * blk, min(D, (l + 1) * blk)):
+                    x = weights[f]
+                    cum = np.float32(cum + x)
+                    if x > 0:
+                        last_pos = f
+                    if factor < 0 and cum > target:
+                        factor = f
             if factor < 0:
                 factor = last_pos
             u2 = (float(w[1] >> 8) + 1.0) * (1.0 / 16777216.0)

@@ -91,12 +91,11 @@ __global__ void invert_order(const int32_t* __restrict__ order, int64_t I, int D
   pos[f * I + order[k]] = (int32_t)q;
 }
 
-// lanes per slot: the factor draw is two sequential fp32 passes over D that every lane of the group
-// repeats, so few lanes per slot (more slots per warp) wins; the seen-row scans stride by it
-#ifndef RBPR_ADA_LANES
-#define RBPR_ADA_LANES 8
-#endif
-constexpr int kAdaLanes = RBPR_ADA_LANES;
+// 8 lanes per slot.  The factor draw is blocked over them: lane l owns the
+// contiguous factors [l*blk, (l+1)*blk), blk = ceil(D/8) rounded up to a multiple of 4, so the
+// inverse CDF costs 2*blk dependent adds per lane instead of 2*D (round 1: two sequential passes
+// over D repeated by every lane: 72 us per 65 536 slots at D=64); the seen-row scans stride by 8.
+constexpr int kAdaLanes = 8;
 
 struct AdaptiveParams {
   const float* __restrict__ user_emb;
@@ -109,7 +108,30 @@ struct AdaptiveParams {
   uint32_t seed_lo, seed_hi;
   uint64_t step;
   int32_t* __restrict__ flag;
+  // lazily updated user rows (stateful optimizers): the draw must see the row dense torch.optim would
+  // hold after `opt_step` steps, so the missed zero-gradient steps are replayed in registers
+  int opt;  // rbpr_optimizer; RBPR_OPT_SGD: rows are always current
+  const float* __restrict__ user_m;
+  const float* __restrict__ user_v;
+  const int32_t* __restrict__ user_last;
+  const float2* __restrict__ adam_tab;
+  int64_t opt_step;
+  float lr, beta1, beta2, eps;
 };
+
+// the current value of four consecutive factors of a user row
+__device__ __forceinline__ float4 current_u4(const AdaptiveParams& p, int64_t user, int c, int64_t last) {
+  float4 u = ld4(p.user_emb + user * p.D + c);
+  if (p.opt != RBPR_OPT_SGD && last > 0 && last < p.opt_step) {
+    float4 m = ld4(p.user_m + user * p.D + c);
+    float4 v = (p.opt == RBPR_OPT_ADAM) ? ld4(p.user_v + user * p.D + c) : f4zero();
+    const OptScalars h = {p.lr, p.beta1, p.beta2, p.eps, 0.f, 1.f};
+    if (p.opt == RBPR_OPT_ADAM) Catchup<RBPR_OPT_ADAM>(last, p.opt_step, p.adam_tab, h).apply(u, m, v);
+    else if (p.opt == RBPR_OPT_SGDM) Catchup<RBPR_OPT_SGDM>(last, p.opt_step, p.adam_tab, h).apply(u, m, v);
+    else Catchup<RBPR_OPT_RMSPROP>(last, p.opt_step, p.adam_tab, h).apply(u, m, v);
+  }
+  return u;
+}
 
 // One group of kAdaLanes lanes per slot.  `masked(c)` enumerates the masked items of the slot's user:
 // c in [0, n_mask) -> item id (0 = padding entries are ignored; item 0 itself is always masked).
@@ -118,7 +140,6 @@ __device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const 
                                                  int64_t user, uint32_t sub_lo, uint32_t sub_hi,
                                                  int64_t n_entries, RowFn entry) {
   const int D = p.D;
-  const float* urow = p.user_emb + user * D;
   // number of unseen, non-padding items
   int64_t n_seen = 0;
   for (int64_t c = g.gl; c < n_entries; c += kAdaLanes) n_seen += (entry(c) != 0);
@@ -131,29 +152,67 @@ __device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const 
   }
   const uint32_t step_lo = (uint32_t)(p.step << 8), step_hi = (uint32_t)(p.step >> 24);
   const philox4 r4 = philox4x32_10(step_lo, step_hi, sub_lo, sub_hi, p.seed_lo, p.seed_hi);
-  // factor ~ Categorical(|u_f| * std_f): sequential fp32 inverse CDF (every lane, same order)
-  float total = 0.f;
-  for (int f = 0; f < D; ++f) total = __fadd_rn(total, __fmul_rn(fabsf(urow[f]), p.fstd[f]));
+  // factor ~ Categorical(|u_f| * std_f), fp32 inverse CDF in a FIXED blocked order: lane l sums its
+  // block sequentially (s_l), the block sums are accumulated in lane order (P_l), and the factor is the
+  // first f, in natural order, with fl(... fl(fl(P_l + w_a) + w_b) ...) > target.
+  const int blk = ((((D + kAdaLanes - 1) / kAdaLanes) + 3) / 4) * 4;
+  const int f0 = g.gl * blk, f1 = min(D, f0 + blk);
+  const int64_t last = (p.opt != RBPR_OPT_SGD) ? (int64_t)p.user_last[user] : 0;
+  float s_l = 0.f;
+  for (int c = f0; c < f1; c += 4) {
+    const float4 u = current_u4(p, user, c, last);
+    const float4 sd = ld4(p.fstd + c);
+    s_l = __fadd_rn(s_l, __fmul_rn(fabsf(u.x), sd.x));
+    s_l = __fadd_rn(s_l, __fmul_rn(fabsf(u.y), sd.y));
+    s_l = __fadd_rn(s_l, __fmul_rn(fabsf(u.z), sd.z));
+    s_l = __fadd_rn(s_l, __fmul_rn(fabsf(u.w), sd.w));
+  }
+  float before = 0.f, total = 0.f;  // P_l of this lane; P_8
+#pragma unroll
+  for (int l = 0; l < kAdaLanes; ++l) {
+    const float sl = __shfl_sync(g.mask, s_l, g.shift + l);
+    if (l == g.gl) before = total;
+    total = __fadd_rn(total, sl);
+  }
   if (!(total > 0.f)) {
     if (g.gl == 0) atomicExch(p.flag, 10);
     return 1;
   }
   const float target = __fmul_rn((float)(r4.x >> 8) * (1.0f / 16777216.0f), total);
-  int factor = -1, last_pos = 0;
-  float cum = 0.f;
-  for (int f = 0; f < D; ++f) {
-    const float w = __fmul_rn(fabsf(urow[f]), p.fstd[f]);
-    cum = __fadd_rn(cum, w);
-    if (w > 0.f) last_pos = f;
-    if (factor < 0 && cum > target) factor = f;
+  int hit = -1, lastpos = -1;
+  float ufac = 0.f, ulast = 0.f;  // value of the user row at the chosen / last positive factor
+  float cum = before;
+  for (int c = f0; c < f1; c += 4) {
+    const float4 u = current_u4(p, user, c, last);
+    const float4 sd = ld4(p.fstd + c);
+    const float uv[4] = {u.x, u.y, u.z, u.w};
+    const float sv[4] = {sd.x, sd.y, sd.z, sd.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float w = __fmul_rn(fabsf(uv[e]), sv[e]);
+      cum = __fadd_rn(cum, w);
+      if (w > 0.f) {
+        lastpos = c + e;
+        ulast = uv[e];
+      }
+      if (hit < 0 && cum > target) {
+        hit = c + e;
+        ufac = uv[e];
+      }
+    }
   }
-  if (factor < 0) factor = last_pos;
+  // first lane (lowest block) that found a crossing; else the last factor with positive weight
+  const unsigned found = __ballot_sync(g.mask, hit >= 0) >> g.shift;
+  const unsigned pos_any = __ballot_sync(g.mask, lastpos >= 0) >> g.shift;
+  const int src = found != 0u ? (__ffs(found) - 1) : (31 - __clz(pos_any));
+  const int factor = __shfl_sync(g.mask, found != 0u ? hit : lastpos, g.shift + src);
+  const float u_factor = __shfl_sync(g.mask, found != 0u ? ufac : ulast, g.shift + src);
   // rank ~ Geometric(p) on {1,2,...}, clamped to the number of unseen items
   const double u2 = ((double)(r4.y >> 8) + 1.0) * (1.0 / 16777216.0);
   double gq = ceil(log(u2) / p.log1m_p);
   if (!(gq >= 1.0)) gq = 1.0;
   const int64_t rank = gq > (double)n_unseen ? n_unseen : (int64_t)gq;
-  const int64_t r = (urow[factor] > 0.f) ? rank - 1 : n_unseen - rank;
+  const int64_t r = (u_factor > 0.f) ? rank - 1 : n_unseen - rank;
   // r-th unmasked position of the factor's order: fixed point of q <- r + #{masked pos <= q}
   const int32_t* prow = p.pos + (int64_t)factor * p.I;
   const int32_t pos0 = prow[0];
@@ -203,7 +262,7 @@ sample_adaptive_padded(const AdaptiveParams p, const int64_t* __restrict__ users
 __global__ void __launch_bounds__(256)
 rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t* order,
                          const int32_t* pos, double log1m_p, int4* __restrict__ records,
-                         uint64_t n_slots, uint64_t step) {
+                         uint64_t n_slots, uint64_t step, int opt) {
   const Group<kAdaLanes> g;
   const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kAdaLanes;
   if (k >= n_slots) return;
@@ -225,6 +284,16 @@ rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t*
   p.seed_hi = tp.seed_hi;
   p.step = step;
   p.flag = tp.flag;
+  p.opt = opt;
+  p.user_m = tp.user_m;
+  p.user_v = tp.user_v;
+  p.user_last = tp.user_last;
+  p.adam_tab = tp.adam_tab;
+  p.opt_step = (int64_t)step;  // optimizer steps applied before this step
+  p.lr = tp.lr;
+  p.beta1 = tp.beta1;
+  p.beta2 = tp.beta2;
+  p.eps = tp.eps;
   const int64_t lo = tp.indptr[uu], hi = tp.indptr[uu + 1];
   const int32_t* idx = tp.indices;
   auto entry = [&](int64_t c) -> int64_t { return (int64_t)__ldg(idx + lo + c); };
@@ -236,10 +305,11 @@ rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t*
 }
 
 int rbpr_internal_adaptive_ready(rbpr_ctx* ctx);
+int rbpr_internal_ensure_adam_table(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t first, int64_t last, cudaStream_t st);
 
 // Records of ONE step from sorted keys, negatives drawn adaptively from the current user rows.
 int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void* records, int64_t n,
-                                      uint64_t step, double sampling_prob, cudaStream_t st) {
+                                      uint64_t step, double sampling_prob, int opt, cudaStream_t st) {
   int rc = rbpr_internal_adaptive_ready(ctx);
   if (rc) return rc;
   if (!(sampling_prob > 0.0 && sampling_prob < 1.0))
@@ -247,7 +317,7 @@ int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void
   const int64_t threads = n * kAdaLanes;
   rbpr_sample_adaptive_csr<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
       tp, ctx->ad_std, ctx->ad_order, ctx->ad_pos, log1p(-sampling_prob),
-      reinterpret_cast<int4*>(records), (uint64_t)n, step);
+      reinterpret_cast<int4*>(records), (uint64_t)n, step, opt);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -322,7 +392,8 @@ int rbpr_adaptive_stats(rbpr_ctx* ctx, const float** factor_std_out, const int32
 
 int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64_t* seen,
                                 int64_t batch, int64_t width, int64_t num, double sampling_prob,
-                                uint64_t seed, uint64_t step, int64_t* neg_out, void* stream) {
+                                uint64_t seed, uint64_t step, int64_t* neg_out, uint64_t opt_step,
+                                const rbpr_hparams* hp, void* stream) {
   if (!ctx) return RBPR_ERR_ARG;
   if (!ctx->user_emb || !ctx->item_emb) RBPR_FAIL(ctx, RBPR_ERR_STATE, "tables not bound");
   int rc = rbpr_internal_adaptive_ready(ctx);
@@ -346,6 +417,29 @@ int rbpr_sample_adaptive_padded(rbpr_ctx* ctx, const int64_t* users, const int64
   p.seed_hi = (uint32_t)(seed >> 32);
   p.step = step;
   p.flag = ctx->flag;
+  p.opt = RBPR_OPT_SGD;
+  p.user_m = p.user_v = nullptr;
+  p.user_last = nullptr;
+  p.adam_tab = nullptr;
+  p.opt_step = 0;
+  p.lr = p.beta1 = p.beta2 = p.eps = 0.f;
+  if (hp != nullptr && hp->optimizer != RBPR_OPT_SGD && ctx->user_last != nullptr && ctx->user_m != nullptr) {
+    // lazily updated user rows: replay their missed zero-gradient steps in registers before drawing
+    if (hp->optimizer == RBPR_OPT_ADAM) {
+      rc = rbpr_internal_ensure_adam_table(ctx, hp, (int64_t)opt_step, (int64_t)opt_step + 1, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    p.opt = hp->optimizer;
+    p.user_m = ctx->user_m;
+    p.user_v = ctx->user_v;
+    p.user_last = ctx->user_last;
+    p.adam_tab = ctx->adam_tab;
+    p.opt_step = (int64_t)opt_step;
+    p.lr = hp->lr;
+    p.beta1 = hp->beta1;
+    p.beta2 = hp->beta2;
+    p.eps = hp->eps;
+  }
   const int64_t threads = batch * num * kAdaLanes;
   sample_adaptive_padded<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       p, users, seen, batch, width, num, ctx->U, neg_out);

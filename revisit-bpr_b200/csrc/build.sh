@@ -13,6 +13,6 @@ for f in api train train_small train_sgd train_adam train_sgdm train_rms score s
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "$obj"/{api,train,train_small,train_sgd,train_adam,train_sgdm,train_rms,score,score_tc,dropin,knn,adaptive,comm,exchange,ingest}.o -ldl
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out" "$obj"/{api,train,train_small,train_sgd,train_adam,train_sgdm,train_rms,score,score_tc,dropin,knn,adaptive,comm,exchange,ingest}.o -ldl -Xlinker -z -Xlinker defs
 cat "$obj"/*.log > "$here/../build.log"
 echo "built $out"

@@ -251,6 +251,19 @@ int score_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t*
 
 }  // namespace
 
+// defined in score_tc.cu
+bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max);
+int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
+                        const int32_t* seen_indices, int64_t row0, const TopkParams& tp_in, int* overflow_host,
+                        cudaStream_t st);
+constexpr int64_t kTcBlock = 16384;  // users per pass of the tensor path (bounds its scratch)
+
+static __global__ void gather_users(const int64_t* __restrict__ users, const int32_t* __restrict__ rows, int n,
+                                    int64_t* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = users[rows[k]];
+}
+
 extern "C" {
 
 int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
@@ -266,19 +279,6 @@ int rbpr_score_dense(rbpr_ctx* ctx, const int64_t* users, int64_t n_users,
   RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
   return score_block(ctx, users, (int)n_users, seen_indptr, seen_indices, 0, out, ctx->I,
                      (cudaStream_t)stream);
-}
-
-// defined in score_tc.cu
-bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max);
-int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
-                        const int32_t* seen_indices, int64_t row0, const TopkParams& tp_in, int* overflow_host,
-                        cudaStream_t st);
-constexpr int64_t kTcBlock = 16384;  // users per pass of the tensor path (bounds its scratch)
-
-static __global__ void gather_users(const int64_t* __restrict__ users, const int32_t* __restrict__ rows, int n,
-                                    int64_t* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[k] = users[rows[k]];
 }
 
 // Shared body of rbpr_score_topk / rbpr_score_metrics.

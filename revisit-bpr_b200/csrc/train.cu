@@ -402,7 +402,7 @@ int check_flag(rbpr_ctx* ctx, cudaStream_t st) {
 
 // defined in adaptive.cu
 int rbpr_internal_sample_adaptive_csr(rbpr_ctx* ctx, const TrainParams& tp, void* records, int64_t n,
-                                      uint64_t step, double sampling_prob, cudaStream_t st);
+                                      uint64_t step, double sampling_prob, int opt, cudaStream_t st);
 
 // defined in comm.cu
 int rbpr_internal_allreduce_item_grads(rbpr_ctx* ctx, cudaStream_t st);
@@ -422,6 +422,11 @@ int rbpr_internal_exchange_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   int rc = rbpr_internal_allreduce_item_grads(ctx, st);
   if (rc) return rc;
   return run_apply(ctx, step, hp, 1, 1, nullptr, 0, st);
+}
+
+int rbpr_internal_ensure_adam_table(rbpr_ctx* ctx, const rbpr_hparams* hp, int64_t first, int64_t last,
+                                    cudaStream_t st) {
+  return ensure_adam_table(ctx, hp, first, last, st);
 }
 
 // ---- helpers shared with dropin.cu ---------------------------------------------------------------
@@ -636,7 +641,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     if (adaptive) {
       const uint64_t s_glob = step0 + (uint64_t)wave_step0(w);
       r = rbpr_internal_sample_adaptive_csr(ctx, q, ctx->records[b], nw, s_glob,
-                                            (double)hp->adaptive_prob, prep_st);
+                                            (double)hp->adaptive_prob, hp->optimizer, prep_st);
       if (r) return r;
       // AdaptiveSampler.sample refreshes its snapshot AFTER the draw of every N-th call
       // (neg_samplers.py:122-123), i.e. from the item table before this step's update

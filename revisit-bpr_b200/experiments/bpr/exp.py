@@ -335,7 +335,8 @@ class BPRExperiment:
         if self._adaptive:
             eng = self._model.logits_model.engine()
             batch["neg"] = eng.sample_adaptive_padded(batch["user"], batch["seen_items"], num,
-                                                      self._adaptive_sampling_prob, self._neg_seed, self._neg_calls)
+                                                      self._adaptive_sampling_prob, self._neg_seed, self._neg_calls,
+                                                      opt_step=getattr(self._model, "_opt_step", None))
         else:
             kind = native.SAMPLER_WEIGHTED if self._weighted else native.SAMPLER_UNIFORM
             batch["neg"] = self._sampler_ctx.sample_padded(batch["seen_items"], self._config["num_items"], num,

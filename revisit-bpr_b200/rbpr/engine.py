@@ -384,7 +384,10 @@ class Engine(Context):
                 "pos": _wrap_device(pos.value, (self.D, self.I), "<i4", self.device)}
 
     def sample_adaptive_padded(self, users: torch.Tensor, seen: torch.Tensor, num: int,
-                               sampling_prob: float, seed: int, step: int, _stats: object = None) -> torch.Tensor:
+                               sampling_prob: float, seed: int, step: int, _stats: object = None,
+                               opt_step: int | None = None) -> torch.Tensor:
+        """`opt_step`: optimizer steps applied so far — with a stateful optimizer the lazily updated user
+        rows are caught up in registers before the draw (None: rows are read as stored)."""
         users = users.to(self.device, torch.int64).contiguous()
         seen = seen.to(self.device, torch.int64).contiguous()
         if seen.dim() != 2 or seen.size(0) != users.numel():
@@ -392,7 +395,8 @@ class Engine(Context):
         out = torch.empty((users.numel(), num), dtype=torch.int64, device=self.device)
         self._check(self.lib.rbpr_sample_adaptive_padded(
             self.ctx, _ptr(users), _ptr(seen), users.numel(), seen.size(1), num, float(sampling_prob),
-            seed & (2**64 - 1), step, _ptr(out), _stream()))
+            seed & (2**64 - 1), step, _ptr(out), int(opt_step or 0),
+            C.byref(self.hp) if opt_step is not None else None, _stream()))
         return out
 
     def pair_logits(self, users: torch.Tensor, items: torch.Tensor, mask: torch.Tensor | None = None,

@@ -82,7 +82,7 @@ def load() -> C.CDLL:
         "rbpr_bind_item_alias": (C.c_int, [vp, vp, vp]),
         "rbpr_adaptive_update_stats": (C.c_int, [vp, vp]),
         "rbpr_adaptive_stats": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
-        "rbpr_sample_adaptive_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_double, u64, u64, vp, vp]),
+        "rbpr_sample_adaptive_padded": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_double, u64, u64, vp, u64, hp, vp]),
         "rbpr_sample_negatives": (C.c_int, [vp, vp, i64, u64, u64, i32, vp, vp]),
         "rbpr_train_steps": (C.c_int, [vp, vp, i64, i64, u64, u64, hp, vp, vp, vp, vp]),
         "rbpr_sync_check": (C.c_int, [vp, vp]),
