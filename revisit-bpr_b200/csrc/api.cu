@@ -53,7 +53,7 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
-  cudaFree(ctx->stamp);
+  cudaFree(ctx->icnt);
   cudaFree(ctx->ord);
   cudaFree(ctx->cnt);
   cudaFree(ctx->stats);
@@ -111,8 +111,9 @@ int rbpr_bind_tables(rbpr_ctx* ctx, float* user_emb, int64_t num_users, float* i
   cudaFree(ctx->item_grad);
   cudaFree(ctx->user_grad);
   cudaFree(ctx->touched);
-  cudaFree(ctx->stamp);
-  ctx->stamp = nullptr;
+  cudaFree(ctx->icnt);
+  ctx->icnt = nullptr;
+  ctx->icnt_cap = 0;
   ctx->item_grad = nullptr;
   ctx->user_grad = nullptr;
   ctx->touched = nullptr;

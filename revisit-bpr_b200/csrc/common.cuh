@@ -37,8 +37,8 @@ struct rbpr_ctx {
   float* item_grad = nullptr;   // (I*D + I) dense item (+bias) gradient accumulator
   float* user_grad = nullptr;   // (U*D) dense user gradient accumulator (multi-occurrence users)
   uint32_t* touched = nullptr;  // (I) item touched in this step
-  uint32_t* stamp = nullptr;    // (I) small-batch path: epoch in which each item row was last applied
-  uint32_t stamp_epoch = 1;
+  uint32_t* icnt = nullptr;     // (icnt_cap) small-batch path: per-step item occurrence counters of the wave being prepared
+  int64_t icnt_cap = 0;
   int64_t small_launches = 0;   // launches of the persistent small-batch kernel
   uint32_t* ord = nullptr;  // (cap) arrival rank of each slot among its user's slots of the step
   int64_t cap = 0;

@@ -13,8 +13,11 @@
 //   select    tau~ = k-th largest group maximum of the user (k distinct unmasked items score at least
 //             that much, so it bounds the k-th largest score from below);
 //   pass B    the same contraction again (cheaper than storing 200 M scores); the epilogue emits the
-//             items with S~ >= tau~ - 2 eps, where eps = 2^-8 |u| max|v| bounds the TF32 error by
-//             Cauchy-Schwarz: a superset of the exact top-k (ties included), ~1.3 k items per user;
+//             items with S~ >= tau~ - 2 eps.  The panels hold operands ROUNDED to TF32 (cvt.rna, so the
+//             tensor core's own fp32->tf32 handling is exact): every product is off by at most
+//             (2 * 2^-11 + 2^-22) |a||b|, hence |S~ - S| <= eps = 1.01 * 2^-10 |u| max|v| by
+//             Cauchy-Schwarz, and the emitted set is a superset of the exact top-k (ties included),
+//             ~1.2 k items per user;
 //   rescore   exact fp32 FMA scores of the candidates (same arithmetic as score_gemm), sort by (score
 //             desc, item asc), hits / NDCG / Recall / Precision / MAP (score_common.cuh).
 // DRAM traffic: the panels, a bitmask of the seen items, 1/16 of the score matrix as group maxima,
@@ -130,6 +133,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 struct Work {  // the CTA's contiguous range of (user tile, item tile) units, user-tile major
   long long begin, end;
@@ -326,7 +335,7 @@ __global__ void pack_items(const float* __restrict__ item_emb, const float* __re
       if (c < D) v = item_emb[(int64_t)r * D + c];
       else if (c == D && item_bias != nullptr) v = item_bias[r];
     }
-    out[(int64_t)r * Kp + c] = v;
+    out[(int64_t)r * Kp + c] = round_tf32(v);
     sq += v * v;
   }
 #pragma unroll
@@ -355,7 +364,7 @@ __global__ void pack_users(const float* __restrict__ user_emb, const int64_t* __
       if (c < D) v = user_emb[u * D + c];
       else if (c == D && with_bias) v = 1.0f;
     }
-    out[(int64_t)r * Kp + c] = v;
+    out[(int64_t)r * Kp + c] = round_tf32(v);
     sq += v * v;
   }
 #pragma unroll
@@ -382,7 +391,7 @@ __global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_
 }
 
 // tau~ = k-th largest group maximum (8-bit radix select over the float keys), then the pass-B
-// threshold tau~ - 2 eps with eps = 2^-8 |u'| max|v'|.
+// threshold tau~ - 2 eps with eps = 1.01 * 2^-10 |u'| max|v'| (see the file header).
 __global__ void __launch_bounds__(256)
 select_threshold(const float* __restrict__ gmax, int G, int k, const float* __restrict__ unorm,
                  const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
@@ -391,7 +400,6 @@ select_threshold(const float* __restrict__ gmax, int G, int k, const float* __re
   const int tid = threadIdx.x;
   const float* row = gmax + (size_t)blockIdx.x * G;
   uint32_t prefix = 0, prefix_mask = 0, need = (uint32_t)k;
-  bool short_row = false;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     hist[tid] = 0;
@@ -417,10 +425,9 @@ select_threshold(const float* __restrict__ gmax, int G, int k, const float* __re
     prefix_mask |= 255u << shift;
     __syncthreads();
   }
-  (void)short_row;
   if (tid == 0) {
     const float tau = ikey(prefix);  // -inf when fewer than k groups hold an unmasked item
-    const float eps2 = 0.0078125f * unorm[blockIdx.x] * __uint_as_float(*vmax_bits);  // 2 * 2^-8 |u'| max|v'|
+    const float eps2 = 0.002f * unorm[blockIdx.x] * __uint_as_float(*vmax_bits);  // >= 2 * 1.01 * 2^-10 |u'| max|v'|
     thr[blockIdx.x] = tau - eps2;
   }
 }

@@ -636,6 +636,19 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     TrainParams q = p;
     q.triple_idx = triple_idx + off;
     q.batch = batch;
+    if (small) {  // per-step item occurrence counters: the sampler designates one applier per item and step
+      const int64_t need = wave_steps(w) * ctx->I;
+      if (need > ctx->icnt_cap) {
+        cudaFree(ctx->icnt);
+        ctx->icnt = nullptr;
+        ctx->icnt_cap = 0;
+        const int64_t cap = alloc_spw * ctx->I > need ? alloc_spw * ctx->I : need;
+        RBPR_CUDA(ctx, cudaMalloc(&ctx->icnt, (size_t)cap * sizeof(uint32_t)));
+        ctx->icnt_cap = cap;
+      }
+      RBPR_CUDA(ctx, cudaMemsetAsync(ctx->icnt, 0, (size_t)need * sizeof(uint32_t), prep_st));
+      q.icnt = ctx->icnt;
+    }
     q.neg_in = neg_in ? neg_in + off : nullptr;
     q.neg_out = neg_out ? neg_out + off : nullptr;
     if (adaptive) {

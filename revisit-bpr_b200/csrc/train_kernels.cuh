@@ -29,6 +29,7 @@ struct TrainParams {
   const uint32_t* __restrict__ bloom;  // (U, 8) 256-bit membership filter of every CSR row, or null
   const int64_t* __restrict__ triple_idx;  // the wave's triple ids, input order
   const uint32_t* __restrict__ cnt;        // (steps in wave, U) occurrences of each user per step
+  uint32_t* __restrict__ icnt;             // (steps in wave, I) item occurrences per step, or null (small-batch path only)
   const uint32_t* __restrict__ ord;        // arrival rank of each slot among its user's slots
   int64_t batch;                           // triples per step
   int64_t U;
@@ -89,6 +90,8 @@ struct ApplyParams {
 constexpr int kRecHead = 1;       // first triple of a user run inside its step
 constexpr int kRecSingle = 2;     // the user occurs exactly once in the step
 constexpr int kRecMultiHead = 4;  // head of a run of length >= 2
+constexpr int kRecApplyPos = 8;   // small-batch path: this slot applies the item row of its positive this step
+constexpr int kRecApplyNeg = 16;  // ... of its negative (exactly one slot per touched item and step)
 
 template <int LANES>
 struct Group {
@@ -356,7 +359,13 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
     }
   }
   if (g.gl == 0) {
-    if (records != nullptr) records[k] = make_int4(uu, i, j, flags);
+    int32_t fl = flags;
+    if (p.icnt != nullptr) {  // designate ONE slot per touched item and step (first to arrive here)
+      uint32_t* row = p.icnt + sl * (uint64_t)p.I;
+      if (i > 0 && (uint32_t)i < p.I && atomicAdd(row + i, 1u) == 0u) fl |= kRecApplyPos;
+      if (j > 0 && (uint32_t)j < p.I && atomicAdd(row + j, 1u) == 0u) fl |= kRecApplyNeg;
+    }
+    if (records != nullptr) records[k] = make_int4(uu, i, j, fl);
     if (p.neg_out != nullptr) p.neg_out[k] = (int64_t)j;
   }
 }

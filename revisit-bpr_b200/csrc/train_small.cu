@@ -14,11 +14,12 @@
 //      coherent), dot / softplus / gradients as in bpr_phase_a; item gradients go to the dense
 //      accumulator with red.global.add.v4.f32, a user occurring once is updated in place, a user
 //      occurring several times accumulates into the user-gradient buffer;
-//   -- barrier.cluster (release/acquire, after a device-scope fence) --
-//   B  the same groups walk the same records again: the first group to reach an item row this step
-//      (atomicExch on a per-item epoch stamp) applies its accumulated gradient and clears it; the
-//      designated triple of a repeated user applies the user row.  No scan over the catalogue, no
-//      touched-flag pass: the work of a step is proportional to its batch.
+//   -- barrier.cluster (release / acquire at cluster scope) --
+//   B  the same groups walk the same records again: the slot the preparation kernel designated for an
+//      item row (one per touched item and step, flags kRecApplyPos / kRecApplyNeg baked into the
+//      record one wave ahead — no atomic on the critical path) applies the accumulated gradient and
+//      clears it; the designated triple of a repeated user applies the user row.  No scan over the
+//      catalogue, no touched-flag pass: the work of a step is proportional to its batch.
 //   -- barrier.cluster --
 // Plain SGD only (a stateful optimizer moves every item row every step — dense torch.optim
 // semantics — which is a sweep over the table, not a small-batch operation); everything else takes
@@ -36,8 +37,6 @@ struct SmallParams {
   TrainParams t;        // tables, accumulators, hyper-parameters (t.batch = triples per step)
   float* item_emb_w;    // the item table, writable
   float* item_bias_w;   // or null
-  uint32_t* stamp;      // (I) epoch in which each item row was last applied
-  uint32_t epoch0;      // stamp value of the first step of this launch (unique per executed step)
   const int4* records;  // the wave's records {u, i+, i-, flags}
   int64_t n;            // triples in the wave
   int n_steps;
@@ -46,8 +45,10 @@ struct SmallParams {
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+// Release / acquire at cluster scope orders every earlier global access of the arriving threads (reds,
+// stores) before every later access of the threads that have waited: all readers and writers of a
+// row sit in this one cluster, so no device-scope fence is needed on top.
 __device__ __forceinline__ void cluster_barrier() {
-  __threadfence();  // reds / stores of this thread are performed at L2 before the barrier releases
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -65,17 +66,19 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
 #pragma unroll
   for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
 
+  // the group's first record of a step is fetched during the previous step (records are static)
+  int4 rec_first = (gid < (uint32_t)(sp.n < p.batch ? sp.n : p.batch)) ? __ldg(sp.records + gid) : make_int4(0, 0, 0, 0);
   for (int s = 0; s < sp.n_steps; ++s) {
     const int64_t off = (int64_t)s * p.batch;
     const int64_t left = sp.n - off;
     const uint32_t n = (uint32_t)(left < p.batch ? left : p.batch);
     const int4* recs = sp.records + off;
-    const uint32_t tag = sp.epoch0 + (uint32_t)s;
     float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
+    const int4 rec0 = rec_first;
 
     // ---- A: gather, loss, gradients ---------------------------------------------------------------
     for (uint32_t k = gid; k < n; k += groups_total) {
-      const int4 rec = __ldg(recs + k);
+      const int4 rec = (k == gid) ? rec0 : __ldg(recs + k);
       const int32_t uu = rec.x, i = rec.y, j = rec.z;
       const bool single = (rec.w & kRecSingle) != 0;
       const float* urow = p.user_emb + (size_t)uu * D;
@@ -183,54 +186,64 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
     }
 
     // ---- B: apply the step's gradients, driven by the step's own records ----------------------------
+    // up to three rows per slot (positive, negative, repeated user): all loads are issued before any
+    // dependent arithmetic, so the phase costs ONE round trip to L2
     for (uint32_t k = gid; k < n; k += groups_total) {
-      const int4 rec = __ldg(recs + k);
+      const int4 rec = (k == gid) ? rec0 : __ldg(recs + k);
+      float* grow[3];
+      float* prow[3];
+      bool on[3];
+      on[0] = (rec.w & kRecApplyPos) != 0;
+      on[1] = (rec.w & kRecApplyNeg) != 0;
+      on[2] = (rec.w & kRecMultiHead) != 0 && rec.x != 0;
+      grow[0] = p.item_grad + (size_t)rec.y * D;
+      prow[0] = sp.item_emb_w + (size_t)rec.y * D;
+      grow[1] = p.item_grad + (size_t)rec.z * D;
+      prow[1] = sp.item_emb_w + (size_t)rec.z * D;
+      grow[2] = p.user_grad + (size_t)rec.x * D;
+      prow[2] = p.user_emb + (size_t)rec.x * D;
+      float4 gr[3][NV], pv[3][NV];
 #pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const int32_t q = side == 0 ? rec.y : rec.z;
-        uint32_t first = 0u;
-        if (g.gl == 0 && q != 0) first = (atomicExch(sp.stamp + q, tag) != tag) ? 1u : 0u;
-        first = __shfl_sync(g.mask, first, g.shift);
-        if (first == 0u) continue;
-        float* grow = p.item_grad + (size_t)q * D;
-        float* prow = sp.item_emb_w + (size_t)q * D;
+      for (int w = 0; w < 3; ++w)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = 4 * (g.gl + LANES * v);
+          const bool ld = on[w] && colok[v];
+          gr[w][v] = ld ? ldcg4(grow[w] + c) : f4zero();
+          pv[w][v] = ld ? ldcg4(prow[w] + c) : f4zero();
+        }
+      float gb[2] = {0.f, 0.f}, bv[2] = {0.f, 0.f};
+      if (g.gl == 0 && p.bias_grad != nullptr) {
+        if (on[0]) { gb[0] = __ldcg(p.bias_grad + rec.y); bv[0] = __ldcg(sp.item_bias_w + rec.y); }
+        if (on[1]) { gb[1] = __ldcg(p.bias_grad + rec.z); bv[1] = __ldcg(sp.item_bias_w + rec.z); }
+      }
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        if (!on[w]) continue;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           if (!colok[v]) continue;
           const int c = 4 * (g.gl + LANES * v);
-          const float4 gr = ldcg4(grow + c);
-          float4 pv = ldcg4(prow + c);
-          pv.x -= lr * gr.x;
-          pv.y -= lr * gr.y;
-          pv.z -= lr * gr.z;
-          pv.w -= lr * gr.w;
-          st4(prow + c, pv);
-          st4(grow + c, f4zero());
-        }
-        if (g.gl == 0 && p.bias_grad != nullptr) {
-          const float gb = __ldcg(p.bias_grad + q);
-          sp.item_bias_w[q] = __ldcg(sp.item_bias_w + q) - lr * gb;
-          p.bias_grad[q] = 0.f;
+          float4 o = pv[w][v];
+          o.x -= lr * gr[w][v].x;
+          o.y -= lr * gr[w][v].y;
+          o.z -= lr * gr[w][v].z;
+          o.w -= lr * gr[w][v].w;
+          st4(prow[w] + c, o);
+          st4(grow[w] + c, f4zero());
         }
       }
-      if ((rec.w & kRecMultiHead) != 0 && rec.x != 0) {
-        const size_t r = (size_t)rec.x;
-        float* grow = p.user_grad + r * D;
-        float* prow = p.user_emb + r * D;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (!colok[v]) continue;
-          const int c = 4 * (g.gl + LANES * v);
-          const float4 gr = ldcg4(grow + c);
-          float4 pv = ldcg4(prow + c);
-          pv.x -= lr * gr.x;
-          pv.y -= lr * gr.y;
-          pv.z -= lr * gr.z;
-          pv.w -= lr * gr.w;
-          st4(prow + c, pv);
-          st4(grow + c, f4zero());
-        }
+      if (g.gl == 0 && p.bias_grad != nullptr) {
+        if (on[0]) { sp.item_bias_w[rec.y] = bv[0] - lr * gb[0]; p.bias_grad[rec.y] = 0.f; }
+        if (on[1]) { sp.item_bias_w[rec.z] = bv[1] - lr * gb[1]; p.bias_grad[rec.z] = 0.f; }
       }
+    }
+    // next step's first record, while this step's stores drain
+    if (s + 1 < sp.n_steps) {
+      const int64_t noff = off + p.batch;
+      const int64_t nleft = sp.n - noff;
+      const uint32_t nn = (uint32_t)(nleft < p.batch ? nleft : p.batch);
+      rec_first = (gid < nn) ? __ldg(sp.records + noff + gid) : make_int4(0, 0, 0, 0);
     }
     cluster_barrier();
   }
@@ -250,26 +263,14 @@ bool rbpr_small_batch_eligible(const rbpr_ctx* ctx, int64_t batch) {
 // `n_steps` consecutive steps over prepared records in one cluster launch on stream st.
 int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* records, int64_t n,
                             int n_steps, double* stats, cudaStream_t st) {
-  if (!ctx->stamp) {
-    RBPR_CUDA(ctx, cudaMalloc(&ctx->stamp, (size_t)ctx->I * sizeof(uint32_t)));
-    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stamp, 0, (size_t)ctx->I * sizeof(uint32_t), st));
-    ctx->stamp_epoch = 1;
-  }
-  if ((uint64_t)ctx->stamp_epoch + (uint64_t)n_steps >= 0xFFFFFFF0ull) {  // 32-bit stamps wrapped: start over
-    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->stamp, 0, (size_t)ctx->I * sizeof(uint32_t), st));
-    ctx->stamp_epoch = 1;
-  }
   SmallParams sp;
   sp.t = p;
   sp.item_emb_w = ctx->item_emb;
   sp.item_bias_w = ctx->item_bias;
-  sp.stamp = ctx->stamp;
-  sp.epoch0 = ctx->stamp_epoch;
   sp.records = records;
   sp.n = n;
   sp.n_steps = n_steps;
   sp.stats = stats;
-  ctx->stamp_epoch += (uint32_t)n_steps;
   if (stats)
     RBPR_CUDA(ctx, cudaMemsetAsync(stats, 0, (size_t)n_steps * RBPR_STATS_PER_STEP * sizeof(double), st));
   int lanes, nv;

@@ -6,6 +6,7 @@ export PYTHONUNBUFFERED=1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 echo "== parity, NCCL exchange" ; RBPR_FUSED_EXCHANGE=0 timeout 300 $TR --master-port 29541 tests/tools/check_multi_gpu.py 2>&1 | tail -4
 echo "== parity, fused exchange"; RBPR_FUSED_EXCHANGE=1 timeout 300 $TR --master-port 29542 tests/tools/check_multi_gpu.py 2>&1 | tail -6
+echo "== experiment ddp"; timeout 400 $TR --master-port 29544 tests/tools/check_experiment_ddp.py 2>&1 | tail -8
 echo "== probe"; timeout 200 $TR --master-port 29543 scripts/probe_symm.py 2>&1 | tail -12
 for fx in 0 1; do
   echo "== bench N=2 fused=$fx"
