@@ -59,7 +59,7 @@ class RefModel:
               + rn * self.item_emb[neg].pow(2).flatten(1).sum(1)
               + ru * self.user_emb[user].pow(2).flatten(1).sum(1)) / 2
         l2 = l2.sum()
-        return {"logits": x, "bpr_loss": bpr, "l2_reg": l2, "loss": bpr + l2}
+        return {"logits_pos": pos, "logits_neg": ng, "logits": x, "bpr_loss": bpr, "l2_reg": l2, "loss": bpr + l2}
 
     @torch.no_grad()
     def eval_logits(self, users: torch.Tensor, seen_padded: torch.Tensor | None) -> torch.Tensor:

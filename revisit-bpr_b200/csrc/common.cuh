@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a pointer check unless a profiler is attached
+
 #include "../../include/rbpr.h"
 
 struct rbpr_ctx {
@@ -111,6 +113,15 @@ struct rbpr_ctx {
   int64_t timed_launches = 0;
   int sm_count = 148;
   int phase_a_blocks_per_sm[4] = {0, 0, 0, 0};  // per optimizer, for the bound dim (0 = not prepared)
+};
+
+// NVTX range over a host-side scope (what the kernels enqueued inside it belong to): preparation
+// waves, phase A, the exchange, the apply, the scoring passes (tracing).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 #define RBPR_FAIL(ctx, code, ...)                     \

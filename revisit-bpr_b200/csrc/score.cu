@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) topk_metrics(const TopkParams p) {
 int score_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
                 const int32_t* seen_indices, int64_t row0, float* S, int64_t ld,
                 cudaStream_t st, const int32_t* row_map = nullptr) {
+  NvtxRange nvtx("rbpr.score_block (dense fp32)");
   dim3 grid((unsigned)((ctx->I + BN - 1) / BN), (unsigned)((n_users + BM - 1) / BM));
   score_gemm<<<grid, 256, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, n_users,
                                    (int)ctx->I, ctx->D, S, ld);

@@ -533,6 +533,7 @@ bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max) {
 int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const int64_t* seen_indptr,
                         const int32_t* seen_indices, int64_t row0, const TopkParams& tp_in, int* overflow_host,
                         cudaStream_t st) {
+  NvtxRange nvtx("rbpr.score_tc_block (pack, pass A, select, pass B, rescore)");
   const int D = ctx->D, I = (int)ctx->I;
   const int with_bias = ctx->item_bias ? 1 : 0;
   const int Kp = ((D + with_bias + KBLK - 1) / KBLK) * KBLK, KB = Kp / KBLK;

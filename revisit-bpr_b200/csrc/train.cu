@@ -621,6 +621,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_inputs, 0));
   }
   auto prepare = [&](int64_t w) -> int {
+    NvtxRange nvtx_prep("rbpr.prepare_wave (count users, sample negatives)");
     const int b = (int)(w & 1);
     const int64_t off = wave_step0(w) * batch;
     const int64_t nw = (n - off) < wave_steps(w) * batch ? (n - off) : wave_steps(w) * batch;
@@ -687,6 +688,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     const int64_t wsteps = wave_steps(w);
     if (piped) RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
     if (small) {
+      NvtxRange nvtx_small("rbpr.small_batch_wave (cluster kernel)");
       // all steps of the wave in ONE launch of one thread-block cluster (train_small.cu)
       p.batch = batch;
       p.step = step0 + (uint64_t)wave_step0(w);
@@ -703,7 +705,10 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
       float4* parts = reinterpret_cast<float4*>(ctx->partials[b]) + s * stride;
       int nb = 0;
-      rc = run_phase_a(ctx, p, hp, recs, parts, blocks, st, &nb);
+      {
+        NvtxRange nvtx_a("rbpr.phase_a");
+        rc = run_phase_a(ctx, p, hp, recs, parts, blocks, st, &nb);
+      }
       if (rc) return rc;
       const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
       double* step_stats = ctx->stats + (wave_step0(w) + s) * RBPR_STATS_PER_STEP;
@@ -716,10 +721,12 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
                        step_stats);
         if (rc) return rc;
         RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_users, ctx->aux2));
+        NvtxRange nvtx_x("rbpr.exchange (reduce + item update across ranks)");
         rc = rbpr_internal_exchange_apply(ctx, p.step, hp, st);
         if (rc) return rc;
         RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_users, 0));
       } else {
+        NvtxRange nvtx_b("rbpr.apply");
         rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32), step_stats);
         if (rc) return rc;
       }

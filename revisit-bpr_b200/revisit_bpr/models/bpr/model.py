@@ -391,16 +391,25 @@ class Model(torch.nn.Module):
             item = item.unsqueeze(-1)
         if neg.dim() < 2:
             neg = neg.unsqueeze(-1)
-        if item.size(-1) != 1 or neg.size(-1) != 1:
-            raise NotImplementedError("the fused BPR step takes one positive and one negative per row")
+        if item.shape != neg.shape or item.dim() != 2:
+            raise IndexError(f"item and neg must both be (batch, num items): got {tuple(item.shape)}, {tuple(neg.shape)}")
         if not (user.size(0) == item.size(0) == neg.size(0)):
             raise IndexError("user, item and neg must share the batch dimension")
         eng = lm.engine()
         self._configure(eng)
-        logits, stats = eng.train_step_triples(user, item.reshape(-1), neg.reshape(-1), self._opt_step)
+        width = item.size(-1)
+        users = user
+        if width > 1:
+            # several (positive, negative) pairs per row (reference model.py:41-42,48-57: logits are
+            # (batch, num items), the loss sums over all of them): B*K triples of the same fused step.
+            # The reference counts the user's L2 term once per ROW, the kernel once per triple, so the
+            # user coefficient is divided by K for this call.
+            users = user.repeat_interleave(width)
+            eng.hp.reg_user = eng.hp.reg_user / width
+        logits, stats = eng.train_step_triples(users, item.reshape(-1), neg.reshape(-1), self._opt_step)
         self._opt_step += 1
         stats32 = stats.to(torch.float32)
-        pos, ng = logits[:, 0:1], logits[:, 1:2]
+        pos, ng = logits[:, 0].reshape(-1, width), logits[:, 1].reshape(-1, width)
         if lm._user_bias is not None:
             # the user bias cancels in pos - neg (zero BPR gradient, so it never trains); it only
             # shifts the two reported logits, like MF.forward does (reference model.py:139-144)

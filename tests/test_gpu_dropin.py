@@ -318,3 +318,50 @@ def test_prepare_target_helper_matches_argsort_gather():
         prepare_target(out.to(DEV), tgt[:, :5].to(DEV))
     from revisit_bpr.metrics.metric import _context
     _context(torch.device(DEV)).sync_check()  # the non-binary target raised no device flag
+
+
+@pytest.mark.parametrize("opt_name,bias", [("sgd", True), ("adam", False)])
+def test_several_positives_and_negatives_per_row_match_the_oracle(opt_name, bias):
+    """`item` / `neg` of shape (batch, K > 1) — the general form of the reference's train forward
+    (model.py:41-42,48-57: logits (batch, num items), loss summed over all of them, the user's L2
+    term once per row) — through the fused step: K triples per row, user coefficient / K."""
+    from oracle import ref_bpr
+    from revisit_bpr.models import BPR
+    from revisit_bpr.models.bpr import MF
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    U, I, D, B, K, steps = 40, 30, 12, 16, 3, 5
+    reg = {"user": 0.02, "item": 0.01, "neg": 0.03}
+    model = BPR(MF(torch.nn.Embedding(U, D, padding_idx=0), torch.nn.Embedding(I, D, padding_idx=0), item_bias=bias),
+                reg_alphas=reg, fuse_forward=True)
+    with torch.no_grad():
+        model.logits_model._user_emb.weight.mul_(D * 2.0)
+        model.logits_model._item_emb.weight.mul_(D * 2.0)
+    feats = model.logits_model.get_features()
+    ref = ref_bpr.RefModel(feats["user"].detach().clone(), feats["item"].detach().clone(),
+                           None if not bias else feats["item_bias"].detach().clone(), reg)
+    kw = {"lr": 0.05} if opt_name == "sgd" else {"lr": 0.01, "betas": (0.9, 0.999)}
+    ropt = ref_bpr.make_optimizer(ref, opt_name, **kw)
+    model = model.to(dev)
+    opt = (torch.optim.SGD if opt_name == "sgd" else torch.optim.Adam)(model.parameters(), **kw)
+    model.bind_optimizer(opt)
+    model.train()
+    g = torch.Generator().manual_seed(9)
+    for _ in range(steps):
+        user = torch.randint(1, U, (B,), generator=g)
+        user[1] = user[0]  # a repeated user inside the batch
+        item = torch.randint(1, I, (B, K), generator=g)
+        neg = torch.randint(1, I, (B, K), generator=g)
+        out = model({"user": user.to(dev), "item": item.to(dev), "neg": neg.to(dev)})
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad()
+        exp = ref_bpr.train_step(ref, ropt, user, item, neg)
+        assert out["logits_pos"].shape == (B, K) and out["logits"].shape == (B, K)
+        np.testing.assert_allclose(out["logits_pos"].cpu().numpy(), exp["logits_pos"].numpy(), atol=1e-5, rtol=1e-4)
+        np.testing.assert_allclose(out["logits"].cpu().numpy(), exp["logits"].numpy(), atol=1e-5, rtol=1e-4)
+        np.testing.assert_allclose(out["bpr_loss"].item(), exp["bpr_loss"].item(), rtol=1e-4)
+        np.testing.assert_allclose(out["l2_reg"].item(), exp["l2_reg"].item(), rtol=1e-4)
+    sd = model.state_dict()
+    np.testing.assert_allclose(sd["logits_model._user_emb.weight"].cpu().numpy(), ref.user_emb.detach().numpy(), atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(sd["logits_model._item_emb.weight"].cpu().numpy(), ref.item_emb.detach().numpy(), atol=1e-5, rtol=1e-4)
