@@ -140,9 +140,22 @@ __device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const 
                                                  int64_t user, uint32_t sub_lo, uint32_t sub_hi,
                                                  int64_t n_entries, RowFn entry) {
   const int D = p.D;
-  // number of unseen, non-padding items
+  // number of unseen, non-padding items.  Rows of up to 32 entries (the common case: median degree
+  // 5 on the Yelp shape) are read ONCE into registers, 4 per lane; longer rows are re-read.
+  constexpr int kCache = 4;
+  const bool cached = n_entries <= (int64_t)kAdaLanes * kCache;
+  int32_t cent[kCache];
   int64_t n_seen = 0;
-  for (int64_t c = g.gl; c < n_entries; c += kAdaLanes) n_seen += (entry(c) != 0);
+  if (cached) {
+#pragma unroll
+    for (int c = 0; c < kCache; ++c) {
+      const int64_t e = g.gl + (int64_t)c * kAdaLanes;
+      cent[c] = e < n_entries ? (int32_t)entry(e) : 0;
+      n_seen += (cent[c] != 0);
+    }
+  } else {
+    for (int64_t c = g.gl; c < n_entries; c += kAdaLanes) n_seen += (entry(c) != 0);
+  }
 #pragma unroll
   for (int o = kAdaLanes / 2; o > 0; o >>= 1) n_seen += __shfl_xor_sync(g.mask, n_seen, o);
   const int64_t n_unseen = (p.I - 1) - n_seen;
@@ -217,18 +230,35 @@ __device__ __forceinline__ int32_t adaptive_draw(const AdaptiveParams& p, const 
   const int32_t* prow = p.pos + (int64_t)factor * p.I;
   const int32_t pos0 = prow[0];
   int64_t q = r;
-  while (true) {
-    int64_t c = 0;
-    for (int64_t e = g.gl; e < n_entries; e += kAdaLanes) {
-      const int64_t it = entry(e);
-      c += (it != 0 && (int64_t)prow[it] <= q);
-    }
+  if (cached) {  // positions of the masked items: one gather, then the fixed point runs on registers
+    int32_t cpos[kCache];
 #pragma unroll
-    for (int o = kAdaLanes / 2; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
-    c += (pos0 <= q);
-    const int64_t nq = r + c;
-    if (nq == q) break;
-    q = nq;
+    for (int c = 0; c < kCache; ++c) cpos[c] = cent[c] != 0 ? prow[cent[c]] : 0x7fffffff;
+    while (true) {
+      int64_t c = 0;
+#pragma unroll
+      for (int e = 0; e < kCache; ++e) c += ((int64_t)cpos[e] <= q);
+#pragma unroll
+      for (int o = kAdaLanes / 2; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
+      c += (pos0 <= q);
+      const int64_t nq = r + c;
+      if (nq == q) break;
+      q = nq;
+    }
+  } else {
+    while (true) {
+      int64_t c = 0;
+      for (int64_t e = g.gl; e < n_entries; e += kAdaLanes) {
+        const int64_t it = entry(e);
+        c += (it != 0 && (int64_t)prow[it] <= q);
+      }
+#pragma unroll
+      for (int o = kAdaLanes / 2; o > 0; o >>= 1) c += __shfl_xor_sync(g.mask, c, o);
+      c += (pos0 <= q);
+      const int64_t nq = r + c;
+      if (nq == q) break;
+      q = nq;
+    }
   }
   return p.order[(int64_t)factor * p.I + q];
 }

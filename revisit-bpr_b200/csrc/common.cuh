@@ -99,7 +99,11 @@ struct rbpr_ctx {
   uint32_t** fx_flags_dev = nullptr;  // device array of every rank's flag words
   std::vector<void*> fx_opened;       // cudaIpcOpenMemHandle mappings to close
   int fx_par = 0;                     // accumulator the current step uses
-  uint32_t fx_epoch = 0;
+  uint32_t fx_epoch = 0;       // epoch of the exchanges' folded barriers (B1 / B2 flag words)
+  uint32_t fx_bar_epoch = 0;   // epoch of the standalone barrier (bind time)
+  uint32_t fx_wait_epoch = 0;  // B2 epoch the next reader of item rows must wait for (0: nothing pending)
+  uint32_t* fx_flags_local = nullptr;  // this rank's flag words (inside fx_sym)
+  uint32_t* fx_done = nullptr;         // CTA completion counter of the exchange kernel
   float* fx_item_grad_owned = nullptr;  // the library's own accumulator while the shared ones are in use
   int64_t fused_exchanges = 0;
   // instrumentation

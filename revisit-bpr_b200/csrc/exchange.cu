@@ -49,6 +49,11 @@ struct ExchangeParams {
   float* item_v;
   float* bias_m;
   float* bias_v;
+  // barriers folded into this kernel: B1 (signal + wait at the start), B2 (signal by the last CTA)
+  uint32_t* const* flags;        // device array: flags[q] = rank q's flag words: [0,W) = B1, [W_MAX, W_MAX+W) = B2
+  uint32_t epoch;                // this exchange's barrier epoch
+  uint32_t* done;                // CTAs finished (self-resetting counter)
+  int32_t* err;
   int world, rank;
   int64_t I, lo, hi;             // rows; [lo, hi) is this rank's slice
   int D;
@@ -73,6 +78,13 @@ __global__ void __launch_bounds__(256) bpr_exchange_apply(const ExchangeParams p
     h.bc2_sqrt = t.y;
   }
   const int W = p.world;
+  // ---- B1: "every rank's phase A has landed".  This kernel runs after this rank's phase A (stream
+  // order), so CTA 0 publishes the arrival; every CTA then waits for all peers' arrivals.
+  if (blockIdx.x == 0 && threadIdx.x < W) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.rank), "r"(p.epoch) : "memory");
+  }
+  wait_peer_flags(p.flags[p.rank], W, p.epoch, p.err);
   // ---- this rank's slice: reduce over ranks, update, publish -------------------------------------
   for (int64_t r = p.lo + gid; r < p.hi; r += groups) {
     float4 gr[NV];
@@ -126,6 +138,24 @@ __global__ void __launch_bounds__(256) bpr_exchange_apply(const ExchangeParams p
   float4* z = reinterpret_cast<float4*>(p.gzero);
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < vecs; k += (int64_t)gridDim.x * blockDim.x)
     z[k] = f4zero();
+  // ---- B2: "this rank's rows have landed everywhere": the last CTA to finish publishes it; the next
+  // kernel that reads item rows (phase A, or the wait at the end of the call) waits for all ranks
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(p.done, 1u) == gridDim.x - 1) {
+      *p.done = 0u;
+      __threadfence_system();
+      for (int q = 0; q < W; ++q)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[q] + kMaxWorld + p.rank), "r"(p.epoch) : "memory");
+    }
+  }
+}
+
+// End of a call: everything that reads the item table next (scoring, torch) runs after every rank's
+// rows of the last step have landed.
+__global__ void xwait_kernel(const uint32_t* flags, int n, uint32_t epoch, int32_t* err) {
+  wait_peer_flags(flags, n, epoch, err);
 }
 
 // Cross-rank barrier on the caller's stream: thread q publishes this rank's arrival (a growing
@@ -137,9 +167,9 @@ __global__ void xrank_barrier(uint32_t* const* flags, int world, int rank, uint3
   const int q = threadIdx.x;
   if (q >= world) return;
   __threadfence_system();
-  uint32_t* theirs = flags[q] + rank;
+  uint32_t* theirs = flags[q] + 2 * kMaxWorld + rank;  // words [2*W_MAX, 3*W_MAX): this standalone barrier
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-  const uint32_t* mine = flags[rank] + q;
+  const uint32_t* mine = flags[rank] + 2 * kMaxWorld + q;
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t seen;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
@@ -177,8 +207,8 @@ size_t sym_gbytes(const rbpr_ctx* ctx) {
 }  // namespace
 
 int rbpr_internal_xrank_barrier(rbpr_ctx* ctx, cudaStream_t st) {
-  ctx->fx_epoch++;
-  xrank_barrier<<<1, 32, 0, st>>>(ctx->fx_flags_dev, ctx->world, ctx->rank, ctx->fx_epoch, ctx->flag);
+  ctx->fx_bar_epoch++;
+  xrank_barrier<<<1, 32, 0, st>>>(ctx->fx_flags_dev, ctx->world, ctx->rank, ctx->fx_bar_epoch, ctx->flag);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -187,9 +217,9 @@ int rbpr_internal_xrank_barrier(rbpr_ctx* ctx, cudaStream_t st) {
 // The exchange of one step on stream st (fused path).  ctx->item_grad is the accumulator phase A
 // used; on return it points at the (cleared) accumulator of the next step.
 int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
-  int rc = rbpr_internal_xrank_barrier(ctx, st);  // B1: every rank's gradients have landed
-  if (rc) return rc;
+  int rc = 0;
   const int par = ctx->fx_par;
+  ctx->fx_epoch++;
   ExchangeParams p;
   memset(&p, 0, sizeof(p));
   for (int q = 0; q < ctx->world; ++q) {
@@ -202,6 +232,10 @@ int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   p.item_v = ctx->item_v;
   p.bias_m = ctx->bias_m;
   p.bias_v = ctx->bias_v;
+  p.flags = ctx->fx_flags_dev;
+  p.epoch = ctx->fx_epoch;
+  p.done = ctx->fx_done;
+  p.err = ctx->flag;
   p.world = ctx->world;
   p.rank = ctx->rank;
   p.I = ctx->I;
@@ -231,11 +265,19 @@ int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   RBPR_FAIL(ctx, RBPR_ERR_ARG, "unsupported dim geometry lanes=%d nv=%d", lanes, nv);
   ctx->launches++;
   RBPR_CUDA(ctx, cudaGetLastError());
-  rc = rbpr_internal_xrank_barrier(ctx, st);  // B2: every rank's rows have landed in every table
-  if (rc) return rc;
   ctx->fx_par = par ^ 1;
+  ctx->fx_wait_epoch = ctx->fx_epoch;  // the next reader of item rows waits for B2 of this exchange
   ctx->item_grad = ctx->fx_grad[ctx->rank][ctx->fx_par];
   ctx->fused_exchanges++;
+  return 0;
+}
+
+// Block stream st until every rank's rows of the last exchange have landed (no-op when none is pending).
+int rbpr_internal_fx_wait(rbpr_ctx* ctx, cudaStream_t st) {
+  if (!ctx->fx_bound || ctx->fx_wait_epoch == 0) return 0;
+  xwait_kernel<<<1, 32, 0, st>>>(ctx->fx_flags_local + kMaxWorld, ctx->world, ctx->fx_wait_epoch, ctx->flag);
+  ctx->launches++;
+  RBPR_CUDA(ctx, cudaGetLastError());
   return 0;
 }
 
@@ -245,6 +287,8 @@ void rbpr_internal_fx_destroy(rbpr_ctx* ctx) {
   ctx->fx_opened.clear();
   cudaFree(ctx->fx_flags_dev);
   ctx->fx_flags_dev = nullptr;
+  cudaFree(ctx->fx_done);
+  ctx->fx_done = nullptr;
   if (ctx->fx_bound) ctx->item_grad = ctx->fx_item_grad_owned;  // freed by rbpr_destroy
   cudaFree(ctx->fx_sym);
   ctx->fx_sym = nullptr;
@@ -339,6 +383,10 @@ int rbpr_comm_ipc_bind(rbpr_ctx* ctx, const void* blobs, int32_t world, int32_t 
     ctx->fx_grad[q][1] = (float*)(sym + gb);
     flags_host[q] = (uint32_t*)(sym + 2 * gb);
   }
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_done, sizeof(uint32_t)));
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_done, 0, sizeof(uint32_t), st));
+  ctx->fx_flags_local = flags_host[rank];
+  ctx->fx_wait_epoch = 0;
   RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_flags_dev, kMaxWorld * sizeof(uint32_t*)));
   RBPR_CUDA(ctx, cudaMemcpyAsync(ctx->fx_flags_dev, flags_host, world * sizeof(uint32_t*), cudaMemcpyHostToDevice, st));
   RBPR_CUDA(ctx, cudaStreamSynchronize(st));

@@ -8,10 +8,13 @@
 //             fp32 panels, with their norms;
 //   pass A    S~ = U V^T on tcgen05 (kind::tf32, operands by TMA with 128-byte swizzle, fp32
 //             accumulators in TMEM, 128x128 tiles, double-buffered accumulators so the epilogue of a
-//             tile overlaps the MMAs of the next).  The epilogue — one thread per user row, straight
-//             from TMEM — applies the seen bitmask and keeps only the MAX of every 16 consecutive items;
-//   select    tau~ = k-th largest group maximum of the user (k distinct unmasked items score at least
-//             that much, so it bounds the k-th largest score from below);
+//             tile overlaps the MMAs of the next).  The epilogue — 8 warps, one thread per (user row,
+//             half of the tile's columns), straight from TMEM — keeps only the MAX of every 16
+//             consecutive items.  Item 0 and the rows padding the catalogue to a multiple of 128 carry
+//             -1e30 in an extra K column, so they never are a maximum; seen items are NOT masked here;
+//   select    tau~ = the (k + n_seen)-th largest group maximum of the user: the group maxima above
+//             it are k + n_seen distinct items, at most n_seen of them seen, so at least k unseen items
+//             score tau~ or more — a lower bound of the k-th largest unseen score;
 //   pass B    the same contraction again (cheaper than storing 200 M scores); the epilogue emits the
 //             items with S~ >= tau~ - 2 eps.  The panels hold operands ROUNDED to TF32 (cvt.rna, so the
 //             tensor core's own fp32->tf32 handling is exact): every product is off by at most
@@ -37,8 +40,11 @@ constexpr int KBLK = 32;           // fp32 per 128-byte swizzle row = one K bloc
 constexpr int KB_MAX = 9;          // K blocks of the resident user panel (D + bias <= 288)
 constexpr int GROUP = 16;          // items per group maximum
 constexpr int NGT = TN / GROUP;    // group maxima per tile and user
-constexpr int CAND_CAP = 512;      // candidate slots per user
-constexpr int kTcThreads = 192;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int CAND_CAP = 512;      // candidates per user the ranking kernel takes
+constexpr int LIST_CAP = 128;      // slots of one private candidate list (user, CTA segment, column half)
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, 64 of the tile's 128 columns each
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr float kNever = -1e30f;   // score offset of item 0 / padding rows (exact in TF32)
 constexpr uint32_t kStageBytes = TN * KBLK * 4;  // 16 KiB: one K block of a 128-row panel
 constexpr int kMinItems = 8192;    // below this the dense path is used
 
@@ -46,11 +52,12 @@ struct TcParams {
   int n_users;       // rows of this block of users
   int n_utiles, n_itiles, KB, stages;
   int pass;          // 0: group maxima, 1: candidates
-  const uint4* mask;       // (n_users, n_itiles) 128 bits per (user, tile): 1 = masked
+  int segs;          // CTA segments a user tile can be split into (private candidate lists)
+  const uint2* mask;       // (n_users, n_itiles, 2) 64 bits per (user, tile, column half): 1 = masked
   float* gmax;             // (n_users, n_itiles * NGT)
   const float* thr;        // (n_users)
-  int32_t* cnt;            // (n_users)
-  int32_t* cand;           // (n_users, CAND_CAP)
+  int32_t* cnt;            // (n_users, segs, 2) candidates in each private list (> LIST_CAP: overflow)
+  int32_t* cand;           // (n_users, segs, 2, LIST_CAP)
   int32_t* err;
 };
 
@@ -106,9 +113,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <- TMEM lane base + i)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <- TMEM lane base + i);
+// issue only: tc_ld_wait() before the values are used
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -119,10 +126,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major panel written by TMA with 128-byte swizzle: rows of
 // 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100), layout SWIZZLE_128B.
@@ -143,6 +148,29 @@ __device__ __forceinline__ float round_tf32(float x) {
 struct Work {  // the CTA's contiguous range of (user tile, item tile) units, user-tile major
   long long begin, end;
 };
+// first CTA whose range contains unit x, for ranges [total*b/G, total*(b+1)/G)
+__host__ __device__ inline long long first_cta_of(long long x, long long total, long long G) {
+  return ((x + 1) * G - 1) / total;
+}
+
+__device__ __forceinline__ float max16(const uint32_t* r) {  // tree: independent FMNMX chains
+  float a = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), b = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+  float c = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), d = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+  float e = fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), f = fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11]));
+  float g = fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), h = fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15]));
+  return fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), fmaxf(fmaxf(e, f), fmaxf(g, h)));
+}
+__device__ __forceinline__ uint32_t ge_mask32(const uint32_t* r, float thr) {  // bit j = r[j] >= thr
+  uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;  // four independent chains
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m0 |= (__uint_as_float(r[j]) >= thr ? 1u : 0u) << j;
+    m1 |= (__uint_as_float(r[8 + j]) >= thr ? 1u : 0u) << (8 + j);
+    m2 |= (__uint_as_float(r[16 + j]) >= thr ? 1u : 0u) << (16 + j);
+    m3 |= (__uint_as_float(r[24 + j]) >= thr ? 1u : 0u) << (24 + j);
+  }
+  return (m0 | m1) | (m2 | m3);
+}
 
 // ---- the contraction + filter kernel --------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -170,7 +198,7 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     mbar_init(a_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full + s, 1);
-      mbar_init(t_empty + s, 4);
+      mbar_init(t_empty + s, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -251,8 +279,9 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
     }
   } else {
-    // ===== epilogue: 4 warps, thread <-> TMEM lane <-> user row of the tile =====
-    const int quarter = warp & 3;  // the TMEM lane quarter this warp may read
+    // ===== epilogue: 8 warps; thread <-> (TMEM lane = user row of the tile, half of the columns) =====
+    const int quarter = warp & 3;          // the TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;      // columns [64*half, 64*half + 64) of the tile
     const int row = quarter * 32 + lane;
     uint32_t t = 0;
     bool ok = true;
@@ -263,52 +292,53 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int u = ut * TM + row;
       const bool valid = u < p.n_users;
       const float thr = (p.pass == 1 && valid) ? __ldg(p.thr + u) : 0.f;
+      // pass B: this thread's private candidate list for the segment (no atomics on the way)
+      const int sg = (int)((long long)blockIdx.x - first_cta_of((long long)ut * p.n_itiles, total, gridDim.x));
+      const size_t list = ((size_t)u * p.segs + (size_t)sg) * 2 + (size_t)half;
+      int32_t* my_cand = p.cand + list * LIST_CAP;
+      int n_cand = 0;
+      const uint2* mrow = p.mask + ((size_t)u * p.n_itiles) * 2 + half;
+      uint2 mw_next = make_uint2(~0u, ~0u);
+      if (p.pass == 1 && valid) mw_next = __ldg(mrow + (size_t)it0 * 2);
       for (int it = it0; it < it1 && ok; ++it, ++t) {
         const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
-        uint4 mw = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (valid) mw = __ldg(p.mask + (size_t)u * p.n_itiles + it);
+        const uint2 mw = mw_next;
+        if (p.pass == 1 && valid && it + 1 < it1) mw_next = __ldg(mrow + (size_t)(it + 1) * 2);  // one tile ahead
         ok = mbar_wait(t_full + acc, aph, p.err);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)TN;
-        const uint32_t words[4] = {mw.x, mw.y, mw.z, mw.w};
-        float gm[NGT];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tc_ld32(taddr + (uint32_t)(c * 32), v);
-          const uint32_t wbits = words[c];
-          if (p.pass == 0) {
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m0 = fmaxf(m0, ((wbits >> j) & 1u) ? -INFINITY : v[j]);
-#pragma unroll
-            for (int j = 16; j < 32; ++j) m1 = fmaxf(m1, ((wbits >> j) & 1u) ? -INFINITY : v[j]);
-            gm[2 * c] = m0;
-            gm[2 * c + 1] = m1;
-          } else {
-            uint32_t pm = 0u;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pm |= (v[j] >= thr ? 1u : 0u) << j;
-            pm &= ~wbits;
-            while (pm != 0u) {  // rare: ~1 % of the scores
-              const int j = __ffs(pm) - 1;
-              pm &= pm - 1u;
-              const int pos = atomicAdd(p.cnt + u, 1);
-              if (pos < CAND_CAP) p.cand[(size_t)u * CAND_CAP + pos] = it * TN + c * 32 + j;
-            }
-          }
-        }
-        // accumulator drained: hand it back to the MMA warp
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)TN + (uint32_t)(half * 64);
+        uint32_t r0[32], r1[32];
+        tc_ld32(taddr, r0);
+        tc_ld32(taddr + 32u, r1);
+        tc_ld_wait();
+        // accumulator drained into registers: hand it back to the MMA warp before the arithmetic
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty + acc);
-        if (p.pass == 0 && valid) {
-          float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u * p.n_itiles * NGT + (size_t)it * NGT);
-          dst[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
-          dst[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+        if (p.pass == 0) {
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u * p.n_itiles * NGT + (size_t)it * NGT + half * 4);
+            *dst = make_float4(max16(r0), max16(r0 + 16), max16(r1), max16(r1 + 16));
+          }
+        } else {
+          uint32_t pm0 = ge_mask32(r0, thr) & ~mw.x, pm1 = ge_mask32(r1, thr) & ~mw.y;
+          const int base = it * TN + half * 64;
+          while (pm0 != 0u) {  // rare: ~1 % of the scores
+            const int j = __ffs(pm0) - 1;
+            pm0 &= pm0 - 1u;
+            if (n_cand < LIST_CAP) my_cand[n_cand] = base + j;
+            ++n_cand;
+          }
+          while (pm1 != 0u) {
+            const int j = __ffs(pm1) - 1;
+            pm1 &= pm1 - 1u;
+            if (n_cand < LIST_CAP) my_cand[n_cand] = base + 32 + j;
+            ++n_cand;
+          }
         }
       }
+      if (p.pass == 1 && valid && ok) p.cnt[list] = n_cand;
       unit += it1 - it0;
     }
   }
@@ -321,10 +351,11 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 }
 
 // ---- small kernels around it ----------------------------------------------------------------------
-// K-padded fp32 panel of the item table: [v_i, bias_i, 0 ...]; rows >= I are zero.  One warp per row;
-// also the squared norm of the packed row and the maximum norm over rows.
+// K-padded TF32 panel of the item table: [v_i, bias_i, never_i, 0 ...] with never_i = -1e30 for item 0
+// and for the rows padding the catalogue to a multiple of 128 (the users' panel holds 1 in that
+// column), 0 otherwise.  One warp per row; also max |[v_i, bias_i]| over the real rows.
 __global__ void pack_items(const float* __restrict__ item_emb, const float* __restrict__ item_bias, int I, int D,
-                           int Kp, int rows, float* __restrict__ out, uint32_t* __restrict__ vmax_bits) {
+                           int with_bias, int Kp, int rows, float* __restrict__ out, uint32_t* __restrict__ vmax_bits) {
   const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -333,16 +364,18 @@ __global__ void pack_items(const float* __restrict__ item_emb, const float* __re
     float v = 0.f;
     if (r < I) {
       if (c < D) v = item_emb[(int64_t)r * D + c];
-      else if (c == D && item_bias != nullptr) v = item_bias[r];
+      else if (c == D && with_bias) v = item_bias[r];
     }
-    out[(int64_t)r * Kp + c] = round_tf32(v);
     sq += v * v;
+    if (c == D + with_bias && (r == 0 || r >= I)) v = kNever;
+    out[(int64_t)r * Kp + c] = round_tf32(v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   if (lane == 0 && r < I) atomicMax(vmax_bits, __float_as_uint(sqrtf(sq)));  // non-negative floats order as uints
 }
 
+// Gathered users' panel [u, 1 (bias column), 1 (never column), 0 ...]; |[u, 1]| for the error bound.
 __global__ void pack_users(const float* __restrict__ user_emb, const int64_t* __restrict__ users, int n_users, int D,
                            int Kp, int rows, int with_bias, int64_t U, float* __restrict__ out,
                            float* __restrict__ unorm, int32_t* __restrict__ err) {
@@ -364,15 +397,16 @@ __global__ void pack_users(const float* __restrict__ user_emb, const int64_t* __
       if (c < D) v = user_emb[u * D + c];
       else if (c == D && with_bias) v = 1.0f;
     }
-    out[(int64_t)r * Kp + c] = round_tf32(v);
     sq += v * v;
+    if (r < n_users && c == D + with_bias) v = 1.0f;
+    out[(int64_t)r * Kp + c] = round_tf32(v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   if (lane == 0 && r < n_users) unorm[r] = sqrtf(sq);
 }
 
-// 128 bits per (user, item tile): item 0, the user's seen items and columns >= I are masked.
+// 128 bits per (user, item tile): item 0, the user's seen items and columns >= I are masked (pass B).
 __global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
                            int64_t row0, int n_users, int I, int n_itiles, uint32_t* __restrict__ mask) {
   const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -390,68 +424,98 @@ __global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_
   }
 }
 
-// tau~ = k-th largest group maximum (8-bit radix select over the float keys), then the pass-B
-// threshold tau~ - 2 eps with eps = 1.01 * 2^-10 |u'| max|v'| (see the file header).
-__global__ void __launch_bounds__(256)
-select_threshold(const float* __restrict__ gmax, int G, int k, const float* __restrict__ unorm,
-                 const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_need;
+// tau~ = the (k + n_seen)-th largest group maximum of a user, by bisection over the monotone uint32
+// float keys held in shared memory (32 rounds, each a strided count + one block reduction), then the
+// pass-B threshold tau~ - 2 eps.  One CTA of 128 threads per user.
+constexpr int kSelThreads = 128;
+__global__ void __launch_bounds__(kSelThreads)
+select_threshold(const float* __restrict__ gmax, int G, int k, const int64_t* __restrict__ seen_indptr, int64_t row0,
+                 const float* __restrict__ unorm, const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
+  extern __shared__ uint32_t keys[];  // G
+  __shared__ int warp_cnt[kSelThreads / 32];
   const int tid = threadIdx.x;
   const float* row = gmax + (size_t)blockIdx.x * G;
-  uint32_t prefix = 0, prefix_mask = 0, need = (uint32_t)k;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    hist[tid] = 0;
+  for (int i = tid; i < G; i += kSelThreads) keys[i] = fkey(row[i]);
+  int64_t n_seen = 0;
+  if (seen_indptr != nullptr) n_seen = seen_indptr[row0 + blockIdx.x + 1] - seen_indptr[row0 + blockIdx.x];
+  const int64_t want64 = (int64_t)k + n_seen;
+  __syncthreads();
+  if (want64 > (int64_t)G) {  // not enough groups to bound the k-th unseen score: everything is a candidate
+    if (tid == 0) thr[blockIdx.x] = -INFINITY;
+    return;
+  }
+  const int want = (int)want64;
+  // largest key T with #{keys >= T} >= want  ==  the want-th largest key
+  uint32_t T = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int i = tid; i < G; i += kSelThreads) c += (keys[i] >= cand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) warp_cnt[tid >> 5] = c;
     __syncthreads();
-    for (int i = tid; i < G; i += 256) {
-      const uint32_t key = fkey(row[i]);
-      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t acc = 0;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (acc + hist[b] >= need) break;
-        acc += hist[b];
-      }
-      s_prefix = prefix | ((uint32_t)b << shift);
-      s_need = need - acc;
-    }
-    __syncthreads();
-    prefix = s_prefix;
-    need = s_need;
-    prefix_mask |= 255u << shift;
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < kSelThreads / 32; ++q) tot += warp_cnt[q];
+    if (tot >= want) T = cand;
     __syncthreads();
   }
   if (tid == 0) {
-    const float tau = ikey(prefix);  // -inf when fewer than k groups hold an unmasked item
+    const float tau = ikey(T);
     const float eps2 = 0.002f * unorm[blockIdx.x] * __uint_as_float(*vmax_bits);  // >= 2 * 1.01 * 2^-10 |u'| max|v'|
     thr[blockIdx.x] = tau - eps2;
   }
 }
 
-// Exact fp32 scores of the candidates, ranking, outputs.  One CTA of 128 threads per user.
-__global__ void __launch_bounds__(128)
+// Exact fp32 scores of the candidates, ranking, outputs.  One CTA of 256 threads per user.
+constexpr int kRankThreads = 256;
+__global__ void __launch_bounds__(kRankThreads)
 rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_emb, const float* __restrict__ item_bias,
-             const int64_t* __restrict__ users, int D, const int32_t* __restrict__ cnt, const int32_t* __restrict__ cand,
-             int32_t* __restrict__ overflow_rows, int32_t* __restrict__ overflow_count, TopkParams p) {
-  __shared__ unsigned long long sel[CAND_CAP];
+             const int64_t* __restrict__ users, int D, int segs, const int32_t* __restrict__ cnt,
+             const int32_t* __restrict__ cand, int32_t* __restrict__ overflow_rows, int32_t* __restrict__ overflow_count,
+             TopkParams p) {
+  __shared__ unsigned long long key_in[CAND_CAP];
+  __shared__ unsigned long long sel[KCAP];
+  __shared__ int32_t items[CAND_CAP];
   __shared__ __align__(16) float s_u[1024];
+  __shared__ int s_n, s_bad;
   const int tid = threadIdx.x;
   const int64_t urow = blockIdx.x;
-  const int n = cnt[urow];
-  if (n > CAND_CAP) {  // mass ties: this user goes through the dense path afterwards
+  const int n_lists = segs * 2;
+  const int32_t* c_row = cnt + (size_t)urow * n_lists;
+  // gather the private lists (thread 0 walks the counts: a handful of lists, 2*segs)
+  if (tid == 0) {
+    int n = 0, bad = 0;
+    for (int l = 0; l < n_lists; ++l) {
+      const int c = c_row[l];
+      bad |= (c > LIST_CAP);
+      n += c;
+    }
+    s_n = n;
+    s_bad = bad | (n > CAND_CAP);
+  }
+  __syncthreads();
+  if (s_bad) {  // mass ties: this user goes through the dense path afterwards
     if (tid == 0) overflow_rows[atomicAdd(overflow_count, 1)] = (int32_t)urow;
     return;
   }
+  const int n = s_n;
+  {
+    int off = 0;
+    for (int l = 0; l < n_lists; ++l) {
+      const int c = c_row[l];
+      const int32_t* src = cand + ((size_t)urow * n_lists + l) * LIST_CAP;
+      for (int i = tid; i < c; i += kRankThreads) items[off + i] = src[i];
+      off += c;
+    }
+  }
   const int64_t u = users[urow];
-  for (int c = tid; c < D; c += 128) s_u[c] = user_emb[u * D + c];
-  for (int i = tid; i < CAND_CAP; i += 128) sel[i] = 0ull;
+  for (int c = tid; c < D; c += kRankThreads) s_u[c] = user_emb[u * D + c];
+  for (int i = tid; i < KCAP; i += kRankThreads) sel[i] = 0ull;
   __syncthreads();
-  for (int q = tid; q < n; q += 128) {
-    const int32_t it = cand[(size_t)urow * CAND_CAP + q];
+  for (int q = tid; q < n; q += kRankThreads) {
+    const int32_t it = items[q];
     const float* v = item_emb + (int64_t)it * D;
     float acc = 0.f;  // k ascending fmaf chain: the arithmetic of score_gemm
     for (int c = 0; c < D; c += 4) {
@@ -462,25 +526,17 @@ rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_
       acc = fmaf(s_u[c + 3], x.w, acc);
     }
     if (item_bias != nullptr) acc += __ldg(item_bias + it);
-    sel[q] = ((unsigned long long)fkey(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)it);
+    key_in[q] = ((unsigned long long)fkey(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)it);
   }
   __syncthreads();
-  // bitonic sort of CAND_CAP composite keys, descending (empty slots are 0 and sink to the end)
-  for (int size = 2; size <= CAND_CAP; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < CAND_CAP / 2; t += 128) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = sel[lo], b = sel[hi];
-        if ((a < b) == desc) {
-          sel[lo] = b;
-          sel[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
+  // rank by counting (keys are distinct: the item id is part of the key): no sorting network, one pass
+  for (int q = tid; q < n; q += kRankThreads) {
+    const unsigned long long mine = key_in[q];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += (key_in[j] > mine);  // same address across the warp: broadcast
+    if (r < KCAP) sel[r] = mine;
   }
+  __syncthreads();
   topk_emit_outputs(p, urow, sel, min(min(p.k_max, p.I), n));
 }
 
@@ -523,8 +579,8 @@ int grow(rbpr_ctx* ctx, void** ptr, size_t* have, size_t need) {
 // Is the tensor path applicable to this context's tables and this request?
 bool rbpr_score_tc_eligible(const rbpr_ctx* ctx, int k_max) {
   if (getenv("RBPR_NO_TC_SCORE") != nullptr) return false;
-  const int kp = ((ctx->D + (ctx->item_bias ? 1 : 0) + KBLK - 1) / KBLK) * KBLK;
-  return ctx->I >= kMinItems && kp / KBLK <= KB_MAX && k_max <= RBPR_MAX_TOPK && ctx->D % 4 == 0 && ctx->D <= 1024;
+  const int kp = ((ctx->D + (ctx->item_bias ? 1 : 0) + 1 + KBLK - 1) / KBLK) * KBLK;
+  return ctx->I >= kMinItems && kp / KBLK <= KB_MAX && k_max <= KCAP && ctx->D % 4 == 0 && ctx->D <= 1024;
 }
 
 // One block of users (n_users <= 16384) through the tensor path.  Outputs as TopkParams describes;
@@ -536,10 +592,21 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   NvtxRange nvtx("rbpr.score_tc_block (pack, pass A, select, pass B, rescore)");
   const int D = ctx->D, I = (int)ctx->I;
   const int with_bias = ctx->item_bias ? 1 : 0;
-  const int Kp = ((D + with_bias + KBLK - 1) / KBLK) * KBLK, KB = Kp / KBLK;
+  const int Kp = ((D + with_bias + 1 + KBLK - 1) / KBLK) * KBLK, KB = Kp / KBLK;  // + the "never" column
   const int n_utiles = (n_users + TM - 1) / TM, n_itiles = (I + TN - 1) / TN;
   const int urows = n_utiles * TM, irows = n_itiles * TN;
   const int G = n_itiles * NGT;
+  // persistent grid: one CTA per SM, contiguous ranges of (user tile, item tile) units; a user tile
+  // split over several CTAs gets one private candidate list per CTA segment
+  const long long units = (long long)n_utiles * n_itiles;
+  const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
+  int segs = 1;
+  for (int ut = 0; ut < n_utiles; ++ut) {
+    const long long a = first_cta_of((long long)ut * n_itiles, units, grid);
+    const long long b = first_cta_of((long long)(ut + 1) * n_itiles - 1, units, grid);
+    if ((int)(b - a + 1) > segs) segs = (int)(b - a + 1);
+  }
+  const size_t n_lists = (size_t)n_users * segs * 2;
   // scratch
   int rc = grow(ctx, (void**)&ctx->tc_items, &ctx->tc_items_bytes, (size_t)irows * Kp * sizeof(float));
   if (rc) return rc;
@@ -549,25 +616,24 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   if (rc) return rc;
   rc = grow(ctx, (void**)&ctx->tc_gmax, &ctx->tc_gmax_bytes, (size_t)n_users * G * sizeof(float));
   if (rc) return rc;
-  rc = grow(ctx, (void**)&ctx->tc_cand, &ctx->tc_cand_bytes, (size_t)n_users * CAND_CAP * sizeof(int32_t));
+  rc = grow(ctx, (void**)&ctx->tc_cand, &ctx->tc_cand_bytes, n_lists * LIST_CAP * sizeof(int32_t));
   if (rc) return rc;
-  // small per-user arrays in one allocation: thr | unorm | cnt | overflow rows | {overflow count, vmax}
-  const size_t small = (size_t)n_users * 4 * sizeof(float) + 256;
+  // small arrays in one allocation: thr | unorm | overflow rows | {overflow count, vmax} | list counts
+  const size_t small = (size_t)n_users * 3 * sizeof(float) + 256 + n_lists * sizeof(int32_t);
   rc = grow(ctx, (void**)&ctx->tc_small, &ctx->tc_small_bytes, small);
   if (rc) return rc;
   float* thr = (float*)ctx->tc_small;
   float* unorm = thr + n_users;
-  int32_t* cnt = (int32_t*)(unorm + n_users);
-  int32_t* ovf_rows = cnt + n_users;
+  int32_t* ovf_rows = (int32_t*)(unorm + n_users);
   int32_t* ovf_count = ovf_rows + n_users;
   uint32_t* vmax_bits = (uint32_t*)(ovf_count + 1);
+  int32_t* cnt = ovf_count + 64;
   ctx->tc_overflow_rows = ovf_rows;
 
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->tc_mask, 0, (size_t)n_users * n_itiles * 16, st));
-  RBPR_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)n_users * sizeof(int32_t), st));
-  RBPR_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, 2 * sizeof(int32_t), st));
-  pack_items<<<(unsigned)(((int64_t)irows * 32 + 255) / 256), 256, 0, st>>>(ctx->item_emb, ctx->item_bias, I, D, Kp, irows,
-                                                                            ctx->tc_items, vmax_bits);
+  RBPR_CUDA(ctx, cudaMemsetAsync(ovf_count, 0, 256 + n_lists * sizeof(int32_t), st));  // count, vmax, list counts
+  pack_items<<<(unsigned)(((int64_t)irows * 32 + 255) / 256), 256, 0, st>>>(ctx->item_emb, ctx->item_bias, I, D, with_bias,
+                                                                            Kp, irows, ctx->tc_items, vmax_bits);
   pack_users<<<(unsigned)(((int64_t)urows * 32 + 255) / 256), 256, 0, st>>>(ctx->user_emb, users, n_users, D, Kp, urows,
                                                                             with_bias, ctx->U, ctx->tc_users, unorm, ctx->flag);
   build_mask<<<(unsigned)(((int64_t)n_users * 32 + 255) / 256), 256, 0, st>>>(seen_indptr, seen_indices, row0, n_users, I,
@@ -585,8 +651,10 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   static bool attr_set = false;
   if (!attr_set) {
     RBPR_CUDA(ctx, cudaFuncSetAttribute(score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RBPR_CUDA(ctx, cudaFuncSetAttribute(select_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
+  if ((size_t)G * sizeof(uint32_t) > 96 * 1024) RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_tc: catalogue too large for the tensor path");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.n_users = n_users;
@@ -594,24 +662,24 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   p.n_itiles = n_itiles;
   p.KB = KB;
   p.stages = stages;
-  p.mask = (const uint4*)ctx->tc_mask;
+  p.segs = segs;
+  p.mask = (const uint2*)ctx->tc_mask;
   p.gmax = ctx->tc_gmax;
   p.thr = thr;
   p.cnt = cnt;
   p.cand = ctx->tc_cand;
   p.err = ctx->flag;
-  const long long units = (long long)n_utiles * n_itiles;
-  const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
   p.pass = 0;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   const int k = tp_in.k_max < I ? tp_in.k_max : I;
-  select_threshold<<<n_users, 256, 0, st>>>(ctx->tc_gmax, G, k, unorm, vmax_bits, thr);
+  select_threshold<<<n_users, kSelThreads, (size_t)G * sizeof(uint32_t), st>>>(ctx->tc_gmax, G, k, seen_indptr, row0, unorm,
+                                                                                vmax_bits, thr);
   p.pass = 1;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   TopkParams tp = tp_in;
   tp.row0 = row0;
-  rescore_rank<<<n_users, 128, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, D, cnt, ctx->tc_cand, ovf_rows,
-                                        ovf_count, tp);
+  rescore_rank<<<n_users, kRankThreads, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, D, segs, cnt,
+                                                 ctx->tc_cand, ovf_rows, ovf_count, tp);
   ctx->launches += 4;
   ctx->topk_launches++;
   ctx->tc_passes++;

@@ -189,6 +189,11 @@ void fill_train_params(rbpr_ctx* ctx, TrainParams& p, uint64_t seed, const rbpr_
   p.alias_prob = ctx->alias_prob;
   p.alias_idx = ctx->alias_idx;
   p.flag = ctx->flag;
+  if (ctx->fx_bound && ctx->fx_wait_epoch != 0) {  // item rows of the previous exchange must have landed
+    p.xwait_flags = ctx->fx_flags_local + RBPR_MAX_PEERS;
+    p.xwait_n = ctx->world;
+    p.xwait_epoch = ctx->fx_wait_epoch;
+  }
   p.D = ctx->D;
   p.I = (uint32_t)ctx->I;
   p.seed_lo = (uint32_t)seed;
@@ -414,6 +419,7 @@ int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* rec
 
 // defined in exchange.cu
 int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st);
+int rbpr_internal_fx_wait(rbpr_ctx* ctx, cudaStream_t st);
 
 // The step's one exchange on stream st: dense item gradient summed over ranks, then the (dense,
 // identical on every rank) item update.
@@ -474,6 +480,8 @@ int rbpr_internal_phase_a_apply(rbpr_ctx* ctx, const rbpr_hparams* hp, const int
     int rc = ensure_adam_table(ctx, hp, (int64_t)step + 1, (int64_t)step + 1, st);
     if (rc) return rc;
     rc = rbpr_internal_exchange_apply(ctx, step, hp, st);
+    if (rc) return rc;
+    rc = rbpr_internal_fx_wait(ctx, st);
     if (rc) return rc;
   }
   if (stats_out)
@@ -702,6 +710,11 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       p.step = step0 + (uint64_t)(wave_step0(w) + s);
       p.item_grad = ctx->item_grad;  // alternates between two buffers under the fused exchange
       p.bias_grad = ctx->item_bias ? ctx->item_grad + ctx->I * ctx->D : nullptr;
+      if (ctx->fx_bound && ctx->fx_wait_epoch != 0) {
+        p.xwait_flags = ctx->fx_flags_local + RBPR_MAX_PEERS;
+        p.xwait_n = ctx->world;
+        p.xwait_epoch = ctx->fx_wait_epoch;
+      }
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
       float4* parts = reinterpret_cast<float4*>(ctx->partials[b]) + s * stride;
       int nb = 0;
@@ -733,6 +746,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     }
     if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
   }
+  rc = rbpr_internal_fx_wait(ctx, st);  // data parallel: the item table is complete when the call's work is
+  if (rc) return rc;
   if (stats_out)
     RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats,
                                    steps * RBPR_STATS_PER_STEP * sizeof(double),

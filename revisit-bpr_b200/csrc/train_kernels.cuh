@@ -53,7 +53,33 @@ struct TrainParams {
   float lr, beta1, beta2, eps;
   float reg_user, reg_item, reg_neg;
   const float2* __restrict__ adam_tab;  // per-step Adam scalars (see adam_catchup4), or null for SGD
+  // fused peer-memory exchange (exchange.cu): before touching item rows, wait until every rank has
+  // published the rows of the previous step (flag words in LOCAL memory, written by the peers)
+  const uint32_t* __restrict__ xwait_flags;  // (world) or null
+  int xwait_n;
+  uint32_t xwait_epoch;
 };
+
+// Every CTA waits (thread 0 polls, bounded) until all `n` flag words have reached `epoch`.
+__device__ __forceinline__ void wait_peer_flags(const uint32_t* flags, int n, uint32_t epoch, int32_t* err) {
+  if (flags == nullptr) return;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < n; ++q) {
+      bool ok = false;
+      for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + q) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) {
+          ok = true;
+          break;
+        }
+        __nanosleep(32);
+      }
+      if (!ok) atomicExch(err, 10);
+    }
+  }
+  __syncthreads();
+}
 
 struct ApplyParams {
   float* __restrict__ item_emb;
@@ -391,6 +417,7 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
   const uint32_t n = (uint32_t)p.n;
   const uint32_t ngroups = (gridDim.x * kPhaseAThreads) / LANES;
   float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
+  wait_peer_flags(p.xwait_flags, p.xwait_n, p.xwait_epoch, p.flag);  // data parallel: last step's rows have landed
 
   bool colok[NV];
 #pragma unroll
@@ -568,41 +595,60 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
     h.bc2_sqrt = t.y;
   }
   if (p.do_users) {
-    for (int64_t k = gid; k < p.n; k += groups) {
-      const int4 rec = __ldg(p.records + k);
-      if ((rec.w & kRecMultiHead) == 0 || rec.x == 0) continue;
-      const int64_t r = rec.x;
-      float* grow = p.user_grad + r * D;
-      float* prow = p.user_emb + r * D;
-      int64_t last = 0;
-      if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
-      const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
-      const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = 4 * (g.gl + LANES * v);
-        if (c >= D) continue;
-        const float4 gr = ld4(grow + c);
-        float4 pp = ld4(prow + c);
-        if (OPT == RBPR_OPT_SGD) {
-          pp.x -= p.lr * gr.x;
-          pp.y -= p.lr * gr.y;
-          pp.z -= p.lr * gr.z;
-          pp.w -= p.lr * gr.w;
-        } else {
-          float4 m = ld4(p.user_m + r * D + c);
-          float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
-          if (behind) cu.apply(pp, m, vv);
-          opt4<OPT>(pp, m, vv, gr, h);
-          st4(p.user_m + r * D + c, m);
-          if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
+    // Warp-coalesced scan of the step's records (32 records = 512 B per warp and round trip; only the
+    // few flagged kRecMultiHead carry work), then the flagged ones are dealt to the warp's lane groups.
+    constexpr int GPW = 32 / LANES;  // lane groups per warp
+    const int lane = threadIdx.x & 31;
+    const int gsub = lane / LANES;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t base = wid * 32; base < p.n; base += warps * 32) {
+      const int64_t k = base + lane;
+      const int4 rec = (k < p.n) ? __ldg(p.records + k) : make_int4(0, 0, 0, 0);
+      unsigned bal = __ballot_sync(0xffffffffu, (rec.w & kRecMultiHead) != 0 && rec.x != 0);
+      while (bal != 0u) {
+        unsigned m = bal;
+        int src = -1;
+        for (int q = 0; q <= gsub && m != 0u; ++q) {  // the gsub-th of the lowest GPW flagged records
+          src = (q == gsub) ? (__ffs(m) - 1) : -1;
+          m &= m - 1u;
         }
-        st4(prow + c, pp);
-        st4(grow + c, f4zero());
-      }
-      if (OPT != RBPR_OPT_SGD) {
-        __syncwarp(g.mask);
-        if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
+#pragma unroll
+        for (int q = 0; q < GPW; ++q) bal &= bal - 1u;  // (x & (x-1) of 0 stays 0)
+        const int64_t r = (int64_t)__shfl_sync(0xffffffffu, rec.x, src < 0 ? 0 : src);
+        if (src < 0) continue;
+        float* grow = p.user_grad + r * D;
+        float* prow = p.user_emb + r * D;
+        int64_t last = 0;
+        if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
+        const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
+        const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = 4 * (g.gl + LANES * v);
+          if (c >= D) continue;
+          const float4 gr = ld4(grow + c);
+          float4 pp = ld4(prow + c);
+          if (OPT == RBPR_OPT_SGD) {
+            pp.x -= p.lr * gr.x;
+            pp.y -= p.lr * gr.y;
+            pp.z -= p.lr * gr.z;
+            pp.w -= p.lr * gr.w;
+          } else {
+            float4 m4 = ld4(p.user_m + r * D + c);
+            float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
+            if (behind) cu.apply(pp, m4, vv);
+            opt4<OPT>(pp, m4, vv, gr, h);
+            st4(p.user_m + r * D + c, m4);
+            if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
+          }
+          st4(prow + c, pp);
+          st4(grow + c, f4zero());
+        }
+        if (OPT != RBPR_OPT_SGD) {
+          __syncwarp(g.mask);
+          if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
+        }
       }
     }
   }

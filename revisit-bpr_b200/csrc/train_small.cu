@@ -66,8 +66,28 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
 #pragma unroll
   for (int v = 0; v < NV; ++v) colok[v] = 4 * (g.gl + LANES * v) < D;
 
-  // the group's first record of a step is fetched during the previous step (records are static)
-  int4 rec_first = (gid < (uint32_t)(sp.n < p.batch ? sp.n : p.batch)) ? __ldg(sp.records + gid) : make_int4(0, 0, 0, 0);
+  // Records are static, so the group's first record of step s+1 is fetched during step s and the rows
+  // it names are prefetched into L2 one step ahead (the user table does not fit L2: without this the
+  // gather of every step waits for DRAM).  A prefetch only warms L2; the load that follows the
+  // barrier still reads the current value.
+  auto first_record = [&](int step) -> int4 {
+    const int64_t o = (int64_t)step * p.batch;
+    const int64_t l = sp.n - o;
+    const int64_t nn = l < p.batch ? l : p.batch;
+    return (step < sp.n_steps && (int64_t)gid < nn) ? __ldg(sp.records + o + gid) : make_int4(0, 0, 0, 0);
+  };
+  auto prefetch_rows = [&](const int4& r) {
+    const int c = 4 * g.gl;  // one 16-byte column per lane: LANES lanes cover the first 16*LANES bytes, NV strides the rest
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!colok[v]) continue;
+      const int cc = c + 4 * LANES * v;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.user_emb + (size_t)r.x * D + cc));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.item_emb + (size_t)r.y * D + cc));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.item_emb + (size_t)r.z * D + cc));
+    }
+  };
+  int4 rec_first = first_record(0), rec_ahead = first_record(1);
   for (int s = 0; s < sp.n_steps; ++s) {
     const int64_t off = (int64_t)s * p.batch;
     const int64_t left = sp.n - off;
@@ -75,6 +95,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
     const int4* recs = sp.records + off;
     float loss_acc = 0.f, absx_acc = 0.f, l2_acc = 0.f, cnt_acc = 0.f;
     const int4 rec0 = rec_first;
+    if (s + 1 < sp.n_steps) prefetch_rows(rec_ahead);  // rows of step s+1 (its record arrived a step ago)
 
     // ---- A: gather, loss, gradients ---------------------------------------------------------------
     for (uint32_t k = gid; k < n; k += groups_total) {
@@ -238,13 +259,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
         if (on[1]) { sp.item_bias_w[rec.z] = bv[1] - lr * gb[1]; p.bias_grad[rec.z] = 0.f; }
       }
     }
-    // next step's first record, while this step's stores drain
-    if (s + 1 < sp.n_steps) {
-      const int64_t noff = off + p.batch;
-      const int64_t nleft = sp.n - noff;
-      const uint32_t nn = (uint32_t)(nleft < p.batch ? nleft : p.batch);
-      rec_first = (gid < nn) ? __ldg(sp.records + noff + gid) : make_int4(0, 0, 0, 0);
-    }
+    rec_first = rec_ahead;
+    rec_ahead = first_record(s + 2);  // consumed two steps from now: its latency is never waited for
     cluster_barrier();
   }
 }

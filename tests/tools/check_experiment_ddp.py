@@ -21,7 +21,10 @@ for p in (ROOT, ROOT / "revisit-bpr_b200", ROOT / "tests"):
     sys.path.insert(0, str(p))
 import test_gpu_experiment as T  # noqa: E402  (config text + dataset writer)
 
+import faulthandler  # noqa: E402
+
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+faulthandler.dump_traceback_later(int(os.environ.get("RBPR_HANG_DUMP_S", "90")), repeat=False, exit=True)
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
@@ -47,7 +50,11 @@ for mode, optimizer, lr in (("stock", "torch.optim.SGD", 0.05), ("fast", "torch.
     if mode == "fast":
         cfg["fast_train"], cfg["fast_steps_per_chunk"] = True, 5
     exp = instantiate(cfg.pop("experiment"), exp_config=lambda: cfg, dir=None, debug=False, seed=13, trackers_params={})
+    print(f"[rank {rank}] {mode} {optimizer}: run()", flush=True)
     exp.run()
+    print(f"[rank {rank}] {mode} {optimizer}: done", flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(int(os.environ.get("RBPR_HANG_DUMP_S", "90")), repeat=False, exit=True)
     ok, why = True, []
     sd = {k: v.detach().clone() for k, v in exp._model.state_dict().items()}
     for k, v in sd.items():
