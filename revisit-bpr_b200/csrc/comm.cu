@@ -16,6 +16,7 @@ typedef int (*fn_get_unique_id)(nccl_unique_id*);
 typedef int (*fn_comm_init_rank)(nccl_comm_t*, int, nccl_unique_id, int);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
 typedef int (*fn_comm_destroy)(nccl_comm_t);
+typedef int (*fn_comm_abort)(nccl_comm_t);
 typedef const char* (*fn_error_string)(int);
 constexpr int kNcclFloat32 = 7, kNcclSum = 0;
 
@@ -25,6 +26,7 @@ struct NcclApi {
   fn_comm_init_rank comm_init_rank = nullptr;
   fn_all_reduce all_reduce = nullptr;
   fn_comm_destroy comm_destroy = nullptr;
+  fn_comm_abort comm_abort = nullptr;
   fn_error_string error_string = nullptr;
 };
 
@@ -44,6 +46,7 @@ NcclApi* nccl_api(rbpr_ctx* ctx) {
   api.comm_init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
   api.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
   api.comm_destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
+  api.comm_abort = (fn_comm_abort)dlsym(h, "ncclCommAbort");
   api.error_string = (fn_error_string)dlsym(h, "ncclGetErrorString");
   if (!api.get_unique_id || !api.comm_init_rank || !api.all_reduce || !api.comm_destroy) {
     ctx->err = "libnccl.so.2 lacks an expected symbol";
@@ -77,7 +80,13 @@ int rbpr_internal_allreduce_item_grads(rbpr_ctx* ctx, cudaStream_t st) {
 void rbpr_internal_comm_destroy(rbpr_ctx* ctx) {
   if (!ctx->comm) return;
   NcclApi* api = nccl_api(ctx);
-  if (api) api->comm_destroy((nccl_comm_t)ctx->comm);
+  // ncclCommAbort, not ncclCommDestroy: contexts die when Python collects them, at a different moment
+  // on every rank; a teardown that waits for the peers deadlocks against whatever collective the
+  // other rank has moved on to (seen with two experiments run back to back in one process group)
+  if (api) {
+    if (api->comm_abort) api->comm_abort((nccl_comm_t)ctx->comm);
+    else api->comm_destroy((nccl_comm_t)ctx->comm);
+  }
   ctx->comm = nullptr;
 }
 

@@ -208,6 +208,12 @@ class BPRExperiment:
             return
 
     def clean(self) -> None:
+        # native contexts first, at the same point of the program on every rank
+        eng = getattr(getattr(getattr(self, "_model", None), "logits_model", None), "_engine", None)
+        if eng is not None:
+            torch.cuda.synchronize()
+            eng.close()
+            self._model.logits_model._engine = None
         self._accelerator.free_memory()
         del self._accelerator, self.trainer
 

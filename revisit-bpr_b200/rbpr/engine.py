@@ -55,11 +55,15 @@ class Context:
             raise native.NativeError(f"rbpr_create failed ({rc}): needs a compute-capability 10.x device")
         self._alias = None
 
+    def close(self) -> None:
+        """Destroy the native context now (scratch, communicator, peer mappings); idempotent."""
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.rbpr_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
     def __del__(self) -> None:
         try:
-            if getattr(self, "ctx", None) is not None and self.ctx.value:
-                self.lib.rbpr_destroy(self.ctx)
-                self.ctx = C.c_void_p()
+            self.close()
         except Exception:
             pass
 

@@ -98,6 +98,8 @@ for mode, optimizer, lr in (("stock", "torch.optim.SGD", 0.05), ("fast", "torch.
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     code |= 0 if flag.item() == 1 else 1
+    exp.clean()
     del exp
+    dist.barrier()
 dist.destroy_process_group()
 sys.exit(code)
