@@ -289,7 +289,7 @@ sample_adaptive_padded(const AdaptiveParams p, const int64_t* __restrict__ users
 }  // namespace
 
 // CSR variant used by bpr_sample-style preparation (train.cu): records for one step (tp.batch >= n).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 rbpr_sample_adaptive_csr(const TrainParams tp, const float* fstd, const int32_t* order,
                          const int32_t* pos, double log1m_p, int4* __restrict__ records,
                          uint64_t n_slots, uint64_t step, int opt) {

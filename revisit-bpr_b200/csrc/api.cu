@@ -59,6 +59,8 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->stats);
   for (int b = 0; b < 2; ++b) {
     cudaFree(ctx->partials[b]);
+    cudaFree(ctx->mh_list[b]);
+    cudaFree(ctx->mh_count[b]);
     cudaFree(ctx->records[b]);
     if (ctx->ev_ready[b]) cudaEventDestroy(ctx->ev_ready[b]);
     if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);

@@ -49,6 +49,9 @@ struct rbpr_ctx {
   // per-wave scratch, double-buffered: wave w+1 is sorted/sampled on `aux` while wave w trains
   void* records[2] = {nullptr, nullptr};  // (records_cap) int4 {u, i+, i-, head}
   int64_t records_cap = 0;
+  int32_t* mh_list[2] = {nullptr, nullptr};   // (records_cap) per step: multi-occurrence users, compacted by the sampler
+  uint32_t* mh_count[2] = {nullptr, nullptr}; // (mh_steps_cap)
+  int64_t mh_steps_cap = 0;
   float* partials[2] = {nullptr, nullptr};  // per-warp step statistics (float4 each)
   int64_t partials_cap = 0;
   cudaStream_t aux = nullptr;            // preparation stream (counting + negative sampling)

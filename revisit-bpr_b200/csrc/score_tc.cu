@@ -40,8 +40,8 @@ constexpr int KBLK = 32;           // fp32 per 128-byte swizzle row = one K bloc
 constexpr int KB_MAX = 9;          // K blocks of the resident user panel (D + bias <= 288)
 constexpr int GROUP = 16;          // items per group maximum
 constexpr int NGT = TN / GROUP;    // group maxima per tile and user
-constexpr int CAND_CAP = 512;      // candidates per user the ranking kernel takes
-constexpr int LIST_CAP = 128;      // slots of one private candidate list (user, CTA segment, column half)
+constexpr int CAND_CAP = 1024;     // candidates per user the ranking kernel takes
+constexpr int LIST_CAP = 256;      // slots of one private candidate list (user, CTA segment, column half)
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, 64 of the tile's 128 columns each
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
 constexpr float kNever = -1e30f;   // score offset of item 0 / padding rows (exact in TF32)
@@ -53,6 +53,8 @@ struct TcParams {
   int n_utiles, n_itiles, KB, stages;
   int pass;          // 0: group maxima, 1: candidates
   int segs;          // CTA segments a user tile can be split into (private candidate lists)
+  int pair;          // 1: a unit is TWO user tiles x one item tile (every item K-block feeds two accumulators:
+                     //    half the L2 traffic of the item panel, which is what bounds the passes)
   const uint2* mask;       // (n_users, n_itiles, 2) 64 bits per (user, tile, column half): 1 = masked
   float* gmax;             // (n_users, n_itiles * NGT)
   const float* thr;        // (n_users)
@@ -177,8 +179,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                   // KB x 16 KiB: the user panel of the current user tile
-  uint8_t* sB = smem + (size_t)p.KB * kStageBytes;      // stages x 16 KiB: K blocks of item tiles
+  const int UT = 1 + p.pair;                            // user tiles per unit
+  uint8_t* sA = smem;                                   // UT x KB x 16 KiB: the user panel(s) of the current unit
+  uint8_t* sB = smem + (size_t)UT * p.KB * kStageBytes; // stages x 16 KiB: K blocks of item tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * kStageBytes);
   uint64_t* full = bars;                 // [stages]  TMA -> MMA
   uint64_t* empty = bars + p.stages;     // [stages]  MMA -> TMA
@@ -202,8 +205,8 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // 2 accumulator stages x 128 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+  if (warp == 1) {  // 2 accumulator stages x UT user tiles x 128 fp32 columns (all 512 allocated: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -211,7 +214,8 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long total = (long long)p.n_utiles * p.n_itiles;
+  const int n_uunits = (p.n_utiles + UT - 1) / UT;       // user tiles (or pairs of them)
+  const long long total = (long long)n_uunits * p.n_itiles;
   Work w;
   w.begin = total * blockIdx.x / gridDim.x;
   w.end = total * (blockIdx.x + 1) / gridDim.x;
@@ -227,8 +231,10 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         const int it1 = (int)((long long)(p.n_itiles - it0) < left ? p.n_itiles : it0 + left);
         ok = mbar_wait(a_free, (seg & 1u) ^ 1u, p.err);
         if (!ok) break;
-        mbar_expect_tx(a_full, (uint32_t)p.KB * kStageBytes);
-        for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + (size_t)kb * kStageBytes, &tmA, kb * KBLK, ut * TM, a_full);
+        mbar_expect_tx(a_full, (uint32_t)(UT * p.KB) * kStageBytes);
+        for (int h = 0; h < UT; ++h)
+          for (int kb = 0; kb < p.KB; ++kb)
+            tma_load_2d(sA + (size_t)(h * p.KB + kb) * kStageBytes, &tmA, kb * KBLK, (ut * UT + h) * TM, a_full);
         for (int it = it0; it < it1 && ok; ++it)
           for (int kb = 0; kb < p.KB; ++kb, ++q) {
             const uint32_t st = q % (uint32_t)p.stages, ph = (q / (uint32_t)p.stages) & 1u;
@@ -258,17 +264,19 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           ok = mbar_wait(t_empty + acc, aph ^ 1u, p.err);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t d = tmem_base + acc * (uint32_t)TN;
           for (int kb = 0; kb < p.KB; ++kb, ++q) {
             const uint32_t st = q % (uint32_t)p.stages, ph = (q / (uint32_t)p.stages) & 1u;
             ok = mbar_wait(full + st, ph, p.err);
             if (!ok) break;
             tc_fence_after();
-            const uint64_t ad = umma_desc(smem_u32(sA + (size_t)kb * kStageBytes));
             const uint64_t bd = umma_desc(smem_u32(sB + (size_t)st * kStageBytes));
+            for (int h = 0; h < UT; ++h) {  // the same item K-block against every resident user tile
+              const uint32_t d = tmem_base + (acc * (uint32_t)UT + (uint32_t)h) * (uint32_t)TN;
+              const uint64_t ad = umma_desc(smem_u32(sA + (size_t)(h * p.KB + kb) * kStageBytes));
 #pragma unroll
-            for (int k4 = 0; k4 < KBLK / 8; ++k4)  // UMMA K = 8 fp32 = 32 bytes inside the swizzled row
-              tc_mma_tf32(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), kIdesc, (kb | k4) != 0 ? 1u : 0u);
+              for (int k4 = 0; k4 < KBLK / 8; ++k4)  // UMMA K = 8 fp32 = 32 bytes inside the swizzled row
+                tc_mma_tf32(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), kIdesc, (kb | k4) != 0 ? 1u : 0u);
+            }
             tc_commit(empty + st);  // frees the stage when these MMAs have read it
           }
           if (ok) tc_commit(t_full + acc);
@@ -289,56 +297,82 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int ut = (int)(unit / p.n_itiles), it0 = (int)(unit % p.n_itiles);
       const long long left = w.end - unit;
       const int it1 = (int)((long long)(p.n_itiles - it0) < left ? p.n_itiles : it0 + left);
-      const int u = ut * TM + row;
-      const bool valid = u < p.n_users;
-      const float thr = (p.pass == 1 && valid) ? __ldg(p.thr + u) : 0.f;
-      // pass B: this thread's private candidate list for the segment (no atomics on the way)
       const int sg = (int)((long long)blockIdx.x - first_cta_of((long long)ut * p.n_itiles, total, gridDim.x));
-      const size_t list = ((size_t)u * p.segs + (size_t)sg) * 2 + (size_t)half;
-      int32_t* my_cand = p.cand + list * LIST_CAP;
-      int n_cand = 0;
-      const uint2* mrow = p.mask + ((size_t)u * p.n_itiles) * 2 + half;
-      uint2 mw_next = make_uint2(~0u, ~0u);
-      if (p.pass == 1 && valid) mw_next = __ldg(mrow + (size_t)it0 * 2);
-      for (int it = it0; it < it1 && ok; ++it, ++t) {
-        const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
-        const uint2 mw = mw_next;
-        if (p.pass == 1 && valid && it + 1 < it1) mw_next = __ldg(mrow + (size_t)(it + 1) * 2);  // one tile ahead
-        ok = mbar_wait(t_full + acc, aph, p.err);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)TN + (uint32_t)(half * 64);
-        uint32_t r0[32], r1[32];
-        tc_ld32(taddr, r0);
-        tc_ld32(taddr + 32u, r1);
-        tc_ld_wait();
-        // accumulator drained into registers: hand it back to the MMA warp before the arithmetic
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + acc);
-        if (p.pass == 0) {
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u * p.n_itiles * NGT + (size_t)it * NGT + half * 4);
-            *dst = make_float4(max16(r0), max16(r0 + 16), max16(r1), max16(r1 + 16));
-          }
-        } else {
-          uint32_t pm0 = ge_mask32(r0, thr) & ~mw.x, pm1 = ge_mask32(r1, thr) & ~mw.y;
-          const int base = it * TN + half * 64;
-          while (pm0 != 0u) {  // rare: ~1 % of the scores
-            const int j = __ffs(pm0) - 1;
-            pm0 &= pm0 - 1u;
-            if (n_cand < LIST_CAP) my_cand[n_cand] = base + j;
-            ++n_cand;
-          }
-          while (pm1 != 0u) {
-            const int j = __ffs(pm1) - 1;
-            pm1 &= pm1 - 1u;
-            if (n_cand < LIST_CAP) my_cand[n_cand] = base + 32 + j;
-            ++n_cand;
+      // per resident user tile: the row this thread owns, its threshold, its private candidate list
+      int u[2];
+      bool valid[2];
+      float thr[2] = {0.f, 0.f};
+      int n_cand[2] = {0, 0};
+      size_t list[2] = {0, 0};
+      uint2 mw_next[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        u[h] = (ut * UT + h) * TM + row;
+        valid[h] = h < UT && u[h] < p.n_users;
+        mw_next[h] = make_uint2(~0u, ~0u);
+        if (valid[h]) {
+          list[h] = ((size_t)u[h] * p.segs + (size_t)sg) * 2 + (size_t)half;
+          if (p.pass == 1) {
+            thr[h] = __ldg(p.thr + u[h]);
+            mw_next[h] = __ldg(p.mask + ((size_t)u[h] * p.n_itiles + it0) * 2 + half);
           }
         }
       }
-      if (p.pass == 1 && valid && ok) p.cnt[list] = n_cand;
+      for (int it = it0; it < it1 && ok; ++it, ++t) {
+        const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+        uint2 mw[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mw[h] = mw_next[h];
+          if (p.pass == 1 && valid[h] && it + 1 < it1)  // one tile ahead
+            mw_next[h] = __ldg(p.mask + ((size_t)u[h] * p.n_itiles + it + 1) * 2 + half);
+        }
+        ok = mbar_wait(t_full + acc, aph, p.err);
+        if (!ok) break;
+        tc_fence_after();
+        for (int h = 0; h < UT; ++h) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * (uint32_t)UT + (uint32_t)h) * (uint32_t)TN +
+                                 (uint32_t)(half * 64);
+          uint32_t r0[32], r1[32];
+          tc_ld32(taddr, r0);
+          tc_ld32(taddr + 32u, r1);
+          tc_ld_wait();
+          if (h == UT - 1) {  // both accumulators of the stage are in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + acc);
+          }
+          if (p.pass == 0) {
+            if (valid[h]) {
+              float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u[h] * p.n_itiles * NGT + (size_t)it * NGT + half * 4);
+              *dst = make_float4(max16(r0), max16(r0 + 16), max16(r1), max16(r1 + 16));
+            }
+          } else {
+            uint32_t pm0 = ge_mask32(r0, thr[h]) & ~mw[h].x, pm1 = ge_mask32(r1, thr[h]) & ~mw[h].y;
+            const int base = it * TN + half * 64;
+            int32_t* my_cand = p.cand + list[h] * LIST_CAP;
+            int n = n_cand[h];
+            while (pm0 != 0u) {  // rare: ~1 % of the scores
+              const int j = __ffs(pm0) - 1;
+              pm0 &= pm0 - 1u;
+              if (n < LIST_CAP) my_cand[n] = base + j;
+              ++n;
+            }
+            while (pm1 != 0u) {
+              const int j = __ffs(pm1) - 1;
+              pm1 &= pm1 - 1u;
+              if (n < LIST_CAP) my_cand[n] = base + 32 + j;
+              ++n;
+            }
+            n_cand[h] = n;
+          }
+        }
+      }
+      if (p.pass == 1 && ok) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (valid[h]) p.cnt[list[h]] = n_cand[h];
+      }
       unit += it1 - it0;
     }
   }
@@ -346,7 +380,7 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -468,6 +502,44 @@ select_threshold(const float* __restrict__ gmax, int G, int k, const int64_t* __
   }
 }
 
+// The same selection with one WARP per user and the keys in registers (G <= 32 * KPL): no block
+// barriers, 32 bisection rounds of KPL compares and one warp reduction.
+template <int KPL>
+__global__ void __launch_bounds__(128)
+select_threshold_warp(const float* __restrict__ gmax, int G, int k, int n_users, const int64_t* __restrict__ seen_indptr,
+                      int64_t row0, const float* __restrict__ unorm, const uint32_t* __restrict__ vmax_bits,
+                      float* __restrict__ thr) {
+  const int lane = threadIdx.x & 31;
+  const int u = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (u >= n_users) return;
+  const float* row = gmax + (size_t)u * G;
+  uint32_t key[KPL];
+#pragma unroll
+  for (int e = 0; e < KPL; ++e) {
+    const int i = lane + 32 * e;
+    key[e] = i < G ? fkey(__ldg(row + i)) : 0u;  // 0 is below every real key
+  }
+  int64_t n_seen = 0;
+  if (seen_indptr != nullptr) n_seen = seen_indptr[row0 + u + 1] - seen_indptr[row0 + u];
+  const int64_t want64 = (int64_t)k + n_seen;
+  if (want64 > (int64_t)G) {
+    if (lane == 0) thr[u] = -INFINITY;
+    return;
+  }
+  const int want = (int)want64;
+  uint32_t T = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < KPL; ++e) c += (key[e] >= cand);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= want) T = cand;
+  }
+  if (lane == 0) thr[u] = ikey(T) - 0.002f * unorm[u] * __uint_as_float(*vmax_bits);
+}
+
 // Exact fp32 scores of the candidates, ranking, outputs.  One CTA of 256 threads per user.
 constexpr int kRankThreads = 256;
 __global__ void __launch_bounds__(kRankThreads)
@@ -518,7 +590,20 @@ rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_
     const int32_t it = items[q];
     const float* v = item_emb + (int64_t)it * D;
     float acc = 0.f;  // k ascending fmaf chain: the arithmetic of score_gemm
-    for (int c = 0; c < D; c += 4) {
+    int c = 0;
+    for (; c + 32 <= D; c += 32) {  // 8 independent 128-bit loads in flight, then the sequential chain
+      float4 x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __ldg(reinterpret_cast<const float4*>(v + c) + e);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc = fmaf(s_u[c + 4 * e], x[e].x, acc);
+        acc = fmaf(s_u[c + 4 * e + 1], x[e].y, acc);
+        acc = fmaf(s_u[c + 4 * e + 2], x[e].z, acc);
+        acc = fmaf(s_u[c + 4 * e + 3], x[e].w, acc);
+      }
+    }
+    for (; c < D; c += 4) {
       const float4 x = *reinterpret_cast<const float4*>(v + c);
       acc = fmaf(s_u[c], x.x, acc);
       acc = fmaf(s_u[c + 1], x.y, acc);
@@ -594,14 +679,18 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   const int with_bias = ctx->item_bias ? 1 : 0;
   const int Kp = ((D + with_bias + 1 + KBLK - 1) / KBLK) * KBLK, KB = Kp / KBLK;  // + the "never" column
   const int n_utiles = (n_users + TM - 1) / TM, n_itiles = (I + TN - 1) / TN;
-  const int urows = n_utiles * TM, irows = n_itiles * TN;
+  // pair mode: two user tiles resident per CTA (2 x KB x 16 KiB) + >= 4 item stages must fit 227 KiB
+  const int pair = (n_utiles >= 2 && (size_t)(2 * KB + 4) * kStageBytes + 2048 <= 227 * 1024 && getenv("RBPR_TC_NO_PAIR") == nullptr) ? 1 : 0;
+  const int UT = 1 + pair;
+  const int n_uunits = (n_utiles + UT - 1) / UT;
+  const int urows = n_uunits * UT * TM, irows = n_itiles * TN;
   const int G = n_itiles * NGT;
-  // persistent grid: one CTA per SM, contiguous ranges of (user tile, item tile) units; a user tile
-  // split over several CTAs gets one private candidate list per CTA segment
-  const long long units = (long long)n_utiles * n_itiles;
+  // persistent grid: one CTA per SM, contiguous ranges of (user tile [pair], item tile) units; a user
+  // tile split over several CTAs gets one private candidate list per CTA segment
+  const long long units = (long long)n_uunits * n_itiles;
   const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
   int segs = 1;
-  for (int ut = 0; ut < n_utiles; ++ut) {
+  for (int ut = 0; ut < n_uunits; ++ut) {
     const long long a = first_cta_of((long long)ut * n_itiles, units, grid);
     const long long b = first_cta_of((long long)(ut + 1) * n_itiles - 1, units, grid);
     if ((int)(b - a + 1) > segs) segs = (int)(b - a + 1);
@@ -644,10 +733,10 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   if (rc) return rc;
   rc = make_panel_map(ctx, &tmB, ctx->tc_items, irows, Kp);
   if (rc) return rc;
-  int stages = (int)((200 * 1024 - (size_t)KB * kStageBytes) / kStageBytes);
+  int stages = (int)((225 * 1024 - (size_t)UT * KB * kStageBytes) / kStageBytes);
   if (stages > 8) stages = 8;
   if (stages < 2) RBPR_FAIL(ctx, RBPR_ERR_ARG, "score_tc: dim too large for the tensor path");
-  const size_t smem = (size_t)(KB + stages) * kStageBytes + (2 * stages + 6) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)(UT * KB + stages) * kStageBytes + (2 * stages + 6) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     RBPR_CUDA(ctx, cudaFuncSetAttribute(score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -663,6 +752,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   p.KB = KB;
   p.stages = stages;
   p.segs = segs;
+  p.pair = pair;
   p.mask = (const uint2*)ctx->tc_mask;
   p.gmax = ctx->tc_gmax;
   p.thr = thr;
@@ -672,8 +762,12 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   p.pass = 0;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   const int k = tp_in.k_max < I ? tp_in.k_max : I;
-  select_threshold<<<n_users, kSelThreads, (size_t)G * sizeof(uint32_t), st>>>(ctx->tc_gmax, G, k, seen_indptr, row0, unorm,
-                                                                                vmax_bits, thr);
+  if (G <= 32 * 48)
+    select_threshold_warp<48><<<(n_users * 32 + 127) / 128, 128, 0, st>>>(ctx->tc_gmax, G, k, n_users, seen_indptr, row0, unorm,
+                                                                          vmax_bits, thr);
+  else
+    select_threshold<<<n_users, kSelThreads, (size_t)G * sizeof(uint32_t), st>>>(ctx->tc_gmax, G, k, seen_indptr, row0, unorm,
+                                                                                  vmax_bits, thr);
   p.pass = 1;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   TopkParams tp = tp_in;

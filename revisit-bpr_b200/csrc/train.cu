@@ -272,7 +272,20 @@ int ensure_step_scratch(rbpr_ctx* ctx, int64_t n, int64_t steps, int stride) {
     }
     ctx->records_cap = 0;
     for (int b = 0; b < 2; ++b) RBPR_CUDA(ctx, cudaMalloc(&ctx->records[b], (size_t)n * 16));
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(ctx->mh_list[b]);
+      ctx->mh_list[b] = nullptr;
+      RBPR_CUDA(ctx, cudaMalloc(&ctx->mh_list[b], (size_t)n * sizeof(int32_t)));
+    }
     ctx->records_cap = n;
+  }
+  if (steps > ctx->mh_steps_cap) {
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(ctx->mh_count[b]);
+      ctx->mh_count[b] = nullptr;
+      RBPR_CUDA(ctx, cudaMalloc(&ctx->mh_count[b], (size_t)steps * sizeof(uint32_t)));
+    }
+    ctx->mh_steps_cap = steps;
   }
   const int64_t need = steps * stride;
   if (need > ctx->partials_cap) {
@@ -333,9 +346,12 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
 // partials/n_partials/stats_out: phase A's per-warp statistics of the step, summed by block 0.
 int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
               const int4* records, int n, cudaStream_t st, const float4* partials = nullptr,
-              int n_partials = 0, double* stats_out = nullptr) {
+              int n_partials = 0, double* stats_out = nullptr, const int32_t* mh_list = nullptr,
+              const uint32_t* mh_count = nullptr) {
   ApplyParams a;
   memset(&a, 0, sizeof(a));
+  a.mh_list = mh_list;
+  a.mh_count = mh_count;
   a.do_items = do_items;
   a.do_users = (records != nullptr && n > 0) ? 1 : 0;
   a.partials = partials;
@@ -672,6 +688,11 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
         if (r) return r;
       }
     } else {
+      if (!small) {  // bpr_apply's user half reads a compact list instead of scanning the records
+        RBPR_CUDA(ctx, cudaMemsetAsync(ctx->mh_count[b], 0, (size_t)wave_steps(w) * sizeof(uint32_t), prep_st));
+        q.mh_list = ctx->mh_list[b];
+        q.mh_count = ctx->mh_count[b];
+      }
       r = run_sample(ctx, q, ctx->records[b], nw, step0 + (uint64_t)wave_step0(w), prep_st);
       if (r) return r;
     }
@@ -716,6 +737,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
         p.xwait_epoch = ctx->fx_wait_epoch;
       }
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
+      const int32_t* mh_l = adaptive ? nullptr : ctx->mh_list[b] + soff;
+      const uint32_t* mh_c = adaptive ? nullptr : ctx->mh_count[b] + s;
       float4* parts = reinterpret_cast<float4*>(ctx->partials[b]) + s * stride;
       int nb = 0;
       {
@@ -731,7 +754,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
         RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_phase_a, st));
         RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2, ctx->ev_phase_a, 0));
         rc = run_apply(ctx, p.step, hp, 0, 0, recs, p.n, ctx->aux2, parts, nb * (kPhaseAThreads / 32),
-                       step_stats);
+                       step_stats, mh_l, mh_c);
         if (rc) return rc;
         RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_users, ctx->aux2));
         NvtxRange nvtx_x("rbpr.exchange (reduce + item update across ranks)");
@@ -740,7 +763,7 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
         RBPR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_users, 0));
       } else {
         NvtxRange nvtx_b("rbpr.apply");
-        rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32), step_stats);
+        rc = run_apply(ctx, p.step, hp, 0, 1, recs, p.n, st, parts, nb * (kPhaseAThreads / 32), step_stats, mh_l, mh_c);
         if (rc) return rc;
       }
     }

@@ -30,6 +30,8 @@ struct TrainParams {
   const int64_t* __restrict__ triple_idx;  // the wave's triple ids, input order
   const uint32_t* __restrict__ cnt;        // (steps in wave, U) occurrences of each user per step
   uint32_t* __restrict__ icnt;             // (steps in wave, I) item occurrences per step, or null (small-batch path only)
+  int32_t* __restrict__ mh_list;           // (wave triples) per step: users flagged kRecMultiHead, compacted; or null
+  uint32_t* __restrict__ mh_count;         // (steps in wave) entries of each step's list
   const uint32_t* __restrict__ ord;        // arrival rank of each slot among its user's slots
   int64_t batch;                           // triples per step
   int64_t U;
@@ -101,6 +103,8 @@ struct ApplyParams {
   int do_items, do_users;
   const int4* __restrict__ records;
   int n;
+  const int32_t* __restrict__ mh_list;   // the step's multi-occurrence users (from the sampler), or null: scan records
+  const uint32_t* __restrict__ mh_count;
   float* __restrict__ user_emb;
   float* __restrict__ user_grad;
   float* __restrict__ user_m;
@@ -392,6 +396,8 @@ static __global__ void __launch_bounds__(256) bpr_sample(TrainParams p, int4* __
       if (j > 0 && (uint32_t)j < p.I && atomicAdd(row + j, 1u) == 0u) fl |= kRecApplyNeg;
     }
     if (records != nullptr) records[k] = make_int4(uu, i, j, fl);
+    if (p.mh_list != nullptr && (fl & kRecMultiHead) != 0 && uu != 0)  // compact list for bpr_apply's user half
+      p.mh_list[sl * (uint64_t)p.batch + atomicAdd(p.mh_count + sl, 1u)] = uu;
     if (p.neg_out != nullptr) p.neg_out[k] = (int64_t)j;
   }
 }
@@ -595,60 +601,50 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
     h.bc2_sqrt = t.y;
   }
   if (p.do_users) {
-    // Warp-coalesced scan of the step's records (32 records = 512 B per warp and round trip; only the
-    // few flagged kRecMultiHead carry work), then the flagged ones are dealt to the warp's lane groups.
-    constexpr int GPW = 32 / LANES;  // lane groups per warp
-    const int lane = threadIdx.x & 31;
-    const int gsub = lane / LANES;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (int64_t base = wid * 32; base < p.n; base += warps * 32) {
-      const int64_t k = base + lane;
-      const int4 rec = (k < p.n) ? __ldg(p.records + k) : make_int4(0, 0, 0, 0);
-      unsigned bal = __ballot_sync(0xffffffffu, (rec.w & kRecMultiHead) != 0 && rec.x != 0);
-      while (bal != 0u) {
-        unsigned m = bal;
-        int src = -1;
-        for (int q = 0; q <= gsub && m != 0u; ++q) {  // the gsub-th of the lowest GPW flagged records
-          src = (q == gsub) ? (__ffs(m) - 1) : -1;
-          m &= m - 1u;
-        }
+    // One lane group finishes one multi-occurrence user: its summed gradient sits in user_grad.
+    auto finish_user = [&](int64_t r) {
+      float* grow = p.user_grad + r * D;
+      float* prow = p.user_emb + r * D;
+      int64_t last = 0;
+      if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
+      const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
+      const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
 #pragma unroll
-        for (int q = 0; q < GPW; ++q) bal &= bal - 1u;  // (x & (x-1) of 0 stays 0)
-        const int64_t r = (int64_t)__shfl_sync(0xffffffffu, rec.x, src < 0 ? 0 : src);
-        if (src < 0) continue;
-        float* grow = p.user_grad + r * D;
-        float* prow = p.user_emb + r * D;
-        int64_t last = 0;
-        if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
-        const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
-        const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c = 4 * (g.gl + LANES * v);
-          if (c >= D) continue;
-          const float4 gr = ld4(grow + c);
-          float4 pp = ld4(prow + c);
-          if (OPT == RBPR_OPT_SGD) {
-            pp.x -= p.lr * gr.x;
-            pp.y -= p.lr * gr.y;
-            pp.z -= p.lr * gr.z;
-            pp.w -= p.lr * gr.w;
-          } else {
-            float4 m4 = ld4(p.user_m + r * D + c);
-            float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
-            if (behind) cu.apply(pp, m4, vv);
-            opt4<OPT>(pp, m4, vv, gr, h);
-            st4(p.user_m + r * D + c, m4);
-            if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
-          }
-          st4(prow + c, pp);
-          st4(grow + c, f4zero());
+      for (int v = 0; v < NV; ++v) {
+        const int c = 4 * (g.gl + LANES * v);
+        if (c >= D) continue;
+        const float4 gr = ld4(grow + c);
+        float4 pp = ld4(prow + c);
+        if (OPT == RBPR_OPT_SGD) {
+          pp.x -= p.lr * gr.x;
+          pp.y -= p.lr * gr.y;
+          pp.z -= p.lr * gr.z;
+          pp.w -= p.lr * gr.w;
+        } else {
+          float4 m = ld4(p.user_m + r * D + c);
+          float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
+          if (behind) cu.apply(pp, m, vv);
+          opt4<OPT>(pp, m, vv, gr, h);
+          st4(p.user_m + r * D + c, m);
+          if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
         }
-        if (OPT != RBPR_OPT_SGD) {
-          __syncwarp(g.mask);
-          if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
-        }
+        st4(prow + c, pp);
+        st4(grow + c, f4zero());
+      }
+      if (OPT != RBPR_OPT_SGD) {
+        __syncwarp(g.mask);
+        if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
+      }
+    };
+    if (p.mh_list != nullptr) {
+      // the sampler compacted the step's multi-occurrence users: no scan, one round trip per user
+      const int64_t n_mh = (int64_t)__ldg(p.mh_count);
+      for (int64_t e = gid; e < n_mh; e += groups) finish_user((int64_t)__ldg(p.mh_list + e));
+    } else {
+      for (int64_t k = gid; k < p.n; k += groups) {
+        const int4 rec = __ldg(p.records + k);
+        if ((rec.w & kRecMultiHead) == 0 || rec.x == 0) continue;
+        finish_user((int64_t)rec.x);
       }
     }
   }

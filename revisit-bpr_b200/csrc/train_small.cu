@@ -30,8 +30,9 @@ using namespace rbpr_dev;
 
 namespace {
 
-constexpr int kSmallThreads = 512;
-constexpr int kSmallCluster = 8;
+// 4096 threads either as 8 CTAs x 512 (portable cluster size) or 16 CTAs x 256 (non-portable: two warps
+// per scheduler instead of four, the same chain of round trips with half the issue contention)
+constexpr int kSmallTotalThreads = 4096;
 
 struct SmallParams {
   TrainParams t;        // tables, accumulators, hyper-parameters (t.batch = triples per step)
@@ -53,7 +54,7 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
-template <int LANES, int NV>
+template <int LANES, int NV, int kSmallThreads>
 __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallParams sp) {
   const TrainParams& p = sp.t;
   const Group<LANES> g;
@@ -272,9 +273,34 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bpr_small_steps(const SmallP
 bool rbpr_small_batch_eligible(const rbpr_ctx* ctx, int64_t batch) {
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  const int64_t groups = (int64_t)kSmallCluster * kSmallThreads / lanes;
+  const int64_t groups = (int64_t)kSmallTotalThreads / lanes;
   return batch <= 4 * groups;
 }
+
+namespace {
+template <int L, int V, int T>
+int launch_small(rbpr_ctx* ctx, const SmallParams& sp, int cluster, cudaStream_t st) {
+  static bool allowed = false;
+  if (cluster > 8 && !allowed) {
+    RBPR_CUDA(ctx, cudaFuncSetAttribute(bpr_small_steps<L, V, T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    allowed = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster);
+  cfg.blockDim = dim3(T);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RBPR_CUDA(ctx, cudaLaunchKernelEx(&cfg, bpr_small_steps<L, V, T>, sp));
+  return 0;
+}
+}  // namespace
 
 // `n_steps` consecutive steps over prepared records in one cluster launch on stream st.
 int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* records, int64_t n,
@@ -291,24 +317,18 @@ int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* rec
     RBPR_CUDA(ctx, cudaMemsetAsync(stats, 0, (size_t)n_steps * RBPR_STATS_PER_STEP * sizeof(double), st));
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(kSmallCluster);
-  cfg.blockDim = dim3(kSmallThreads);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kSmallCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define X(L, V)                                                                   \
-  if (lanes == L && nv == V) {                                                    \
-    RBPR_CUDA(ctx, cudaLaunchKernelEx(&cfg, bpr_small_steps<L, V>, sp));          \
-    ctx->launches++;                                                              \
-    ctx->small_launches++;                                                        \
-    return 0;                                                                     \
+  static int cluster = 0;
+  if (cluster == 0) {
+    const char* e = getenv("RBPR_SMALL_CLUSTER");
+    cluster = (e && atoi(e) == 16) ? 16 : 8;
+  }
+#define X(L, V)                                                                              \
+  if (lanes == L && nv == V) {                                                               \
+    int rc = cluster == 16 ? launch_small<L, V, 256>(ctx, sp, 16, st) : launch_small<L, V, 512>(ctx, sp, 8, st); \
+    if (rc) return rc;                                                                       \
+    ctx->launches++;                                                                         \
+    ctx->small_launches++;                                                                   \
+    return 0;                                                                                \
   }
   RBPR_FOR_EACH_GEOMETRY(X)
 #undef X

@@ -43,6 +43,7 @@ def _run(eng, users, seen, held, ks, monkeypatch, tensor):
 
 
 @pytest.mark.parametrize("U,I,D,bias,popular", [(900, 9000, 128, False, False), (800, 12345, 128, True, True),
+                                                 (600, 8700, 128, False, False),  # odd number of user tiles in pair mode
                                                  (500, 8300, 64, True, False), (400, 8200, 20, False, False),
                                                  (300, 9100, 256, True, False)])
 def test_tensor_path_equals_dense_path_bit_for_bit(U, I, D, bias, popular, monkeypatch):
