@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--ref-sample", type=int, default=512,
                     help="reference arm: triples of each batch the CPU step actually processes (bounded sample)")
-    ap.add_argument("--e2e-steps-per-call", type=int, default=30,
+    ap.add_argument("--e2e-steps-per-call", type=int, default=60,
                     help="steps handed to one host-buffer API call in the e2e leg")
     ap.add_argument("--leg", default=None, help=argparse.SUPPRESS)  # internal: cpu legs run as a child process
     return ap.parse_args()

@@ -83,6 +83,14 @@ __device__ __forceinline__ void topk_emit_outputs(const TopkParams& p, int64_t u
     __syncthreads();
     n_pos = s_npos;
   }
+  // the user's held-out row in shared memory when it is short (the usual case): every ranked item then
+  // checks its hit with a scan of shared memory instead of a chain of dependent global loads
+  __shared__ int32_t s_held[KCAP];
+  __shared__ float s_wtot[4][4];  // [array][warp] totals of the block scan below
+  const bool held_small = p.target == nullptr && n_pos <= KCAP;
+  if (held_small && tid < n_pos) s_held[tid] = p.held_indices[hlo + tid];
+  __syncthreads();
+  float v_disc = 0.f, v_hit = 0.f, v_dl = 0.f, v_hl = 0.f;
   if (tid < KCAP) {
     if (tid < k) {
       const unsigned long long c = sel[tid];
@@ -91,6 +99,8 @@ __device__ __forceinline__ void topk_emit_outputs(const TopkParams& p, int64_t u
       if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = ikey((uint32_t)(c >> 32));
       if (p.target != nullptr) {
         hit = (p.target[orow * p.target_ld + item] == 1.0f) ? 1.f : 0.f;
+      } else if (held_small) {
+        for (int q = 0; q < n_pos; ++q) hit = (s_held[q] == item) ? 1.f : hit;
       } else {
         int64_t lo = hlo, hi = hhi;
         while (lo < hi) {
@@ -104,35 +114,48 @@ __device__ __forceinline__ void topk_emit_outputs(const TopkParams& p, int64_t u
       if (p.topk_items) p.topk_items[orow * p.k_max + tid] = -1;
       if (p.topk_scores) p.topk_scores[orow * p.k_max + tid] = kMasked;
     }
-    const float disc = p.linear_gain ? 1.0f / ((float)tid + 1.0f) : 1.0f / log2f((float)tid + 2.0f);
-    disc_scan[tid] = disc;
-    hit_scan[tid] = hit * disc;
-    if (p.ndcg_linear_out != nullptr) {
-      const float dl = 1.0f / ((float)tid + 1.0f);
-      disc_lin[tid] = dl;
-      hit_lin[tid] = hit * dl;
-    }
+    v_disc = p.linear_gain ? 1.0f / ((float)tid + 1.0f) : 1.0f / log2f((float)tid + 2.0f);
+    v_hit = hit * v_disc;
+    v_dl = 1.0f / ((float)tid + 1.0f);
+    v_hl = hit * v_dl;
   }
-  __syncthreads();
-  // sequential prefix sums in rank order (fp32, like a left-to-right sum) by two threads
-  if (tid == 0) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += disc_scan[r]; disc_scan[r] = s; }
-  } else if (tid == 32) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += hit_scan[r]; hit_scan[r] = s; }
-  } else if (tid == 64 && p.ndcg_linear_out != nullptr) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += disc_lin[r]; disc_lin[r] = s; }
-  } else if (tid == 96 && p.ndcg_linear_out != nullptr) {
-    float s = 0.f;
-    for (int r = 0; r < KCAP; ++r) { s += hit_lin[r]; hit_lin[r] = s; }
-  }
-  // hit counts: reuse ballots
-  
+  // inclusive prefix sums in rank order over the KCAP = 128 ranks: a shuffle scan inside each of the
+  // four warps, then the totals of the warps before (fp32; both scoring paths share this code, so
+  // they agree bit for bit; against the reference's torch.sum the order differs by ~1e-7 relative)
   {
+    const int lane = tid & 31, wrp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float a0 = __shfl_up_sync(0xffffffffu, v_disc, o), a1 = __shfl_up_sync(0xffffffffu, v_hit, o);
+      const float a2 = __shfl_up_sync(0xffffffffu, v_dl, o), a3 = __shfl_up_sync(0xffffffffu, v_hl, o);
+      if (lane >= o) {
+        v_disc += a0;
+        v_hit += a1;
+        v_dl += a2;
+        v_hl += a3;
+      }
+    }
+    if (tid < KCAP && lane == 31) {
+      s_wtot[0][wrp] = v_disc;
+      s_wtot[1][wrp] = v_hit;
+      s_wtot[2][wrp] = v_dl;
+      s_wtot[3][wrp] = v_hl;
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, hit > 0.f);
-    if (tid < KCAP && (tid & 31) == 0) hitbits[tid >> 5] = bal;
+    if (tid < KCAP && lane == 0) hitbits[wrp] = bal;
+    __syncthreads();
+    if (tid < KCAP) {
+      for (int q = 0; q < wrp; ++q) {
+        v_disc += s_wtot[0][q];
+        v_hit += s_wtot[1][q];
+        v_dl += s_wtot[2][q];
+        v_hl += s_wtot[3][q];
+      }
+      disc_scan[tid] = v_disc;
+      hit_scan[tid] = v_hit;
+      disc_lin[tid] = v_dl;
+      hit_lin[tid] = v_hl;
+    }
   }
   __syncthreads();
   if (tid < p.n_ks) {

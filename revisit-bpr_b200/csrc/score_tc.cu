@@ -11,10 +11,13 @@
 //             tile overlaps the MMAs of the next).  The epilogue — 8 warps, one thread per (user row,
 //             half of the tile's columns), straight from TMEM — keeps only the MAX of every 16
 //             consecutive items.  Item 0 and the rows padding the catalogue to a multiple of 128 carry
-//             -1e30 in an extra K column, so they never are a maximum; seen items are NOT masked here;
+//             -1e30 in an extra K column, so they never are a maximum; seen items are NOT masked here
+//             (a per-element select would triple the epilogue), except for the few users with more
+//             than 64 seen items;
 //   select    tau~ = the (k + n_seen)-th largest group maximum of the user: the group maxima above
 //             it are k + n_seen distinct items, at most n_seen of them seen, so at least k unseen items
-//             score tau~ or more — a lower bound of the k-th largest unseen score;
+//             score tau~ or more — a lower bound of the k-th largest unseen score (users with masked
+//             maxima: simply the k-th largest);
 //   pass B    the same contraction again (cheaper than storing 200 M scores); the epilogue emits the
 //             items with S~ >= tau~ - 2 eps.  The panels hold operands ROUNDED to TF32 (cvt.rna, so the
 //             tensor core's own fp32->tf32 handling is exact): every product is off by at most
@@ -58,6 +61,7 @@ struct TcParams {
   const uint2* mask;       // (n_users, n_itiles, 2) 64 bits per (user, tile, column half): 1 = masked
   float* gmax;             // (n_users, n_itiles * NGT)
   const float* thr;        // (n_users)
+  const uint8_t* heavy;    // (n_users) 1: many seen items -> this user's group maxima are taken over UNSEEN items only
   int32_t* cnt;            // (n_users, segs, 2) candidates in each private list (> LIST_CAP: overflow)
   int32_t* cand;           // (n_users, segs, 2, LIST_CAP)
   int32_t* err;
@@ -161,6 +165,12 @@ __device__ __forceinline__ float max16(const uint32_t* r) {  // tree: independen
   float e = fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), f = fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11]));
   float g = fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), h = fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15]));
   return fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), fmaxf(fmaxf(e, f), fmaxf(g, h)));
+}
+__device__ __forceinline__ float max16_masked(const uint32_t* r, uint32_t bits) {  // bit j set: column j is masked
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m = fmaxf(m, ((bits >> j) & 1u) ? -INFINITY : __uint_as_float(r[j]));
+  return m;
 }
 __device__ __forceinline__ uint32_t ge_mask32(const uint32_t* r, float thr) {  // bit j = r[j] >= thr
   uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;  // four independent chains
@@ -300,7 +310,7 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int sg = (int)((long long)blockIdx.x - first_cta_of((long long)ut * p.n_itiles, total, gridDim.x));
       // per resident user tile: the row this thread owns, its threshold, its private candidate list
       int u[2];
-      bool valid[2];
+      bool valid[2], need_mask[2];
       float thr[2] = {0.f, 0.f};
       int n_cand[2] = {0, 0};
       size_t list[2] = {0, 0};
@@ -310,12 +320,12 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         u[h] = (ut * UT + h) * TM + row;
         valid[h] = h < UT && u[h] < p.n_users;
         mw_next[h] = make_uint2(~0u, ~0u);
+        need_mask[h] = false;
         if (valid[h]) {
           list[h] = ((size_t)u[h] * p.segs + (size_t)sg) * 2 + (size_t)half;
-          if (p.pass == 1) {
-            thr[h] = __ldg(p.thr + u[h]);
-            mw_next[h] = __ldg(p.mask + ((size_t)u[h] * p.n_itiles + it0) * 2 + half);
-          }
+          if (p.pass == 1) thr[h] = __ldg(p.thr + u[h]);
+          need_mask[h] = p.pass == 1 || __ldg(p.heavy + u[h]) != 0;
+          if (need_mask[h]) mw_next[h] = __ldg(p.mask + ((size_t)u[h] * p.n_itiles + it0) * 2 + half);
         }
       }
       for (int it = it0; it < it1 && ok; ++it, ++t) {
@@ -324,7 +334,7 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mw[h] = mw_next[h];
-          if (p.pass == 1 && valid[h] && it + 1 < it1)  // one tile ahead
+          if (need_mask[h] && it + 1 < it1)  // one tile ahead
             mw_next[h] = __ldg(p.mask + ((size_t)u[h] * p.n_itiles + it + 1) * 2 + half);
         }
         ok = mbar_wait(t_full + acc, aph, p.err);
@@ -345,7 +355,11 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           if (p.pass == 0) {
             if (valid[h]) {
               float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u[h] * p.n_itiles * NGT + (size_t)it * NGT + half * 4);
-              *dst = make_float4(max16(r0), max16(r0 + 16), max16(r1), max16(r1 + 16));
+              if (need_mask[h])  // heavy user: maxima over unseen items only (the selection then asks for rank k)
+                *dst = make_float4(max16_masked(r0, mw[h].x), max16_masked(r0 + 16, mw[h].x >> 16),
+                                   max16_masked(r1, mw[h].y), max16_masked(r1 + 16, mw[h].y >> 16));
+              else
+                *dst = make_float4(max16(r0), max16(r0 + 16), max16(r1), max16(r1 + 16));
             }
           } else {
             uint32_t pm0 = ge_mask32(r0, thr[h]) & ~mw[h].x, pm1 = ge_mask32(r1, thr[h]) & ~mw[h].y;
@@ -441,11 +455,15 @@ __global__ void pack_users(const float* __restrict__ user_emb, const int64_t* __
 }
 
 // 128 bits per (user, item tile): item 0, the user's seen items and columns >= I are masked (pass B).
+constexpr int kHeavySeen = 64;  // users with more seen items take masked group maxima (pass A)
 __global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
-                           int64_t row0, int n_users, int I, int n_itiles, uint32_t* __restrict__ mask) {
+                           int64_t row0, int n_users, int I, int n_itiles, uint32_t* __restrict__ mask,
+                           uint8_t* __restrict__ heavy) {
   const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n_users) return;
+  if (lane == 0)
+    heavy[r] = (seen_indptr != nullptr && seen_indptr[row0 + r + 1] - seen_indptr[row0 + r] > kHeavySeen) ? 1 : 0;
   uint32_t* m = mask + (size_t)r * n_itiles * 4;
   if (lane == 0) atomicOr(m, 1u);
   for (int c = I + lane; c < n_itiles * TN; c += 32) atomicOr(m + (c >> 5), 1u << (c & 31));
@@ -464,14 +482,16 @@ __global__ void build_mask(const int64_t* __restrict__ seen_indptr, const int32_
 constexpr int kSelThreads = 128;
 __global__ void __launch_bounds__(kSelThreads)
 select_threshold(const float* __restrict__ gmax, int G, int k, const int64_t* __restrict__ seen_indptr, int64_t row0,
-                 const float* __restrict__ unorm, const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
+                 const uint8_t* __restrict__ heavy, const float* __restrict__ unorm, const uint32_t* __restrict__ vmax_bits,
+                 float* __restrict__ thr) {
   extern __shared__ uint32_t keys[];  // G
   __shared__ int warp_cnt[kSelThreads / 32];
   const int tid = threadIdx.x;
   const float* row = gmax + (size_t)blockIdx.x * G;
   for (int i = tid; i < G; i += kSelThreads) keys[i] = fkey(row[i]);
   int64_t n_seen = 0;
-  if (seen_indptr != nullptr) n_seen = seen_indptr[row0 + blockIdx.x + 1] - seen_indptr[row0 + blockIdx.x];
+  if (seen_indptr != nullptr && heavy[blockIdx.x] == 0)  // heavy users' maxima already exclude their seen items
+    n_seen = seen_indptr[row0 + blockIdx.x + 1] - seen_indptr[row0 + blockIdx.x];
   const int64_t want64 = (int64_t)k + n_seen;
   __syncthreads();
   if (want64 > (int64_t)G) {  // not enough groups to bound the k-th unseen score: everything is a candidate
@@ -507,8 +527,8 @@ select_threshold(const float* __restrict__ gmax, int G, int k, const int64_t* __
 template <int KPL>
 __global__ void __launch_bounds__(128)
 select_threshold_warp(const float* __restrict__ gmax, int G, int k, int n_users, const int64_t* __restrict__ seen_indptr,
-                      int64_t row0, const float* __restrict__ unorm, const uint32_t* __restrict__ vmax_bits,
-                      float* __restrict__ thr) {
+                      int64_t row0, const uint8_t* __restrict__ heavy, const float* __restrict__ unorm,
+                      const uint32_t* __restrict__ vmax_bits, float* __restrict__ thr) {
   const int lane = threadIdx.x & 31;
   const int u = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (u >= n_users) return;
@@ -520,7 +540,7 @@ select_threshold_warp(const float* __restrict__ gmax, int G, int k, int n_users,
     key[e] = i < G ? fkey(__ldg(row + i)) : 0u;  // 0 is below every real key
   }
   int64_t n_seen = 0;
-  if (seen_indptr != nullptr) n_seen = seen_indptr[row0 + u + 1] - seen_indptr[row0 + u];
+  if (seen_indptr != nullptr && heavy[u] == 0) n_seen = seen_indptr[row0 + u + 1] - seen_indptr[row0 + u];
   const int64_t want64 = (int64_t)k + n_seen;
   if (want64 > (int64_t)G) {
     if (lane == 0) thr[u] = -INFINITY;
@@ -614,12 +634,49 @@ rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_
     key_in[q] = ((unsigned long long)fkey(acc) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)it);
   }
   __syncthreads();
-  // rank by counting (keys are distinct: the item id is part of the key): no sorting network, one pass
-  for (int q = tid; q < n; q += kRankThreads) {
-    const unsigned long long mine = key_in[q];
-    int r = 0;
-    for (int j = 0; j < n; ++j) r += (key_in[j] > mine);  // same address across the warp: broadcast
-    if (r < KCAP) sel[r] = mine;
+  // Ranks (keys are distinct: the item id is part of the key).  Up to 256 candidates (the usual case):
+  // every warp sorts its 32 keys in registers (bitonic network over shuffles), publishes them, and a
+  // key's rank is its place in its own warp plus, for every other warp, the number of larger keys
+  // there (5-step binary search in that warp's sorted list): ~250 instructions per thread instead of
+  // an n-step counting loop.  Above 256 candidates: counting.
+  if (n <= kRankThreads) {
+    __shared__ unsigned long long sorted[kRankThreads];
+    const int lane = tid & 31, wrp = tid >> 5;
+    unsigned long long mine = tid < n ? key_in[tid] : 0ull;  // 0 sorts last
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, stride);
+        const bool upper = (lane & stride) != 0;          // holds the second element of the pair
+        const bool desc = (lane & size) == 0;             // this sub-sequence sorts descending
+        const bool take_max = (upper != desc);            // first element of a descending pair keeps the larger key
+        const unsigned long long hi = mine > other ? mine : other, lo = mine > other ? other : mine;
+        mine = take_max ? hi : lo;
+      }
+    }
+    // (lane & 32) == 0 for every lane, so the last merge sorted all 32 keys descending
+    sorted[tid] = mine;
+    __syncthreads();
+    int r = lane;
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+      if (w == wrp) continue;
+      const unsigned long long* lst = sorted + w * 32;
+      int lo = 0, hi = 32;  // first position whose key is <= mine == number of keys > mine
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lst[mid] > mine) lo = mid + 1; else hi = mid;
+      }
+      r += lo;
+    }
+    if (mine != 0ull && r < KCAP) sel[r] = mine;
+  } else {
+    for (int q = tid; q < n; q += kRankThreads) {
+      const unsigned long long mine = key_in[q];
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += (key_in[j] > mine);  // same address across the warp: broadcast
+      if (r < KCAP) sel[r] = mine;
+    }
   }
   __syncthreads();
   topk_emit_outputs(p, urow, sel, min(min(p.k_max, p.I), n));
@@ -708,7 +765,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   rc = grow(ctx, (void**)&ctx->tc_cand, &ctx->tc_cand_bytes, n_lists * LIST_CAP * sizeof(int32_t));
   if (rc) return rc;
   // small arrays in one allocation: thr | unorm | overflow rows | {overflow count, vmax} | list counts
-  const size_t small = (size_t)n_users * 3 * sizeof(float) + 256 + n_lists * sizeof(int32_t);
+  const size_t small = (size_t)n_users * 3 * sizeof(float) + 256 + n_lists * sizeof(int32_t) + (size_t)n_users + 16;
   rc = grow(ctx, (void**)&ctx->tc_small, &ctx->tc_small_bytes, small);
   if (rc) return rc;
   float* thr = (float*)ctx->tc_small;
@@ -717,6 +774,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   int32_t* ovf_count = ovf_rows + n_users;
   uint32_t* vmax_bits = (uint32_t*)(ovf_count + 1);
   int32_t* cnt = ovf_count + 64;
+  uint8_t* heavy = (uint8_t*)(cnt + n_lists);
   ctx->tc_overflow_rows = ovf_rows;
 
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->tc_mask, 0, (size_t)n_users * n_itiles * 16, st));
@@ -726,7 +784,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   pack_users<<<(unsigned)(((int64_t)urows * 32 + 255) / 256), 256, 0, st>>>(ctx->user_emb, users, n_users, D, Kp, urows,
                                                                             with_bias, ctx->U, ctx->tc_users, unorm, ctx->flag);
   build_mask<<<(unsigned)(((int64_t)n_users * 32 + 255) / 256), 256, 0, st>>>(seen_indptr, seen_indices, row0, n_users, I,
-                                                                              n_itiles, (uint32_t*)ctx->tc_mask);
+                                                                              n_itiles, (uint32_t*)ctx->tc_mask, heavy);
   ctx->launches += 3;
   CUtensorMap tmA, tmB;
   rc = make_panel_map(ctx, &tmA, ctx->tc_users, urows, Kp);
@@ -756,6 +814,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   p.mask = (const uint2*)ctx->tc_mask;
   p.gmax = ctx->tc_gmax;
   p.thr = thr;
+  p.heavy = heavy;
   p.cnt = cnt;
   p.cand = ctx->tc_cand;
   p.err = ctx->flag;
@@ -763,11 +822,11 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   const int k = tp_in.k_max < I ? tp_in.k_max : I;
   if (G <= 32 * 48)
-    select_threshold_warp<48><<<(n_users * 32 + 127) / 128, 128, 0, st>>>(ctx->tc_gmax, G, k, n_users, seen_indptr, row0, unorm,
-                                                                          vmax_bits, thr);
+    select_threshold_warp<48><<<(n_users * 32 + 127) / 128, 128, 0, st>>>(ctx->tc_gmax, G, k, n_users, seen_indptr, row0, heavy,
+                                                                          unorm, vmax_bits, thr);
   else
-    select_threshold<<<n_users, kSelThreads, (size_t)G * sizeof(uint32_t), st>>>(ctx->tc_gmax, G, k, seen_indptr, row0, unorm,
-                                                                                  vmax_bits, thr);
+    select_threshold<<<n_users, kSelThreads, (size_t)G * sizeof(uint32_t), st>>>(ctx->tc_gmax, G, k, seen_indptr, row0, heavy,
+                                                                                  unorm, vmax_bits, thr);
   p.pass = 1;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
   TopkParams tp = tp_in;
