@@ -536,7 +536,7 @@ def run_ours(args) -> None:
     small = head["kernel_n"] == 0
     k_ms = head["ms_per_step"] if small else head["kernel_ms"]
 
-    want = args.configs
+    want = os.environ.get("RBPR_BENCH_CONFIGS", args.configs)  # (scripts override the default set)
     if want == "auto":
         want = "all" if world == 1 else "c3,c5"
     names = ["c2_b256", "c2_b262144", "c3", "c4", "c5", "experiment"] if want == "all" else \

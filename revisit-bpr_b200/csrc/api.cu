@@ -80,7 +80,6 @@ void rbpr_destroy(rbpr_ctx* ctx) {
   cudaFree(ctx->tc_mask);
   cudaFree(ctx->tc_small);
   cudaFree(ctx->tc_cand);
-  cudaFree(ctx->tc_cand_s);
   cudaFree(ctx->tc_ovf_users);
   cudaFree(ctx->adam_tab);
   cudaFree(ctx->ad_snap);

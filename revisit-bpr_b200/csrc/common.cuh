@@ -78,8 +78,6 @@ struct rbpr_ctx {
   // tensor-core scoring path (score_tc.cu): K-padded panels, seen bitmask, group maxima, candidates
   float *tc_items = nullptr, *tc_users = nullptr, *tc_gmax = nullptr;
   void *tc_mask = nullptr, *tc_small = nullptr;
-  float* tc_cand_s = nullptr;  // approximate scores of the candidates
-  size_t tc_cand_s_bytes = 0;
   int32_t *tc_cand = nullptr, *tc_overflow_rows = nullptr;  // (tc_overflow_rows points into tc_small)
   size_t tc_items_bytes = 0, tc_users_bytes = 0, tc_gmax_bytes = 0, tc_mask_bytes = 0, tc_small_bytes = 0,
          tc_cand_bytes = 0;

@@ -64,7 +64,6 @@ struct TcParams {
   const uint8_t* heavy;    // (n_users) 1: many seen items -> this user's group maxima are taken over UNSEEN items only
   int32_t* cnt;            // (n_users, segs, 2) candidates in each private list (> LIST_CAP: overflow)
   int32_t* cand;           // (n_users, segs, 2, LIST_CAP)
-  float* cand_s;           // approximate scores of the candidates, same layout
   int32_t* err;
 };
 
@@ -341,27 +340,18 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         ok = mbar_wait(t_full + acc, aph, p.err);
         if (!ok) break;
         tc_fence_after();
-        // both accumulators of the stage into registers first, then the stage goes back to the MMA warp
-        // BEFORE any arithmetic: the next unit's MMAs overlap this unit's epilogue
-        uint32_t rr[2][64];
-        {
-          const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * (uint32_t)UT) * (uint32_t)TN + (uint32_t)(half * 64);
-          tc_ld32(t0, rr[0]);
-          tc_ld32(t0 + 32u, rr[0] + 32);
-          if (UT == 2) {
-            tc_ld32(t0 + (uint32_t)TN, rr[1]);
-            tc_ld32(t0 + (uint32_t)TN + 32u, rr[1] + 32);
-          }
+        for (int h = 0; h < UT; ++h) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * (uint32_t)UT + (uint32_t)h) * (uint32_t)TN +
+                                 (uint32_t)(half * 64);
+          uint32_t r0[32], r1[32];
+          tc_ld32(taddr, r0);
+          tc_ld32(taddr + 32u, r1);
           tc_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + acc);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h >= UT) break;
-          const uint32_t* r0 = rr[h];
-          const uint32_t* r1 = rr[h] + 32;
+          if (h == UT - 1) {  // both accumulators of the stage are in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + acc);
+          }
           if (p.pass == 0) {
             if (valid[h]) {
               float4* dst = reinterpret_cast<float4*>(p.gmax + (size_t)u[h] * p.n_itiles * NGT + (size_t)it * NGT + half * 4);
@@ -375,30 +365,17 @@ score_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             uint32_t pm0 = ge_mask32(r0, thr[h]) & ~mw[h].x, pm1 = ge_mask32(r1, thr[h]) & ~mw[h].y;
             const int base = it * TN + half * 64;
             int32_t* my_cand = p.cand + list[h] * LIST_CAP;
-            float* my_s = p.cand_s + list[h] * LIST_CAP;
             int n = n_cand[h];
             while (pm0 != 0u) {  // rare: ~1 % of the scores
               const int j = __ffs(pm0) - 1;
               pm0 &= pm0 - 1u;
-              if (n < LIST_CAP) {
-                my_cand[n] = base + j;
-                float sj = 0.f;  // r0[j] without dynamic register indexing
-#pragma unroll
-                for (int e = 0; e < 32; ++e) sj = (e == j) ? __uint_as_float(r0[e]) : sj;
-                my_s[n] = sj;
-              }
+              if (n < LIST_CAP) my_cand[n] = base + j;
               ++n;
             }
             while (pm1 != 0u) {
               const int j = __ffs(pm1) - 1;
               pm1 &= pm1 - 1u;
-              if (n < LIST_CAP) {
-                my_cand[n] = base + 32 + j;
-                float sj = 0.f;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) sj = (e == j) ? __uint_as_float(r1[e]) : sj;
-                my_s[n] = sj;
-              }
+              if (n < LIST_CAP) my_cand[n] = base + 32 + j;
               ++n;
             }
             n_cand[h] = n;
@@ -588,9 +565,8 @@ constexpr int kRankThreads = 256;
 __global__ void __launch_bounds__(kRankThreads)
 rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_emb, const float* __restrict__ item_bias,
              const int64_t* __restrict__ users, int D, int segs, const int32_t* __restrict__ cnt,
-             const int32_t* __restrict__ cand, const float* __restrict__ cand_s, const float* __restrict__ unorm,
-             const uint32_t* __restrict__ vmax_bits, int32_t* __restrict__ overflow_rows,
-             int32_t* __restrict__ overflow_count, TopkParams p) {
+             const int32_t* __restrict__ cand, int32_t* __restrict__ overflow_rows, int32_t* __restrict__ overflow_count,
+             TopkParams p) {
   __shared__ unsigned long long key_in[CAND_CAP];
   __shared__ unsigned long long sel[KCAP];
   __shared__ int32_t items[CAND_CAP];
@@ -616,61 +592,15 @@ rescore_rank(const float* __restrict__ user_emb, const float* __restrict__ item_
     if (tid == 0) overflow_rows[atomicAdd(overflow_count, 1)] = (int32_t)urow;
     return;
   }
-  int n = s_n;
-  __shared__ float approx[CAND_CAP];
+  const int n = s_n;
   {
     int off = 0;
     for (int l = 0; l < n_lists; ++l) {
       const int c = c_row[l];
       const int32_t* src = cand + ((size_t)urow * n_lists + l) * LIST_CAP;
-      const float* src_s = cand_s + ((size_t)urow * n_lists + l) * LIST_CAP;
-      for (int i = tid; i < c; i += kRankThreads) {
-        items[off + i] = src[i];
-        approx[off + i] = src_s[i];
-      }
+      for (int i = tid; i < c; i += kRankThreads) items[off + i] = src[i];
       off += c;
     }
-  }
-  // Second filter, on the candidates' own approximate scores (all unseen): with t = the k-th largest
-  // S~ among them, the exact k-th largest score is >= t - eps, so an item of the exact top-k has
-  // S~ >= t - 2 eps.  This cuts the rows gathered for the exact rescoring from ~2k to ~k.
-  const int kk = min(p.k_max, p.I);
-  if (n > kk) {
-    __shared__ int s_keep;
-    __shared__ uint32_t s_t;
-    __syncthreads();
-    // bisection on the float keys for the kk-th largest approximate score (block-wide counts)
-    __shared__ int wcnt[kRankThreads / 32];
-    uint32_t T = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t c2 = T | (1u << bit);
-      int c = 0;
-      for (int i = tid; i < n; i += kRankThreads) c += (fkey(approx[i]) >= c2);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if ((tid & 31) == 0) wcnt[tid >> 5] = c;
-      __syncthreads();
-      int tot = 0;
-#pragma unroll
-      for (int q = 0; q < kRankThreads / 32; ++q) tot += wcnt[q];
-      if (tot >= kk) T = c2;
-      __syncthreads();
-    }
-    if (tid == 0) {
-      s_keep = 0;
-      s_t = T;
-    }
-    __syncthreads();
-    const float cut = ikey(s_t) - 0.002f * unorm[urow] * __uint_as_float(*vmax_bits);
-    // compact the survivors (order is irrelevant: the exact keys are ranked below)
-    int32_t mine_it[CAND_CAP / kRankThreads];
-    int n_mine = 0;
-    for (int i = tid; i < n; i += kRankThreads)
-      if (approx[i] >= cut) mine_it[n_mine++] = items[i];
-    __syncthreads();
-    for (int e = 0; e < n_mine; ++e) items[atomicAdd(&s_keep, 1)] = mine_it[e];
-    __syncthreads();
-    n = s_keep;
   }
   const int64_t u = users[urow];
   for (int c = tid; c < D; c += kRankThreads) s_u[c] = user_emb[u * D + c];
@@ -834,8 +764,6 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   if (rc) return rc;
   rc = grow(ctx, (void**)&ctx->tc_cand, &ctx->tc_cand_bytes, n_lists * LIST_CAP * sizeof(int32_t));
   if (rc) return rc;
-  rc = grow(ctx, (void**)&ctx->tc_cand_s, &ctx->tc_cand_s_bytes, n_lists * LIST_CAP * sizeof(float));
-  if (rc) return rc;
   // small arrays in one allocation: thr | unorm | overflow rows | {overflow count, vmax} | list counts
   const size_t small = (size_t)n_users * 3 * sizeof(float) + 256 + n_lists * sizeof(int32_t) + (size_t)n_users + 16;
   rc = grow(ctx, (void**)&ctx->tc_small, &ctx->tc_small_bytes, small);
@@ -889,7 +817,6 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   p.heavy = heavy;
   p.cnt = cnt;
   p.cand = ctx->tc_cand;
-  p.cand_s = ctx->tc_cand_s;
   p.err = ctx->flag;
   p.pass = 0;
   score_tc<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
@@ -905,7 +832,7 @@ int rbpr_score_tc_block(rbpr_ctx* ctx, const int64_t* users, int n_users, const 
   TopkParams tp = tp_in;
   tp.row0 = row0;
   rescore_rank<<<n_users, kRankThreads, 0, st>>>(ctx->user_emb, ctx->item_emb, ctx->item_bias, users, D, segs, cnt,
-                                                 ctx->tc_cand, ctx->tc_cand_s, unorm, vmax_bits, ovf_rows, ovf_count, tp);
+                                                 ctx->tc_cand, ovf_rows, ovf_count, tp);
   ctx->launches += 4;
   ctx->topk_launches++;
   ctx->tc_passes++;

@@ -19,6 +19,6 @@ if not ok: print(open("gpurun_out/r2n_bench_$tag.err").read()[-1500:])
 P
 }
 run 8 n8_fused RBPR_FUSED_EXCHANGE=1
-run 8 n8_nccl RBPR_FUSED_EXCHANGE=0 BENCH_CONFIGS_NONE=1
-run 4 n4_fused RBPR_FUSED_EXCHANGE=1 BENCH_CONFIGS_NONE=1
+run 8 n8_nccl RBPR_FUSED_EXCHANGE=0 RBPR_BENCH_CONFIGS=none
+run 4 n4_fused RBPR_FUSED_EXCHANGE=1 RBPR_BENCH_CONFIGS=none
 echo "== experiment ddp (8 ranks)"; RBPR_HANG_DUMP_S=90 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 tests/tools/check_experiment_ddp.py > gpurun_out/r2n_ddp8.log 2>&1; echo "exit $?"; grep "experiment ddp\|Timeout\|Error" gpurun_out/r2n_ddp8.log | head -12
