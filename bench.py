@@ -399,6 +399,8 @@ class Runner:
         loss_last = stats[-1, 0].item() / max(stats[-1, 3].item(), 1.0)
         res = {"inter": inter, "ms": ms, "value": K * B * self.world / (ms * 1e-3), "ms_per_step": ms / K,
                "launches": launches, "collectives": collectives, "fused_exchanges": exchanges,
+               "exchange": (("nvswitch multicast (multimem.ld_reduce / multimem.st)" if getattr(eng, "multicast", False)
+                             else "peer loads / stores") if exchanges else ("nccl all-reduce" if collectives else None)),
                "kernel_ms": (k_ms / k_n) if k_n else None, "kernel_n": k_n, "loss": loss_last,
                "clocks": self.clocks.window(mark, mark1) if self.clocks else None}
         if e2e:  # end to end with host buffers: H2D of the step's triple ids, D2H of its stats, every call
@@ -436,7 +438,7 @@ class Runner:
             extra["bytes_per_triple_incl_adam_state"] = 72 * D
         return {"metric": "BPR triples/sec", "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
                 "steps": K, "warmup": W, "config": cfg, "roofline": roofline(kern, key, alg, k_ms, hot, extra),
-                "gpu_launches": r["launches"], "nccl_allreduces": r["collectives"], "fused_exchanges": r["fused_exchanges"],
+                "gpu_launches": r["launches"], "nccl_allreduces": r["collectives"], "fused_exchanges": r["fused_exchanges"], "exchange": r["exchange"],
                 "final_bpr_loss_per_triple": r["loss"], "clocks": r["clocks"]}
 
     # ---- scoring configuration (BASELINE configs[4]) -------------------------------------------------
@@ -575,7 +577,7 @@ def run_ours(args) -> None:
                                   "step_frac_algorithmic": alg / (head["ms_per_step"] * 1e-3) / 1e9 / peaks()[0],
                                   "frac_of_nominal_8TBs": (alg / (k_ms * 1e-3) / 1e9 / 8000.0) if k_ms else None}),
             "e2e": head["e2e"], "gpu_launches": head["launches"], "nccl_allreduces": head["collectives"],
-            "fused_exchanges": head["fused_exchanges"], "clocks": head["clocks"],
+            "fused_exchanges": head["fused_exchanges"], "exchange": head["exchange"], "clocks": head["clocks"],
             "final_bpr_loss_per_triple": head["loss"], "configs": configs,
         }
         if parity is not None:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RBPR_ABI_VERSION 8
+#define RBPR_ABI_VERSION 9
 
 typedef struct rbpr_ctx rbpr_ctx;
 
@@ -258,6 +258,22 @@ int64_t rbpr_collective_count(const rbpr_ctx* ctx);
 #define RBPR_IPC_BLOB_BYTES 512
 int rbpr_comm_ipc_export(rbpr_ctx* ctx, void* blob_out);
 int rbpr_comm_ipc_bind(rbpr_ctx* ctx, const void* blobs, int32_t world, int32_t rank, void* stream);
+/* The same exchange over a SYMMETRIC buffer the host shell allocates (same size on every rank, mapped
+ * into every peer — torch.distributed._symmetric_memory, or cuMemCreate + cuMemMap + cuMulticastBindMem):
+ * peer_bases[q] is this process's mapping of rank q's buffer (own one included), multicast_base the
+ * multicast alias of the buffer or 0.  With a multicast alias the reduction runs INSIDE the NVSwitch
+ * (multimem.ld_reduce: one 16-byte response per element instead of one load per rank) and the
+ * updated rows leave the owner once (multimem.st), which roughly halves the NVLink bytes per GPU;
+ * the order of the in-switch sum is the hardware's, so results may differ in the last bit from the
+ * rank-order sum of the unicast path (replicas stay bit-identical: the owner computes, everybody
+ * receives the same bits).  The buffer must hold rbpr_comm_symm_bytes(ctx) bytes, be 256-byte
+ * aligned and ZERO before any rank binds.  The bind MOVES the item table and bias into the buffer
+ * and returns their new device addresses: the caller re-points its tensors there (the old storage
+ * is no longer read or written by the library).  Collective: every rank calls it. */
+int64_t rbpr_comm_symm_bytes(const rbpr_ctx* ctx);
+int rbpr_comm_symm_bind(rbpr_ctx* ctx, const uint64_t* peer_bases, uint64_t multicast_base, int32_t world,
+                        int32_t rank, uint64_t* item_emb_out, uint64_t* item_bias_out, void* stream);
+int32_t rbpr_fused_exchange_multicast(const rbpr_ctx* ctx);
 int64_t rbpr_fused_exchange_count(const rbpr_ctx* ctx);
 
 /* Bring every lazily-updated user row up to `step` optimizer steps (dense-Adam semantics

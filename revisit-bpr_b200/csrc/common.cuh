@@ -107,6 +107,15 @@ struct rbpr_ctx {
   uint32_t fx_wait_epoch = 0;  // B2 epoch the next reader of item rows must wait for (0: nothing pending)
   uint32_t* fx_flags_local = nullptr;  // this rank's flag words (inside fx_sym)
   uint32_t* fx_done = nullptr;         // CTA completion counter of the exchange kernel
+  unsigned long long* fx_trace = nullptr;  // RBPR_FX_TRACE: globaltimer stamps of the exchange kernel (ring)
+  int64_t fx_trace_n = 0;
+  // symmetric-memory binding (rbpr_comm_symm_bind): host-owned buffer, optional NVSwitch multicast alias
+  bool fx_symm_host = false;
+  const float* fx_mc_grad[2] = {nullptr, nullptr};
+  float* fx_mc_item = nullptr;
+  float* fx_mc_bias = nullptr;
+  float* fx_item_prev = nullptr;  // the caller's item table / bias before they moved into the symmetric buffer
+  float* fx_bias_prev = nullptr;
   float* fx_item_grad_owned = nullptr;  // the library's own accumulator while the shared ones are in use
   int64_t fused_exchanges = 0;
   // instrumentation

@@ -28,6 +28,7 @@ using namespace rbpr_dev;
 namespace {
 
 constexpr int kMaxWorld = RBPR_MAX_PEERS;
+constexpr int kTraceSlots = 512;  // RBPR_FX_TRACE ring: exchanges kept per report
 
 struct IpcBlob {  // what one rank tells the others (host-exchanged, fixed size: RBPR_IPC_BLOB_BYTES)
   cudaIpcMemHandle_t sym;    // library-owned: buf[0] | buf[1] | flags
@@ -49,7 +50,7 @@ struct ExchangeParams {
   float* item_v;
   float* bias_m;
   float* bias_v;
-  // barriers folded into this kernel: B1 (signal + wait at the start), B2 (signal by the last CTA)
+  // barriers folded into this kernel: B1 (signal at the start, wait before the reduce), B2 (signal by the last CTA)
   uint32_t* const* flags;        // device array: flags[q] = rank q's flag words: [0,W) = B1, [W_MAX, W_MAX+W) = B2
   uint32_t epoch;                // this exchange's barrier epoch
   uint32_t* done;                // CTAs finished (self-resetting counter)
@@ -60,84 +61,157 @@ struct ExchangeParams {
   uint64_t step;
   float lr, beta1, beta2, eps;
   const float2* adam_tab;
+  unsigned long long* trace;     // RBPR_FX_TRACE: 8 globaltimer words of this exchange, or null
+  // NVSwitch multicast (symmetric-memory binding only; null = unicast loads / stores through gsrc / idst):
+  const float* mc_grad;          // multicast address of this parity's accumulators: multimem.ld_reduce sums
+                                 // the W copies INSIDE the switch, one 16-byte response per element
+  float* mc_item;                // multicast address of the item tables: one multimem.st reaches every replica
+  float* mc_bias;
+  int n_xchg;                    // CTAs [0, n_xchg) run the exchange, the others the local work
 };
 
 __device__ __forceinline__ float4 ldcg4x(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
+// One launch per step and rank; the CTAs split into two roles that run side by side (they are bound
+// by different resources: NVLink vs HBM):
+//   exchange CTAs [0, n_xchg):
+//     1. CTA 0 publishes "this rank's phase A has landed" (B1) to every peer; all wait for every peer's B1;
+//     2. the slice, one 16-byte element per thread and iteration: the W accumulators summed — by the
+//        NVSwitch (multimem.ld_reduce: one response per element) under the symmetric-memory binding,
+//        else W independent 128-bit peer loads in flight at once, summed in rank order — optimizer,
+//        then the updated element stored into every replica (multimem.st, else W 128-bit stores);
+//   local CTAs [n_xchg, grid): work that needs no peer — the user half of the step's apply (users are
+//        sharded by owner, their gradients never leave the rank), the step statistics, clearing the
+//        accumulator of the next step;
+//   the last CTA to finish publishes "this rank's rows have landed" (B2).
 template <int LANES, int NV, int OPT>
-__global__ void __launch_bounds__(256) bpr_exchange_apply(const ExchangeParams p) {
-  const Group<LANES> g;
+__global__ void __launch_bounds__(256, 4) bpr_exchange_apply(const ExchangeParams p, const ApplyParams u) {
   const int D = p.D;
-  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   OptScalars h = {p.lr, p.beta1, p.beta2, p.eps, 0.f, 1.f};
   if (OPT == RBPR_OPT_ADAM) {
     const float2 t = __ldg(p.adam_tab + (p.step + 1));
     h.step_size = t.x;
     h.bc2_sqrt = t.y;
   }
+  // the next phase A may be placed as soon as SM resources free up (launch_phase_a, train_kernels.cuh)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int W = p.world;
-  // ---- B1: "every rank's phase A has landed".  This kernel runs after this rank's phase A (stream
-  // order), so CTA 0 publishes the arrival; every CTA then waits for all peers' arrivals.
+  const int G = (int)gridDim.x;
+  const bool both = p.n_xchg >= G;  // no role split: every CTA does the local work, then the exchange
+  const bool tracer = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracer) p.trace[0] = gtime();
+  // B1 signal: this kernel runs after this rank's phase A (stream order)
   if (blockIdx.x == 0 && threadIdx.x < W) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.rank), "r"(p.epoch) : "memory");
   }
-  wait_peer_flags(p.flags[p.rank], W, p.epoch, p.err);
-  // ---- this rank's slice: reduce over ranks, update, publish -------------------------------------
-  for (int64_t r = p.lo + gid; r < p.hi; r += groups) {
-    float4 gr[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) gr[v] = f4zero();
-    for (int q = 0; q < W; ++q) {  // fixed order: every run sums in the same order
-      const float* src = p.gsrc[q] + r * D;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = 4 * (g.gl + LANES * v);
-        if (c < D) gr[v] = add4(gr[v], ldcg4x(src + c));
-      }
-    }
-    const float* prow = p.idst[p.rank] + r * D;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = 4 * (g.gl + LANES * v);
-      if (c >= D) continue;
-      float4 pp = ldcg4x(prow + c);
-      if (OPT == RBPR_OPT_SGD) {
-        pp.x -= p.lr * gr[v].x;
-        pp.y -= p.lr * gr[v].y;
-        pp.z -= p.lr * gr[v].z;
-        pp.w -= p.lr * gr[v].w;
-      } else {
-        float4 m = ld4(p.item_m + r * D + c);
-        float4 vv = opt_has_s2(OPT) ? ld4(p.item_v + r * D + c) : f4zero();
-        opt4<OPT>(pp, m, vv, gr[v], h);
-        st4(p.item_m + r * D + c, m);
-        if (opt_has_s2(OPT)) st4(p.item_v + r * D + c, vv);
-      }
-      for (int q = 0; q < W; ++q) st4(p.idst[q] + r * D + c, pp);
-    }
-    if (g.gl == 0 && p.bdst[p.rank] != nullptr) {
-      float gb = 0.f;
-      for (int q = 0; q < W; ++q) gb += __ldcg(p.gsrc[q] + p.I * D + r);
-      float b = __ldcg(p.bdst[p.rank] + r);
-      if (OPT == RBPR_OPT_SGD) {
-        b -= p.lr * gb;
-      } else {
-        float m = p.bias_m[r], vv = opt_has_s2(OPT) ? p.bias_v[r] : 0.f;
-        opt1<OPT>(b, m, vv, gb, h);
-        p.bias_m[r] = m;
-        if (opt_has_s2(OPT)) p.bias_v[r] = vv;
-      }
-      for (int q = 0; q < W; ++q) p.bdst[q][r] = b;
-    }
+  if (both || (int)blockIdx.x >= p.n_xchg) {
+    // ---- local CTAs
+    const int lb = both ? (int)blockIdx.x : (int)blockIdx.x - p.n_xchg, ln = both ? G : G - p.n_xchg;
+    const int64_t nthreads = (int64_t)ln * blockDim.x;
+    const int64_t tid = (int64_t)lb * blockDim.x + threadIdx.x;
+    if (u.do_users) apply_users<LANES, NV, OPT>(u, h, tid / LANES, nthreads / LANES);
+    // the accumulator the NEXT step uses: the peers finished reading it before their B2 of the
+    // previous exchange, which this rank's phase A (earlier in this stream) has waited for
+    const int64_t vecs = (p.I * D + (p.bdst[p.rank] != nullptr ? p.I : 0) + 3) / 4;  // buffer is padded to 16 B
+    float4* z = reinterpret_cast<float4*>(p.gzero);
+    for (int64_t k = tid; k < vecs; k += nthreads) z[k] = f4zero();
+    if (lb == ln - 1 && u.stats_out != nullptr) apply_stats(u);
+    if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + 1, gtime());
   }
-  // ---- clear the accumulator the NEXT step uses (local; the peers read it one step ago) -----------
-  const int64_t vecs = (p.I * D + (p.bdst[p.rank] != nullptr ? p.I : 0) + 3) / 4;  // buffer is padded to 16 B
-  float4* z = reinterpret_cast<float4*>(p.gzero);
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < vecs; k += (int64_t)gridDim.x * blockDim.x)
-    z[k] = f4zero();
+  if (both || (int)blockIdx.x < p.n_xchg) {
+    // ---- exchange CTAs
+    const int64_t nthreads = (int64_t)(both ? G : p.n_xchg) * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    wait_peer_flags(p.flags[p.rank], W, p.epoch, p.err);
+    if (tracer) p.trace[2] = gtime();
+    const int64_t e_lo = p.lo * D / 4, e_hi = p.hi * D / 4;
+    for (int64_t e = e_lo + tid; e < e_hi; e += nthreads) {
+      const int64_t off = 4 * e;
+      float4 gr;
+      if (p.mc_grad != nullptr) {
+        gr = mc_ld_reduce4(p.mc_grad + off);
+      } else {
+        float4 t[kMaxWorld];
+#pragma unroll
+        for (int j = 0; j < kMaxWorld; ++j)  // all W loads are independent: issued back to back
+          if (j < W) t[j] = ldcg4x(p.gsrc[j] + off);
+        gr = t[0];
+#pragma unroll
+        for (int j = 1; j < kMaxWorld; ++j)  // fixed order (rank 0, 1, ...): every run sums the same way
+          if (j < W) gr = add4(gr, t[j]);
+      }
+      float4 pp = ldcg4x(p.idst[p.rank] + off);
+      if (OPT == RBPR_OPT_SGD) {
+        pp.x -= p.lr * gr.x;
+        pp.y -= p.lr * gr.y;
+        pp.z -= p.lr * gr.z;
+        pp.w -= p.lr * gr.w;
+      } else {
+        float4 m = ld4(p.item_m + off);
+        float4 vv = opt_has_s2(OPT) ? ld4(p.item_v + off) : f4zero();
+        opt4<OPT>(pp, m, vv, gr, h);
+        st4(p.item_m + off, m);
+        if (opt_has_s2(OPT)) st4(p.item_v + off, vv);
+      }
+      if (p.mc_item != nullptr) {
+        mc_st4(p.mc_item + off, pp);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kMaxWorld; ++j)
+          if (j < W) st4(p.idst[j] + off, pp);
+      }
+    }
+    if (p.bdst[p.rank] != nullptr) {
+      for (int64_t r = p.lo + tid; r < p.hi; r += nthreads) {
+        float gb = 0.f;
+        if (p.mc_grad != nullptr) {
+          gb = mc_ld_reduce1(p.mc_grad + p.I * D + r);
+        } else {
+          for (int q = 0; q < W; ++q) gb += __ldcg(p.gsrc[q] + p.I * D + r);
+        }
+        float b = __ldcg(p.bdst[p.rank] + r);
+        if (OPT == RBPR_OPT_SGD) {
+          b -= p.lr * gb;
+        } else {
+          float m = p.bias_m[r], vv = opt_has_s2(OPT) ? p.bias_v[r] : 0.f;
+          opt1<OPT>(b, m, vv, gb, h);
+          p.bias_m[r] = m;
+          if (opt_has_s2(OPT)) p.bias_v[r] = vv;
+        }
+        if (p.mc_bias != nullptr) {
+          mc_st1(p.mc_bias + r, b);
+        } else {
+          for (int q = 0; q < W; ++q) p.bdst[q][r] = b;
+        }
+      }
+    }
+    if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + 3, gtime());
+  }
   // ---- B2: "this rank's rows have landed everywhere": the last CTA to finish publishes it; the next
   // kernel that reads item rows (phase A, or the wait at the end of the call) waits for all ranks
   __syncthreads();
@@ -148,6 +222,7 @@ __global__ void __launch_bounds__(256) bpr_exchange_apply(const ExchangeParams p
       __threadfence_system();
       for (int q = 0; q < W; ++q)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[q] + kMaxWorld + p.rank), "r"(p.epoch) : "memory");
+      if (p.trace != nullptr) p.trace[4] = gtime();
     }
   }
 }
@@ -215,8 +290,10 @@ int rbpr_internal_xrank_barrier(rbpr_ctx* ctx, cudaStream_t st) {
 }
 
 // The exchange of one step on stream st (fused path).  ctx->item_grad is the accumulator phase A
-// used; on return it points at the (cleared) accumulator of the next step.
-int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
+// used; on return it points at the (cleared) accumulator of the next step.  `users` (optional): the
+// user half of the step's apply and its statistics, run inside the same kernel ahead of the B1 wait.
+int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st,
+                                 const ApplyParams* users) {
   int rc = 0;
   const int par = ctx->fx_par;
   ctx->fx_epoch++;
@@ -248,16 +325,36 @@ int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   p.beta2 = hp->beta2;
   p.eps = hp->eps;
   p.adam_tab = ctx->adam_tab;
+  if (ctx->fx_trace != nullptr) p.trace = ctx->fx_trace + 8 * (size_t)(ctx->fx_trace_n++ % kTraceSlots);
+  if (ctx->fx_mc_grad[par] != nullptr) {
+    p.mc_grad = ctx->fx_mc_grad[par];
+    p.mc_item = ctx->fx_mc_item;
+    p.mc_bias = ctx->fx_mc_bias;
+  }
+  ApplyParams u;
+  if (users != nullptr) {
+    u = *users;
+  } else {
+    memset(&u, 0, sizeof(u));
+  }
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
+  // one wave of 4 CTAs per SM (<= 64 registers).  RBPR_FX_XCHG_CTAS = how many of the 4 run the
+  // exchange role (the rest the local role); 4 = no split: every CTA does the local work first
+  static const int xchg_per_sm = [] {
+    const char* e = getenv("RBPR_FX_XCHG_CTAS");
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
   const int blocks = ctx->sm_count * 4;
+  p.n_xchg = ctx->sm_count * xchg_per_sm;
 #define X(L, V)                                                                                       \
   if (lanes == L && nv == V) {                                                                        \
     switch (hp->optimizer) {                                                                          \
-      case RBPR_OPT_SGD: bpr_exchange_apply<L, V, RBPR_OPT_SGD><<<blocks, 256, 0, st>>>(p); break;     \
-      case RBPR_OPT_ADAM: bpr_exchange_apply<L, V, RBPR_OPT_ADAM><<<blocks, 256, 0, st>>>(p); break;   \
-      case RBPR_OPT_SGDM: bpr_exchange_apply<L, V, RBPR_OPT_SGDM><<<blocks, 256, 0, st>>>(p); break;   \
-      default: bpr_exchange_apply<L, V, RBPR_OPT_RMSPROP><<<blocks, 256, 0, st>>>(p); break;           \
+      case RBPR_OPT_SGD: bpr_exchange_apply<L, V, RBPR_OPT_SGD><<<blocks, 256, 0, st>>>(p, u); break;     \
+      case RBPR_OPT_ADAM: bpr_exchange_apply<L, V, RBPR_OPT_ADAM><<<blocks, 256, 0, st>>>(p, u); break;   \
+      case RBPR_OPT_SGDM: bpr_exchange_apply<L, V, RBPR_OPT_SGDM><<<blocks, 256, 0, st>>>(p, u); break;   \
+      default: bpr_exchange_apply<L, V, RBPR_OPT_RMSPROP><<<blocks, 256, 0, st>>>(p, u); break;           \
     }                                                                                                 \
   } else
   RBPR_FOR_EACH_GEOMETRY(X)
@@ -281,8 +378,45 @@ int rbpr_internal_fx_wait(rbpr_ctx* ctx, cudaStream_t st) {
   return 0;
 }
 
+// RBPR_FX_TRACE=1: where the time of the exchange kernel goes (globaltimer stamps written by the
+// kernel), printed per call to stderr.  Diagnostic only: synchronises the stream.
+int rbpr_internal_fx_trace_report(rbpr_ctx* ctx, cudaStream_t st) {
+  if (ctx->fx_trace == nullptr || ctx->fx_trace_n == 0) return 0;
+  const int n = ctx->fx_trace_n < kTraceSlots ? (int)ctx->fx_trace_n : kTraceSlots;
+  std::vector<unsigned long long> t((size_t)8 * kTraceSlots);
+  RBPR_CUDA(ctx, cudaMemcpyAsync(t.data(), ctx->fx_trace, t.size() * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+  RBPR_CUDA(ctx, cudaStreamSynchronize(st));
+  double local = 0, b1 = 0, loop = 0, tail = 0, total = 0, between = 0;
+  int nb = 0;
+  for (int i = 0; i < n; ++i) {
+    const unsigned long long* w = t.data() + 8 * i;
+    local += (double)(w[1] - w[0]);   // local CTAs done (runs beside the exchange CTAs)
+    b1 += (double)(w[2] - w[0]);
+    loop += (double)(w[3] - w[2]);
+    tail += (double)(w[4] - (w[3] > w[1] ? w[3] : w[1]));
+    total += (double)(w[4] - w[0]);
+    if (i + 1 < n) {
+      between += (double)(t[8 * (i + 1)] - w[4]);
+      nb++;
+    }
+  }
+  fprintf(stderr,
+          "[rbpr fx trace] rank %d: %d exchanges, mean us: local CTAs (users+clear) done at %.2f | B1 signal+wait %.2f | slice reduce+publish %.2f | "
+          "tail(fence+B2) %.2f | kernel %.2f | B2 -> next exchange start (phase A etc.) %.2f\n",
+          ctx->rank, n, local / n * 1e-3, b1 / n * 1e-3, loop / n * 1e-3, tail / n * 1e-3, total / n * 1e-3,
+          nb ? between / nb * 1e-3 : 0.0);
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_trace, 0, t.size() * sizeof(unsigned long long), st));
+  ctx->fx_trace_n = 0;
+  return 0;
+}
+
 void rbpr_internal_fx_destroy(rbpr_ctx* ctx) {
   if (!ctx->fx_bound && !ctx->fx_sym) return;
+  ctx->fx_mc_grad[0] = ctx->fx_mc_grad[1] = nullptr;
+  ctx->fx_mc_item = ctx->fx_mc_bias = nullptr;
+  cudaFree(ctx->fx_trace);
+  ctx->fx_trace = nullptr;
   for (void* m : ctx->fx_opened) cudaIpcCloseMemHandle(m);
   ctx->fx_opened.clear();
   cudaFree(ctx->fx_flags_dev);
@@ -385,6 +519,11 @@ int rbpr_comm_ipc_bind(rbpr_ctx* ctx, const void* blobs, int32_t world, int32_t 
   }
   RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_done, sizeof(uint32_t)));
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_done, 0, sizeof(uint32_t), st));
+  if (getenv("RBPR_FX_TRACE") != nullptr && ctx->fx_trace == nullptr) {
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_trace, (size_t)8 * kTraceSlots * sizeof(unsigned long long)));
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_trace, 0, (size_t)8 * kTraceSlots * sizeof(unsigned long long), st));
+    ctx->fx_trace_n = 0;
+  }
   ctx->fx_flags_local = flags_host[rank];
   ctx->fx_wait_epoch = 0;
   RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_flags_dev, kMaxWorld * sizeof(uint32_t*)));
@@ -400,6 +539,86 @@ int rbpr_comm_ipc_bind(rbpr_ctx* ctx, const void* blobs, int32_t world, int32_t 
   // nobody accumulates before every rank has mapped and cleared its buffers
   return rbpr_internal_xrank_barrier(ctx, st);
 }
+
+// ---- symmetric-memory binding ---------------------------------------------------------------------
+// Layout of the host-allocated symmetric buffer (every offset 256-byte aligned):
+//   [ accumulator 0 | accumulator 1 | flag words | item table | item bias ]
+static size_t symm_item_off(const rbpr_ctx* ctx) { return 2 * sym_gbytes(ctx) + 256; }
+static size_t symm_bias_off(const rbpr_ctx* ctx) {
+  return symm_item_off(ctx) + (((size_t)ctx->I * ctx->D * sizeof(float) + 255) / 256) * 256;
+}
+
+int64_t rbpr_comm_symm_bytes(const rbpr_ctx* ctx) {
+  if (!ctx || !ctx->item_emb) return 0;
+  return (int64_t)(symm_bias_off(ctx) + (ctx->item_bias ? (((size_t)ctx->I * sizeof(float) + 255) / 256) * 256 : 0));
+}
+
+int rbpr_comm_symm_bind(rbpr_ctx* ctx, const uint64_t* peer_bases, uint64_t multicast_base, int32_t world,
+                        int32_t rank, uint64_t* item_emb_out, uint64_t* item_bias_out, void* stream) {
+  if (!ctx) return RBPR_ERR_ARG;
+  if (!peer_bases || world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
+    RBPR_FAIL(ctx, RBPR_ERR_ARG, "symm_bind: need 2..%d ranks and every rank's mapping of the symmetric buffer", kMaxWorld);
+  if (!ctx->item_emb || !ctx->item_grad) RBPR_FAIL(ctx, RBPR_ERR_STATE, "symm_bind: bind tables first");
+  if (ctx->fx_bound) RBPR_FAIL(ctx, RBPR_ERR_STATE, "symm_bind: peer memory already bound");
+  for (int q = 0; q < world; ++q)
+    if (peer_bases[q] == 0 || (peer_bases[q] & 255u)) RBPR_FAIL(ctx, RBPR_ERR_ARG, "symm_bind: mapping %d is null or not 256-byte aligned", q);
+  if (multicast_base & 255u) RBPR_FAIL(ctx, RBPR_ERR_ARG, "symm_bind: multicast address not 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  RBPR_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t gb = sym_gbytes(ctx), ioff = symm_item_off(ctx), boff = symm_bias_off(ctx);
+  // the tables move into the symmetric buffer (the caller re-points its tensors at *_out)
+  char* mine = (char*)(uintptr_t)peer_bases[rank];
+  RBPR_CUDA(ctx, cudaMemcpyAsync(mine + ioff, ctx->item_emb, (size_t)ctx->I * ctx->D * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+  if (ctx->item_bias)
+    RBPR_CUDA(ctx, cudaMemcpyAsync(mine + boff, ctx->item_bias, (size_t)ctx->I * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  uint32_t* flags_host[kMaxWorld];
+  for (int q = 0; q < world; ++q) {
+    char* sym = (char*)(uintptr_t)peer_bases[q];
+    ctx->fx_grad[q][0] = (float*)sym;
+    ctx->fx_grad[q][1] = (float*)(sym + gb);
+    flags_host[q] = (uint32_t*)(sym + 2 * gb);
+    ctx->fx_item[q] = (float*)(sym + ioff);
+    ctx->fx_bias[q] = ctx->item_bias ? (float*)(sym + boff) : nullptr;
+  }
+  if (multicast_base != 0) {
+    char* mc = (char*)(uintptr_t)multicast_base;
+    ctx->fx_mc_grad[0] = (const float*)mc;
+    ctx->fx_mc_grad[1] = (const float*)(mc + gb);
+    ctx->fx_mc_item = (float*)(mc + ioff);
+    ctx->fx_mc_bias = ctx->item_bias ? (float*)(mc + boff) : nullptr;
+  }
+  ctx->fx_item_prev = ctx->item_emb;
+  ctx->fx_bias_prev = ctx->item_bias;
+  ctx->item_emb = ctx->fx_item[rank];
+  if (ctx->item_bias) ctx->item_bias = ctx->fx_bias[rank];
+  if (item_emb_out) *item_emb_out = (uint64_t)(uintptr_t)ctx->item_emb;
+  if (item_bias_out) *item_bias_out = (uint64_t)(uintptr_t)ctx->item_bias;
+  ctx->fx_symm_host = true;
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_done, sizeof(uint32_t)));
+  RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_done, 0, sizeof(uint32_t), st));
+  if (getenv("RBPR_FX_TRACE") != nullptr && ctx->fx_trace == nullptr) {
+    RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_trace, (size_t)8 * kTraceSlots * sizeof(unsigned long long)));
+    RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_trace, 0, (size_t)8 * kTraceSlots * sizeof(unsigned long long), st));
+    ctx->fx_trace_n = 0;
+  }
+  ctx->fx_flags_local = flags_host[rank];
+  ctx->fx_wait_epoch = 0;
+  RBPR_CUDA(ctx, cudaMalloc(&ctx->fx_flags_dev, kMaxWorld * sizeof(uint32_t*)));
+  RBPR_CUDA(ctx, cudaMemcpyAsync(ctx->fx_flags_dev, flags_host, world * sizeof(uint32_t*), cudaMemcpyHostToDevice, st));
+  RBPR_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->world = world;
+  ctx->rank = rank;
+  ctx->fx_par = 0;
+  ctx->fx_epoch = 0;
+  ctx->fx_item_grad_owned = ctx->item_grad;
+  ctx->item_grad = ctx->fx_grad[rank][0];
+  ctx->fx_bound = true;
+  // nobody accumulates (or reads a replica) before every rank has placed its tables
+  return rbpr_internal_xrank_barrier(ctx, st);
+}
+
+int32_t rbpr_fused_exchange_multicast(const rbpr_ctx* ctx) { return (ctx && ctx->fx_bound && ctx->fx_mc_item) ? 1 : 0; }
 
 int64_t rbpr_fused_exchange_count(const rbpr_ctx* ctx) { return ctx ? ctx->fused_exchanges : 0; }
 

@@ -326,6 +326,7 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
     e0 = next_event(ctx);
     e1 = next_event(ctx);
     cudaEventRecord(e0, st);
+    p.pdl = 0;  // a timed launch must not start (and spin) while the previous kernel still runs
   }
   // the last (short) step of a call may need fewer CTAs; never more than `blocks` (partials stride)
   const int64_t need = ((int64_t)p.n + (kPhaseAThreads / lanes) - 1) / (kPhaseAThreads / lanes);
@@ -344,10 +345,9 @@ int run_phase_a(rbpr_ctx* ctx, TrainParams& p, const rbpr_hparams* hp, const int
 
 // do_items / do_users select the halves of bpr_apply; records/n are the step's records (users).
 // partials/n_partials/stats_out: phase A's per-warp statistics of the step, summed by block 0.
-int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
-              const int4* records, int n, cudaStream_t st, const float4* partials = nullptr,
-              int n_partials = 0, double* stats_out = nullptr, const int32_t* mh_list = nullptr,
-              const uint32_t* mh_count = nullptr) {
+ApplyParams make_apply_params(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
+                              const int4* records, int n, const float4* partials, int n_partials,
+                              double* stats_out, const int32_t* mh_list, const uint32_t* mh_count) {
   ApplyParams a;
   memset(&a, 0, sizeof(a));
   a.mh_list = mh_list;
@@ -357,7 +357,6 @@ int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, i
   a.partials = partials;
   a.n_partials = n_partials;
   a.stats_out = stats_out;
-  if (!a.do_items && !a.do_users && !stats_out) return 0;
   a.records = records;
   a.n = n;
   a.user_emb = ctx->user_emb;
@@ -383,6 +382,16 @@ int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, i
   a.beta2 = hp->beta2;
   a.eps = hp->eps;
   a.adam_tab = ctx->adam_tab;
+  return a;
+}
+
+int run_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, int dense, int do_items,
+              const int4* records, int n, cudaStream_t st, const float4* partials = nullptr,
+              int n_partials = 0, double* stats_out = nullptr, const int32_t* mh_list = nullptr,
+              const uint32_t* mh_count = nullptr) {
+  const ApplyParams a = make_apply_params(ctx, step, hp, dense, do_items, records, n, partials, n_partials,
+                                          stats_out, mh_list, mh_count);
+  if (!a.do_items && !a.do_users && !stats_out) return 0;
   int lanes, nv;
   rbpr_geometry(ctx->D, &lanes, &nv);
   int rc = hp->optimizer == RBPR_OPT_SGD    ? rbpr_launch_apply_sgd(ctx, a, lanes, nv, st)
@@ -434,13 +443,15 @@ int rbpr_launch_small_steps(rbpr_ctx* ctx, const TrainParams& p, const int4* rec
                             double* stats, cudaStream_t st);
 
 // defined in exchange.cu
-int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st);
+int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st,
+                                 const ApplyParams* users);
 int rbpr_internal_fx_wait(rbpr_ctx* ctx, cudaStream_t st);
+int rbpr_internal_fx_trace_report(rbpr_ctx* ctx, cudaStream_t st);
 
 // The step's one exchange on stream st: dense item gradient summed over ranks, then the (dense,
 // identical on every rank) item update.
 int rbpr_internal_exchange_apply(rbpr_ctx* ctx, uint64_t step, const rbpr_hparams* hp, cudaStream_t st) {
-  if (ctx->fx_bound) return rbpr_internal_fused_exchange(ctx, step, hp, st);  // one kernel over peer memory
+  if (ctx->fx_bound) return rbpr_internal_fused_exchange(ctx, step, hp, st, nullptr);  // one kernel over peer memory
   int rc = rbpr_internal_allreduce_item_grads(ctx, st);
   if (rc) return rc;
   return run_apply(ctx, step, hp, 1, 1, nullptr, 0, st);
@@ -639,6 +650,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
   // small batches (the reference configs' own 256): a persistent cluster kernel runs whole waves
   const bool small = hp->optimizer == RBPR_OPT_SGD && !adaptive && !(ctx->comm != nullptr && ctx->world > 1) &&
                      rbpr_small_batch_eligible(ctx, batch) && getenv("RBPR_NO_SMALL_BATCH") == nullptr;
+  const bool fx_split_users = getenv("RBPR_FX_SPLIT_USERS") != nullptr;
+  const bool fx_pdl = !fx_split_users && (getenv("RBPR_FX_PDL") == nullptr || atoi(getenv("RBPR_FX_PDL")) != 0);
   cudaStream_t prep_st = piped ? ctx->aux : st;
   if (piped) {
     RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_inputs, st));
@@ -731,10 +744,12 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       p.step = step0 + (uint64_t)(wave_step0(w) + s);
       p.item_grad = ctx->item_grad;  // alternates between two buffers under the fused exchange
       p.bias_grad = ctx->item_bias ? ctx->item_grad + ctx->I * ctx->D : nullptr;
+      p.pdl = 0;
       if (ctx->fx_bound && ctx->fx_wait_epoch != 0) {
         p.xwait_flags = ctx->fx_flags_local + RBPR_MAX_PEERS;
         p.xwait_n = ctx->world;
         p.xwait_epoch = ctx->fx_wait_epoch;
+        p.pdl = (fx_pdl && s > 0) ? 1 : 0;  // the kernel before this one in the stream is the exchange of step s-1
       }
       const int4* recs = reinterpret_cast<const int4*>(ctx->records[b]) + soff;
       const int32_t* mh_l = adaptive ? nullptr : ctx->mh_list[b] + soff;
@@ -748,9 +763,18 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
       if (rc) return rc;
       const int multi = (ctx->comm != nullptr && ctx->world > 1) ? 1 : 0;
       double* step_stats = ctx->stats + (wave_step0(w) + s) * RBPR_STATS_PER_STEP;
-      if (multi) {
-        // The one exchange of the step: dense item gradient, summed over ranks.  The user half of
-        // the apply (local rows only) and the statistics run on a side stream meanwhile.
+      if (multi && ctx->fx_bound && !fx_split_users) {
+        // The one exchange of the step, ONE kernel: user half of the apply + statistics (local),
+        // then reduce / item update / publish across ranks over peer memory (exchange.cu).
+        NvtxRange nvtx_x("rbpr.exchange (users + reduce + item update across ranks)");
+        const ApplyParams ua = make_apply_params(ctx, p.step, hp, 0, 0, recs, p.n, parts, nb * (kPhaseAThreads / 32),
+                                                 step_stats, mh_l, mh_c);
+        rc = rbpr_internal_fused_exchange(ctx, p.step, hp, st, &ua);
+        if (rc) return rc;
+      } else if (multi) {
+        // NCCL fallback (or RBPR_FX_SPLIT_USERS=1): dense item gradient summed over ranks on the
+        // caller's stream; the user half of the apply (local rows only) and the statistics run on a
+        // side stream meanwhile.
         RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_phase_a, st));
         RBPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2, ctx->ev_phase_a, 0));
         rc = run_apply(ctx, p.step, hp, 0, 0, recs, p.n, ctx->aux2, parts, nb * (kPhaseAThreads / 32),
@@ -770,6 +794,8 @@ static int train_steps_impl(rbpr_ctx* ctx, int64_t* triple_idx, int64_t n, int64
     if (piped) RBPR_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
   }
   rc = rbpr_internal_fx_wait(ctx, st);  // data parallel: the item table is complete when the call's work is
+  if (rc) return rc;
+  rc = rbpr_internal_fx_trace_report(ctx, st);
   if (rc) return rc;
   if (stats_out)
     RBPR_CUDA(ctx, cudaMemcpyAsync(stats_out, ctx->stats,

@@ -60,6 +60,7 @@ struct TrainParams {
   const uint32_t* __restrict__ xwait_flags;  // (world) or null
   int xwait_n;
   uint32_t xwait_epoch;
+  int pdl;  // host side only: launch with programmatic stream serialization (see launch_phase_a)
 };
 
 // Every CTA waits (thread 0 polls, bounded) until all `n` flag words have reached `epoch`.
@@ -582,12 +583,100 @@ __global__ void __launch_bounds__(kPhaseAThreads) bpr_phase_a(const TrainParams 
     p.partials[blockIdx.x * (kPhaseAThreads / 32) + (threadIdx.x >> 5)] = make_float4(a, b, cabs, d);
 }
 
+// ---- pieces of phase B, shared by bpr_apply and the fused exchange kernel (exchange.cu) ------------
+
+// users: rows of users with several triples in the step (records flagged kRecMultiHead): their summed
+// gradient sits in user_grad; single-occurrence users were finished by phase A.  One lane group
+// finishes one user.
+template <int LANES, int NV, int OPT>
+__device__ __forceinline__ void apply_users(const ApplyParams& p, const OptScalars& h, int64_t gid, int64_t groups) {
+  const Group<LANES> g;
+  const int D = p.D;
+  auto finish_user = [&](int64_t r) {
+    float* grow = p.user_grad + r * D;
+    float* prow = p.user_emb + r * D;
+    int64_t last = 0;
+    if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
+    const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
+    const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (g.gl + LANES * v);
+      if (c >= D) continue;
+      const float4 gr = ld4(grow + c);
+      float4 pp = ld4(prow + c);
+      if (OPT == RBPR_OPT_SGD) {
+        pp.x -= p.lr * gr.x;
+        pp.y -= p.lr * gr.y;
+        pp.z -= p.lr * gr.z;
+        pp.w -= p.lr * gr.w;
+      } else {
+        float4 m = ld4(p.user_m + r * D + c);
+        float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
+        if (behind) cu.apply(pp, m, vv);
+        opt4<OPT>(pp, m, vv, gr, h);
+        st4(p.user_m + r * D + c, m);
+        if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
+      }
+      st4(prow + c, pp);
+      st4(grow + c, f4zero());
+    }
+    if (OPT != RBPR_OPT_SGD) {
+      __syncwarp(g.mask);
+      if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
+    }
+  };
+  if (p.mh_list != nullptr) {
+    // the sampler compacted the step's multi-occurrence users: no scan, one round trip per user
+    const int64_t n_mh = (int64_t)__ldg(p.mh_count);
+    for (int64_t e = gid; e < n_mh; e += groups) finish_user((int64_t)__ldg(p.mh_list + e));
+  } else {
+    for (int64_t k = gid; k < p.n; k += groups) {
+      const int4 rec = __ldg(p.records + k);
+      if ((rec.w & kRecMultiHead) == 0 || rec.x == 0) continue;
+      finish_user((int64_t)rec.x);
+    }
+  }
+}
+
+// step statistics: one block sums phase A's per-warp partials in double (no extra launch)
+__device__ __forceinline__ void apply_stats(const ApplyParams& p) {
+  __shared__ double red[4][8];
+  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+  for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) {
+    const float4 v = p.partials[i];
+    a += (double)v.x;
+    b += (double)v.y;
+    c += (double)v.z;
+    d += (double)v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[0][warp] = a;
+    red[1][warp] = b;
+    red[2][warp] = c;
+    red[3][warp] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    p.stats_out[threadIdx.x] = t;
+  }
+}
+
 // Phase B — apply the accumulated gradients and clear the accumulators.
 //   items: SGD touches only the rows flagged by phase A; Adam (and the multi-GPU path, where the
 //          accumulator holds the all-reduced gradient) sweeps every row, which is torch.optim's
 //          dense semantics for the replicated item table.
-//   users: rows of users with several triples in the step (records flagged kRecMultiHead): their
-//          summed gradient sits in user_grad; single-occurrence users were finished by phase A.
+//   users: apply_users above.
 template <int LANES, int NV, int OPT>
 __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
   const Group<LANES> g;
@@ -600,54 +689,7 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
     h.step_size = t.x;
     h.bc2_sqrt = t.y;
   }
-  if (p.do_users) {
-    // One lane group finishes one multi-occurrence user: its summed gradient sits in user_grad.
-    auto finish_user = [&](int64_t r) {
-      float* grow = p.user_grad + r * D;
-      float* prow = p.user_emb + r * D;
-      int64_t last = 0;
-      if (OPT != RBPR_OPT_SGD) last = p.user_last[r];
-      const bool behind = OPT != RBPR_OPT_SGD && last > 0 && last < (int64_t)p.step;
-      const Catchup<OPT> cu(last, behind ? (int64_t)p.step : last, p.adam_tab, h);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = 4 * (g.gl + LANES * v);
-        if (c >= D) continue;
-        const float4 gr = ld4(grow + c);
-        float4 pp = ld4(prow + c);
-        if (OPT == RBPR_OPT_SGD) {
-          pp.x -= p.lr * gr.x;
-          pp.y -= p.lr * gr.y;
-          pp.z -= p.lr * gr.z;
-          pp.w -= p.lr * gr.w;
-        } else {
-          float4 m = ld4(p.user_m + r * D + c);
-          float4 vv = opt_has_s2(OPT) ? ld4(p.user_v + r * D + c) : f4zero();
-          if (behind) cu.apply(pp, m, vv);
-          opt4<OPT>(pp, m, vv, gr, h);
-          st4(p.user_m + r * D + c, m);
-          if (opt_has_s2(OPT)) st4(p.user_v + r * D + c, vv);
-        }
-        st4(prow + c, pp);
-        st4(grow + c, f4zero());
-      }
-      if (OPT != RBPR_OPT_SGD) {
-        __syncwarp(g.mask);
-        if (g.gl == 0) p.user_last[r] = (int32_t)(p.step + 1);
-      }
-    };
-    if (p.mh_list != nullptr) {
-      // the sampler compacted the step's multi-occurrence users: no scan, one round trip per user
-      const int64_t n_mh = (int64_t)__ldg(p.mh_count);
-      for (int64_t e = gid; e < n_mh; e += groups) finish_user((int64_t)__ldg(p.mh_list + e));
-    } else {
-      for (int64_t k = gid; k < p.n; k += groups) {
-        const int4 rec = __ldg(p.records + k);
-        if ((rec.w & kRecMultiHead) == 0 || rec.x == 0) continue;
-        finish_user((int64_t)rec.x);
-      }
-    }
-  }
+  if (p.do_users) apply_users<LANES, NV, OPT>(p, h, gid, groups);
   for (int64_t r = gid; p.do_items && r < p.I; r += groups) {
     if (!p.dense) {
       if (p.touched[r] == 0u) continue;
@@ -693,37 +735,7 @@ __global__ void __launch_bounds__(256) bpr_apply(const ApplyParams p) {
       }
     }
   }
-  if (blockIdx.x == 0 && p.stats_out != nullptr) {
-    __shared__ double red[4][8];
-    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-    for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) {
-      const float4 v = p.partials[i];
-      a += (double)v.x;
-      b += (double)v.y;
-      c += (double)v.z;
-      d += (double)v.w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-      d += __shfl_xor_sync(0xffffffffu, d, o);
-    }
-    const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-      red[0][warp] = a;
-      red[1][warp] = b;
-      red[2][warp] = c;
-      red[3][warp] = d;
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-      double t = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
-      p.stats_out[threadIdx.x] = t;
-    }
-  }
+  if (blockIdx.x == 0 && p.stats_out != nullptr) apply_stats(p);
 }
 
 // Bring all user rows to `step` applied optimizer steps (dense semantics), grid-stride over rows.
@@ -756,6 +768,33 @@ __global__ void __launch_bounds__(256) bpr_flush_users(float* __restrict__ user_
   }
 }
 
+}  // namespace rbpr_dev
+
+namespace rbpr_dev {
+// Launch of phase A.  p.pdl (data parallel, fused exchange): the previous kernel of the stream is the
+// exchange kernel, whose CTAs all run `griddepcontrol.launch_dependents` first thing, so this
+// grid's CTAs are placed as soon as SM resources free up instead of after the exchange grid has
+// drained and a launch latency has passed; nothing of the previous step is read before
+// wait_peer_flags has seen every rank's B2 flag, this rank's own included (its last CTA sets it after
+// the local work, the table slice and the accumulator clear are all fenced).
+template <typename Kernel>
+inline void launch_phase_a(Kernel kern, int blocks, cudaStream_t st, const TrainParams& p, const int4* records) {
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kPhaseAThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p, records);
+  } else {
+    kern<<<blocks, kPhaseAThreads, 0, st>>>(p, records);
+  }
+}
 }  // namespace rbpr_dev
 
 // Per-optimizer launchers (train_sgd.cu / train_adam.cu), one translation unit each so the

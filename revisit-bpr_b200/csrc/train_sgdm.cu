@@ -7,7 +7,7 @@ int rbpr_launch_phase_a_sgdm(rbpr_ctx* ctx, const TrainParams& p, int lanes, int
                               const int4* records, int blocks, cudaStream_t st) {
 #define X(L, V)                                                                       \
   if (lanes == L && nv == V) {                                                        \
-    bpr_phase_a<L, V, RBPR_OPT_SGDM><<<blocks, kPhaseAThreads, 0, st>>>(p, records);    \
+    launch_phase_a(bpr_phase_a<L, V, RBPR_OPT_SGDM>, blocks, st, p, records);    \
     return 0;                                                                         \
   }
   RBPR_FOR_EACH_GEOMETRY(X)

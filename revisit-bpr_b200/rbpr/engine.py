@@ -445,17 +445,29 @@ class Engine(Context):
 
     def init_fused_exchange(self, group=None, strict: bool = False) -> bool:
         """Replace the per-step all-reduce + dense apply by the fused reduce + update + broadcast kernel
-        over NVLink peer memory (csrc/exchange.cu).  Every rank exports cudaIpc handles of its gradient
-        buffers and of the item table / bias storages; the blobs travel through torch.distributed.
+        over NVLink peer memory (csrc/exchange.cu).  Two bindings, tried in this order:
+          * symmetric memory (torch.distributed._symmetric_memory; RBPR_FX_SYMM=0 skips it): one buffer
+            per rank holding the gradient accumulators AND the item table / bias, mapped into every
+            peer and aliased by an NVSwitch multicast address, so the reduction runs inside the switch
+            (multimem.ld_reduce) and updated rows leave their owner once (multimem.st).  The item
+            table and bias MOVE into that buffer: `self.item_emb` / `self.item_bias` are re-pointed in
+            place (`Tensor.set_`), so the tensor objects handed to the constructor follow; callers
+            holding other aliases (an nn.Parameter's `.data`) re-point them at `self.item_emb`;
+          * cudaIpc handles of the library's accumulators and of the item table / bias storages,
+            exchanged as blobs through torch.distributed (unicast peer loads / stores).
         Returns False (and keeps the NCCL path) when peer memory cannot be shared, unless `strict`.
         With a stateful optimizer the item table's optimizer state becomes SHARDED by row block
         (`item_cuts`); call `gather_item_state` before reading it (checkpoints)."""
+        import os
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world < 2 or world > native.MAX_PEERS:
             if strict:
                 raise native.NativeError(f"the fused exchange needs 2..{native.MAX_PEERS} ranks on one node")
             return False
+        if os.environ.get("RBPR_FX_SYMM", "1") != "0" and self._bind_symmetric(group, world, rank):
+            self.world, self.rank, self.fused_exchange = world, rank, True
+            return True
         blob = torch.zeros(native.IPC_BLOB_BYTES, dtype=torch.uint8)
         ok = torch.ones(1, dtype=torch.int32, device=self.device)
         err = ""
@@ -482,6 +494,61 @@ class Engine(Context):
             raise native.NativeError(f"fused exchange: binding peer memory failed on some rank ({err}); the ranks are "
                                      "now inconsistent, restart without it (RBPR_FUSED_EXCHANGE=0)")
         self.world, self.rank, self.fused_exchange = world, rank, True
+        return True
+
+    def _bind_symmetric(self, group, world: int, rank: int) -> bool:
+        """Allocate the symmetric buffer, rendezvous, bind (rbpr_comm_symm_bind) and re-point the item
+        table / bias into it.  False (nothing changed) when any rank cannot allocate or map it."""
+        import os
+        import torch.distributed as dist
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        buf = hdl = None
+        nbytes = int(self.lib.rbpr_comm_symm_bytes(self.ctx))
+        try:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            buf = symm.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm.rendezvous(buf, group=pg)
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            if len(bases) != world or any(b == 0 or b % 256 for b in bases) or bases[rank] != buf.data_ptr():
+                raise RuntimeError(f"unexpected symmetric mapping {bases}")
+        except Exception as e:  # noqa: BLE001  (any failure means "not available here": fall back, all ranks together)
+            ok.zero_()
+            self._symm_error = repr(e)[:300]
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            return False
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if os.environ.get("RBPR_FX_MULTICAST", "1") == "0":
+            mc = 0  # unicast peer loads / stores over the same buffer: rank-order sum, bit-reproducible
+        mcs = torch.tensor([mc != 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(mcs, op=dist.ReduceOp.MIN, group=group)
+        if mcs.item() == 0:
+            mc = 0
+        arr = (C.c_uint64 * world)(*bases)
+        new_item, new_bias = C.c_uint64(0), C.c_uint64(0)
+        err = ""
+        try:
+            self._check(self.lib.rbpr_comm_symm_bind(self.ctx, arr, C.c_uint64(mc), world, rank,
+                                                      C.byref(new_item), C.byref(new_bias), _stream()))
+        except native.NativeError as e:
+            ok.zero_()
+            err = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            raise native.NativeError(f"fused exchange: binding the symmetric buffer failed on some rank ({err}); the "
+                                     "ranks are now inconsistent, restart with RBPR_FX_SYMM=0")
+        torch.cuda.synchronize(self.device)
+        off = (new_item.value - buf.data_ptr()) // 4
+        with torch.no_grad():
+            self.item_emb.set_(buf[off:off + self.I * self.D].view(self.I, self.D))
+            if self.item_bias is not None:
+                offb = (new_bias.value - buf.data_ptr()) // 4
+                self.item_bias.set_(buf[offb:offb + self.I].view(self.item_bias.shape))
+        self._symm_buf, self._symm_hdl = buf, hdl  # keep the allocation and its peer mappings alive
+        self.multicast = bool(self.lib.rbpr_fused_exchange_multicast(self.ctx))
         return True
 
     def item_cuts(self) -> list[int]:

@@ -11,7 +11,7 @@ OPT_SGD, OPT_ADAM, OPT_SGDM, OPT_RMSPROP = 0, 1, 2, 3
 SAMPLER_UNIFORM, SAMPLER_WEIGHTED, SAMPLER_INJECTED, SAMPLER_ADAPTIVE = 0, 1, 2, 3
 STATS_PER_STEP = 4
 MAX_TOPK = 128
-ABI_VERSION = 8
+ABI_VERSION = 9
 IPC_BLOB_BYTES = 512
 MAX_PEERS = 8
 
@@ -30,6 +30,7 @@ SYMBOLS = (
     "rbpr_launch_count", "rbpr_kernel_timing", "rbpr_kernel_time_ms",
     "rbpr_score_metrics", "rbpr_topk_launch_count",
     "rbpr_score_path_counts", "rbpr_comm_ipc_export", "rbpr_comm_ipc_bind", "rbpr_fused_exchange_count",
+    "rbpr_comm_symm_bytes", "rbpr_comm_symm_bind", "rbpr_fused_exchange_multicast",
 )
 
 
@@ -101,6 +102,9 @@ def load() -> C.CDLL:
         "rbpr_comm_ipc_export": (C.c_int, [vp, vp]),
         "rbpr_comm_ipc_bind": (C.c_int, [vp, vp, i32, i32, vp]),
         "rbpr_fused_exchange_count": (i64, [vp]),
+        "rbpr_comm_symm_bytes": (i64, [vp]),
+        "rbpr_comm_symm_bind": (C.c_int, [vp, C.POINTER(u64), u64, i32, i32, C.POINTER(u64), C.POINTER(u64), vp]),
+        "rbpr_fused_exchange_multicast": (i32, [vp]),
         "rbpr_train_step_triples": (C.c_int, [vp, vp, vp, vp, i64, u64, hp, vp, vp, vp]),
         "rbpr_pair_logits": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
         "rbpr_sample_negatives_padded": (C.c_int, [vp, vp, i64, i64, i64, i64, u64, u64, i32, vp, vp]),

@@ -98,6 +98,23 @@ class MF(BaseLogitModel):
         return self._engine
 
     @torch.no_grad()
+    def adopt_engine_tables(self) -> None:
+        """The symmetric-memory binding of the fused exchange moves the item table / bias into a buffer
+        every peer maps (Engine.init_fused_exchange): re-point the parameters at the engine's tensors
+        so that module, optimizer and checkpoints keep seeing the live storage."""
+        eng = self._engine
+        if eng is None:
+            return
+        iw, ib = self._item_emb.weight, self._item_bias
+        if iw.data_ptr() != eng.item_emb.data_ptr():
+            iw.data = eng.item_emb
+        if ib is not None and eng.item_bias is not None and ib.data_ptr() != eng.item_bias.data_ptr():
+            ib.data = eng.item_bias
+        uw = self._user_emb.weight
+        self._engine_key = (uw.data_ptr(), iw.data_ptr(), None if ib is None else ib.data_ptr(), tuple(uw.shape),
+                            tuple(iw.shape))
+
+    @torch.no_grad()
     def forward(self, user: torch.Tensor, item: torch.Tensor, _: dict[str, torch.Tensor] | None = None,
                 mask: torch.Tensor | None = None) -> torch.Tensor:
         # user (B,), item (B, ...) -> logits (B, ...)
@@ -349,8 +366,9 @@ class Model(torch.nn.Module):
             eng.init_comm(group)
             import os
             if os.environ.get("RBPR_FUSED_EXCHANGE", "1") != "0":
-                # the exchange as one kernel over NVLink peer memory; NCCL stays when IPC is unavailable
+                # the exchange as one kernel over NVLink peer memory; NCCL stays when it is unavailable
                 eng.init_fused_exchange(group)
+                self.logits_model.adopt_engine_tables()
         self._dp = {"cuts": np.asarray(user_cuts, dtype=np.int64), "group": group}
 
     @torch.no_grad()

@@ -21,10 +21,22 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 code = 0
+binding = {}
+
+
+def setup(eng):  # RBPR_FUSED_EXCHANGE=0: NCCL all-reduce + dense apply; else the fused exchange kernel
+    if os.environ.get("RBPR_FUSED_EXCHANGE", "1") != "0":
+        fused = eng.init_fused_exchange()
+        binding["kind"] = ("multicast" if getattr(eng, "multicast", False) else
+                           "symmetric unicast" if getattr(eng, "_symm_buf", None) is not None else "cudaIpc") if fused else "nccl (fused unavailable)"
+    else:
+        binding["kind"] = "nccl"
+
+
 for opt in ("sgd", "adam"):
-    ok, why = dp_parity.run(dev, rank, world, opt)
+    ok, why = dp_parity.run(dev, rank, world, opt, setup=setup)
     if rank == 0:
-        print(f"multi-gpu check world={world} optimizer={opt}: {'OK' if ok else 'FAILED ' + why}", flush=True)
+        print(f"multi-gpu check world={world} optimizer={opt} exchange={binding.get('kind')}: {'OK' if ok else 'FAILED ' + why}", flush=True)
     code |= 0 if ok else 1
 dist.destroy_process_group()
 sys.exit(code)

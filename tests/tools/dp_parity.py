@@ -79,5 +79,6 @@ def run(dev: torch.device, rank: int, world: int, optimizer: str = "sgd", setup=
         why.append("owned user rows vs oracle")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    eng.close()
     del eng
     return flag.item() == 1, "; ".join(why)
