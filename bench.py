@@ -319,6 +319,16 @@ class Runner:
             self.dist.barrier()
         torch.cuda.synchronize()
 
+    def align(self):
+        """After barrier(): a device-side rendezvous on the current stream with NO host wait, so the
+        timed region of every rank starts at the same point of the GPU timeline (the hosts leave
+        dist.barrier() hundreds of microseconds apart, which a 60-step region of ~0.1 ms steps would
+        otherwise book as step time: the first exchange waits for the last host)."""
+        if self.world > 1:
+            if not hasattr(self, "_align_buf"):
+                self._align_buf = torch.zeros(1, device=self.dev)
+            self.dist.all_reduce(self._align_buf)
+
     def max_over_ranks(self, x: float) -> float:
         if self.world > 1:
             t = torch.tensor([x], device=self.dev, dtype=torch.float64)
@@ -385,6 +395,7 @@ class Runner:
         mark = self.clocks.mark() if self.clocks else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
+        self.align()
         e0.record()
         stats = eng.train_steps(perm[W * B:], B, SEED, W)[0]
         e1.record()

@@ -21,6 +21,8 @@
 // (rbpr_comm_ipc_export / rbpr_comm_ipc_bind); NCCL stays the fallback when peer access or IPC is
 // not available.  Replaces the DDP gradient all-reduce + dense optimizer step of the reference
 // (experiments/launcher.py:59-70, experiments/trainer.py:76-79).
+#include <algorithm>
+
 #include "train_kernels.cuh"
 
 using namespace rbpr_dev;
@@ -68,6 +70,7 @@ struct ExchangeParams {
   float* mc_item;                // multicast address of the item tables: one multimem.st reaches every replica
   float* mc_bias;
   int n_xchg;                    // CTAs [0, n_xchg) run the exchange, the others the local work
+  int mc_chunks;                 // > 1: chunk-major pull / push pipeline of the multicast path
 };
 
 __device__ __forceinline__ float4 ldcg4x(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -150,21 +153,8 @@ __global__ void __launch_bounds__(256, 4) bpr_exchange_apply(const ExchangeParam
     wait_peer_flags(p.flags[p.rank], W, p.epoch, p.err);
     if (tracer) p.trace[2] = gtime();
     const int64_t e_lo = p.lo * D / 4, e_hi = p.hi * D / 4;
-    for (int64_t e = e_lo + tid; e < e_hi; e += nthreads) {
-      const int64_t off = 4 * e;
-      float4 gr;
-      if (p.mc_grad != nullptr) {
-        gr = mc_ld_reduce4(p.mc_grad + off);
-      } else {
-        float4 t[kMaxWorld];
-#pragma unroll
-        for (int j = 0; j < kMaxWorld; ++j)  // all W loads are independent: issued back to back
-          if (j < W) t[j] = ldcg4x(p.gsrc[j] + off);
-        gr = t[0];
-#pragma unroll
-        for (int j = 1; j < kMaxWorld; ++j)  // fixed order (rank 0, 1, ...): every run sums the same way
-          if (j < W) gr = add4(gr, t[j]);
-      }
+    // optimizer on one 16-byte element of the slice, then the new value into every replica
+    auto finish = [&](int64_t off, float4 gr) {
       float4 pp = ldcg4x(p.idst[p.rank] + off);
       if (OPT == RBPR_OPT_SGD) {
         pp.x -= p.lr * gr.x;
@@ -184,6 +174,50 @@ __global__ void __launch_bounds__(256, 4) bpr_exchange_apply(const ExchangeParam
 #pragma unroll
         for (int j = 0; j < kMaxWorld; ++j)
           if (j < W) st4(p.idst[j] + off, pp);
+      }
+    };
+    if (p.mc_grad != nullptr && p.mc_chunks > 1) {
+      // EXPERIMENTAL (RBPR_FX_MC_CHUNKS > 1; default off, see the launcher).
+      // Multicast: the pull loads every GPU's OUT links (the switch reads all W copies), the push its
+      // IN links (every replica receives every slice), so the two can overlap — if pushes start while
+      // pulls are still queued.  The slice is cut into kChunks consecutive chunks; a thread issues its
+      // element of every chunk back to back (requests reach the switch chunk-major) and finishes them
+      // in that order: chunk c is being published while chunks > c are still being reduced.
+      constexpr int kChunks = 4;
+      const int64_t n = e_hi - e_lo;
+      for (int64_t base = 0; base < n; base += nthreads * kChunks) {
+        const int64_t span = (n - base) < nthreads * kChunks ? (n - base) : nthreads * kChunks;
+        const int64_t T = (span + kChunks - 1) / kChunks;
+        if (tid >= T) continue;
+        float4 g4[kChunks];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int64_t idx = c * T + tid;
+          if (idx < span) g4[c] = mc_ld_reduce4(p.mc_grad + 4 * (e_lo + base + idx));
+        }
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int64_t idx = c * T + tid;
+          if (idx < span) finish(4 * (e_lo + base + idx), g4[c]);
+        }
+      }
+    } else {
+      for (int64_t e = e_lo + tid; e < e_hi; e += nthreads) {
+        const int64_t off = 4 * e;
+        float4 gr;
+        if (p.mc_grad != nullptr) {
+          gr = mc_ld_reduce4(p.mc_grad + off);
+        } else {
+          float4 t[kMaxWorld];
+#pragma unroll
+          for (int j = 0; j < kMaxWorld; ++j)  // all W loads are independent: issued back to back
+            if (j < W) t[j] = ldcg4x(p.gsrc[j] + off);
+          gr = t[0];
+#pragma unroll
+          for (int j = 1; j < kMaxWorld; ++j)  // fixed order (rank 0, 1, ...): every run sums the same way
+            if (j < W) gr = add4(gr, t[j]);
+        }
+        finish(off, gr);
       }
     }
     if (p.bdst[p.rank] != nullptr) {
@@ -343,11 +377,16 @@ int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   // exchange role (the rest the local role); 4 = no split: every CTA does the local work first
   static const int xchg_per_sm = [] {
     const char* e = getenv("RBPR_FX_XCHG_CTAS");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 4;
     return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  static const int mc_chunks = [] {
+    const char* e = getenv("RBPR_FX_MC_CHUNKS");
+    return e ? atoi(e) : 1;  // off by default: measured slower at N=2 (85.6 vs 82.7 us/step), unmeasured at N=8
   }();
   const int blocks = ctx->sm_count * 4;
   p.n_xchg = ctx->sm_count * xchg_per_sm;
+  p.mc_chunks = mc_chunks;
 #define X(L, V)                                                                                       \
   if (lanes == L && nv == V) {                                                                        \
     switch (hp->optimizer) {                                                                          \
@@ -387,25 +426,26 @@ int rbpr_internal_fx_trace_report(rbpr_ctx* ctx, cudaStream_t st) {
   RBPR_CUDA(ctx, cudaMemcpyAsync(t.data(), ctx->fx_trace, t.size() * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
   RBPR_CUDA(ctx, cudaStreamSynchronize(st));
-  double local = 0, b1 = 0, loop = 0, tail = 0, total = 0, between = 0;
-  int nb = 0;
+  // medians: the first exchange of a call waits for the slowest HOST to get going, which would own the mean
+  std::vector<double> f[6];
   for (int i = 0; i < n; ++i) {
     const unsigned long long* w = t.data() + 8 * i;
-    local += (double)(w[1] - w[0]);   // local CTAs done (runs beside the exchange CTAs)
-    b1 += (double)(w[2] - w[0]);
-    loop += (double)(w[3] - w[2]);
-    tail += (double)(w[4] - (w[3] > w[1] ? w[3] : w[1]));
-    total += (double)(w[4] - w[0]);
-    if (i + 1 < n) {
-      between += (double)(t[8 * (i + 1)] - w[4]);
-      nb++;
-    }
+    f[0].push_back((double)(w[1] - w[0]));  // local CTAs done (they run beside / before the exchange CTAs)
+    f[1].push_back((double)(w[2] - w[0]));
+    f[2].push_back((double)(w[3] - w[2]));
+    f[3].push_back((double)(w[4] - (w[3] > w[1] ? w[3] : w[1])));
+    f[4].push_back((double)(w[4] - w[0]));
+    if (i + 1 < n) f[5].push_back((double)(t[8 * (i + 1)] - w[4]));
   }
+  auto med = [](std::vector<double>& v) {
+    if (v.empty()) return 0.0;
+    std::sort(v.begin(), v.end());
+    return v[v.size() / 2] * 1e-3;
+  };
   fprintf(stderr,
-          "[rbpr fx trace] rank %d: %d exchanges, mean us: local CTAs (users+clear) done at %.2f | B1 signal+wait %.2f | slice reduce+publish %.2f | "
+          "[rbpr fx trace] rank %d: %d exchanges, median us: local work done at %.2f | B1 signal+wait %.2f | slice reduce+publish %.2f | "
           "tail(fence+B2) %.2f | kernel %.2f | B2 -> next exchange start (phase A etc.) %.2f\n",
-          ctx->rank, n, local / n * 1e-3, b1 / n * 1e-3, loop / n * 1e-3, tail / n * 1e-3, total / n * 1e-3,
-          nb ? between / nb * 1e-3 : 0.0);
+          ctx->rank, n, med(f[0]), med(f[1]), med(f[2]), med(f[3]), med(f[4]), med(f[5]));
   RBPR_CUDA(ctx, cudaMemsetAsync(ctx->fx_trace, 0, t.size() * sizeof(unsigned long long), st));
   ctx->fx_trace_n = 0;
   return 0;

@@ -521,8 +521,13 @@ class Engine(Context):
         if ok.item() == 0:
             return False
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-        if os.environ.get("RBPR_FX_MULTICAST", "1") == "0":
-            mc = 0  # unicast peer loads / stores over the same buffer: rank-order sum, bit-reproducible
+        # In-switch reduction pays from 4 ranks on (measured: N=2 unicast 68 us/step vs multicast 78;
+        # N=4 equal; N=8 multicast 95 vs unicast 101): with 2 ranks the switch reads BOTH copies over
+        # NVLink, the own one included.  RBPR_FX_MULTICAST=1 / 0 forces it on / off; off also gives
+        # the rank-order (bit-reproducible) sum of the unicast path.
+        want = os.environ.get("RBPR_FX_MULTICAST", "auto")
+        if want == "0" or (want == "auto" and world < 4):
+            mc = 0
         mcs = torch.tensor([mc != 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(mcs, op=dist.ReduceOp.MIN, group=group)
         if mcs.item() == 0:
