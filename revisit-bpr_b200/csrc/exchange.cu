@@ -361,9 +361,16 @@ int rbpr_internal_fused_exchange(rbpr_ctx* ctx, uint64_t step, const rbpr_hparam
   p.adam_tab = ctx->adam_tab;
   if (ctx->fx_trace != nullptr) p.trace = ctx->fx_trace + 8 * (size_t)(ctx->fx_trace_n++ % kTraceSlots);
   if (ctx->fx_mc_grad[par] != nullptr) {
+    // RBPR_FX_MC_PUSH=0: in-switch reduction for the pull, unicast stores for the push
+    static const bool mc_push = [] {
+      const char* e = getenv("RBPR_FX_MC_PUSH");
+      return e == nullptr || atoi(e) != 0;
+    }();
     p.mc_grad = ctx->fx_mc_grad[par];
-    p.mc_item = ctx->fx_mc_item;
-    p.mc_bias = ctx->fx_mc_bias;
+    if (mc_push) {
+      p.mc_item = ctx->fx_mc_item;
+      p.mc_bias = ctx->fx_mc_bias;
+    }
   }
   ApplyParams u;
   if (users != nullptr) {
