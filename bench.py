@@ -499,7 +499,25 @@ class Runner:
         flops = 2.0 * D * inter.num_items * n_all
         min_bytes = (inter.num_items * D * 4) * self.world + n_all * D * 4 + n_all * len(ks) * 2 * 4
         traffic = ncu_traffic(f"score:ml-20m:D{D}:U{n_all}:N{self.world}")
-        peak_gbs, _, _ = peaks()
+        peak_gbs, peak_bf16, _ = peaks()
+        # dominant kernel: score_tc, two tcgen05 kind::tf32 passes over the padded (users x items x K) problem
+        # (K = D + bias column + "never" column, padded to 32-float swizzle atoms); tf32 dense peak = half
+        # the measured bf16 rate.  `achieved` divides by the WHOLE call (pack, 2 passes, select, rescore):
+        # the kernel alone is in profiles/round2/z_launches_c5_score.txt.
+        tc_passes, tc_ovf = eng.score_path_counts() if hasattr(eng, "score_path_counts") else (0, 0)
+        up, ip = -(-(b - a) // 128) * 128, -(-inter.num_items // 128) * 128
+        kp = -(-(D + 1) // 32) * 32
+        tc_flops = 2 * 2.0 * up * ip * kp
+        tc_roof = {"bound": "tensor" if tc_passes else "fp32 FMA (dense fallback)",
+                   "kernel": "score_tc (tcgen05 tf32, 2 passes) + select_threshold + rescore_rank",
+                   "achieved": tc_flops / (ms * 1e-3) / 1e12, "peak": peak_bf16 / 2, "unit": "TFLOP/s",
+                   "frac": tc_flops / (ms * 1e-3) / 1e12 / (peak_bf16 / 2),
+                   "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate)",
+                   "executed_tf32_flops_per_call": tc_flops, "useful_fp32_flops_per_call": 2.0 * D * inter.num_items * (b - a),
+                   "algorithmic_min_bytes": min_bytes, "traffic": traffic,
+                   "traffic_over_algorithmic": (traffic / min_bytes) if traffic else None,
+                   "hbm_view_frac": min_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
+                   "tensor_passes": tc_passes, "overflow_users_on_dense_path": tc_ovf}
         entry = {"metric": "users/sec scored (full catalog, NDCG@100 + Recall@20)", "value": n_all / (ms * 1e-3),
                  "unit": "users/s", "ms": ms, "users": n_all, "ndcg@100": ndcg, "recall@20": recall,
                  "effective_tflops": flops / (ms * 1e-3) / 1e12, "gpu_launches_per_pass": launches,
@@ -507,11 +525,7 @@ class Runner:
                                         "items held out, the rest masked), whole set in one call" +
                                         (f", eval users sharded over {self.world} GPUs" if self.world > 1 else ""),
                             "n_gpus": self.world},
-                 "roofline": {"bound": "fp32 FMA (score_gemm) + L2 (topk_metrics)",
-                              "algorithmic_min_bytes": min_bytes, "traffic": traffic,
-                              "achieved": min_bytes / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                              "frac": min_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
-                              "traffic_over_algorithmic": (traffic / min_bytes) if traffic else None},
+                 "roofline": tc_roof,
                  "e2e": {"value": n_all / e2e_s, "unit": "users/s", "h2d_bytes_per_step": int((b - a) * 8 + sp.nbytes + hp.nbytes + si.nbytes + hi.nbytes),
                          "d2h_bytes_per_step": int(sums.numel() * 4)}}
         del eng
