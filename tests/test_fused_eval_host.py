@@ -108,3 +108,37 @@ def test_metric_reduction_is_one_exact_sum_count_allreduce_gloo():
     for rank, ndcg, loss, tag, rows in res:
         assert abs(ndcg - 2.5 / 4) < 1e-12 and abs(loss - 2.5) < 1e-12 and tag == "x"
         assert rows == want
+
+
+def test_parameters_follow_the_engine_into_the_symmetric_buffer():
+    """Engine.init_fused_exchange (symmetric-memory binding) moves the item table / bias into a buffer
+    every peer maps; MF.adopt_engine_tables re-points the parameters there WITHOUT replacing the
+    parameter objects (the torch optimizer and its state are keyed by them) and keeps the engine."""
+    from types import SimpleNamespace
+    from revisit_bpr.models.bpr.model import MF
+    U, I, D = 7, 9, 4
+    mf = MF(torch.nn.Embedding(U, D, padding_idx=0), torch.nn.Embedding(I, D, padding_idx=0), item_bias=True)
+    with torch.no_grad():
+        mf._item_bias.copy_(torch.arange(mf._item_bias.numel(), dtype=torch.float32).view_as(mf._item_bias))
+    feats = mf.get_features()
+    iw, ib = feats["item"], feats["item_bias"]
+    opt = torch.optim.Adam(mf.parameters(), lr=1e-3)
+    opt.state[iw]["exp_avg"] = torch.ones_like(iw)
+    # what the engine holds after the bind: views of ONE buffer, filled with the old values
+    buf = torch.zeros(I * D + I + 16)
+    new_item = buf[8:8 + I * D].view(I, D)
+    new_bias = buf[8 + I * D:8 + I * D + I].view(ib.shape)
+    new_item.copy_(iw.data)
+    new_bias.copy_(ib.data)
+    mf._engine = SimpleNamespace(item_emb=new_item, item_bias=new_bias)
+    before = iw.detach().clone()
+    mf.adopt_engine_tables()
+    assert mf.get_features()["item"] is iw and "exp_avg" in opt.state[iw]        # same parameter object
+    assert iw.data_ptr() == new_item.data_ptr() and ib.data_ptr() == new_bias.data_ptr()
+    assert torch.equal(iw.detach(), before)
+    buf[8] = 42.0                                                                  # a peer's store lands ...
+    assert iw[0, 0].item() == 42.0                                                 # ... in the parameter
+    key = mf._engine_key
+    assert key[1] == iw.data_ptr() and key[2] == ib.data_ptr()                    # engine() will not rebuild
+    mf.adopt_engine_tables()                                                       # idempotent
+    assert mf._engine_key == key
