@@ -1,26 +1,38 @@
-// The data-parallel step's ONE exchange as ONE kernel over NVLink peer memory (sm_100a, NVSwitch):
-// reduce the ranks' dense item gradients, apply the optimizer, and publish the updated item rows to
-// every replica — tile by tile, no separate all-reduce pass, no dense re-read of the reduced buffer.
+// The data-parallel step's ONE exchange as ONE kernel over NVLink / NVSwitch (sm_100a): reduce the
+// ranks' dense item gradients, apply the optimizer, and publish the updated item rows to every
+// replica — element by element, no separate all-reduce pass, no dense re-read of the reduced buffer —
+// plus everything else a step does after phase A (user half of the apply, statistics, accumulator
+// clear), so that a data-parallel step is two launches.
 //
 //   every rank r owns a contiguous slice of the item rows, [I*r/W, I*(r+1)/W):
-//     g   = sum over ranks q = 0..W-1 of grad_q[row]      (128-bit loads from the peers' accumulators
-//                                                           through NVLink; fixed order: deterministic)
-//     row = optimizer(row, g [, m, v of the slice])        (SGD / Adam / SGD-momentum / RMSprop; the
+//     g   = sum over ranks q = 0..W-1 of grad_q[element]   multicast binding: ONE multimem.ld_reduce —
+//                                                           the NVSwitch reads the W copies and returns
+//                                                           their sum; otherwise W independent 128-bit
+//                                                           peer loads summed in rank order
+//     x   = optimizer(x, g [, m, v of the slice])          SGD / Adam / SGD-momentum / RMSprop; the
 //                                                           optimizer state of the item table is
-//                                                           SHARDED: only the owner keeps its slice)
-//     item_q[row] = row   for every rank q                 (128-bit stores into the peers' tables)
-//   so replicas are bit-identical by construction, each rank sweeps 1/W of the table (the dense
-//   Adam sweep of the 8-GPU MSD configuration shrinks 8x), and per-GPU NVLink traffic is one
-//   gradient buffer in + one table slice out per step instead of an all-reduce plus a dense apply.
+//                                                           SHARDED: only the owner keeps its slice
+//     item_q[element] = x   for every rank q               multicast binding: ONE multimem.st;
+//                                                           otherwise W 128-bit peer stores
+//   so replicas are bit-identical by construction and each rank sweeps 1/W of the table (the dense
+//   Adam sweep of the 8-GPU MSD configuration shrinks 8x).
 //
 // Synchronisation: two gradient accumulators used alternately (step s accumulates into buf[s&1], the
 // exchange of step s clears the local buf[(s+1)&1], which the peers finished reading one step ago),
-// and two cross-rank barriers per step (flags in peer memory, st.release.sys / ld.acquire.sys):
-// B1 "every rank's phase A has landed" before the reduce, B2 "every rank's rows have landed" before
-// the next phase A.  Memory is shared with cudaIpc handles exchanged by the host shell
-// (rbpr_comm_ipc_export / rbpr_comm_ipc_bind); NCCL stays the fallback when peer access or IPC is
-// not available.  Replaces the DDP gradient all-reduce + dense optimizer step of the reference
-// (experiments/launcher.py:59-70, experiments/trainer.py:76-79).
+// and two cross-rank barriers per step (flag words in peer memory, st.release.sys / ld.acquire.sys,
+// bounded spins): B1 "every rank's phase A has landed" before the reduce, B2 "every rank's rows have
+// landed" before the next phase A, which is launched with programmatic stream serialization and waits
+// for the flags itself.
+//
+// Memory is shared in one of two ways (the host shell chooses; include/rbpr.h):
+//   * rbpr_comm_symm_bind: ONE symmetric buffer per rank allocated by the host (torch symmetric
+//     memory / cuMem + cuMulticast) holding accumulators, flags AND the item table / bias, mapped
+//     into every peer, optionally aliased by an NVSwitch multicast address;
+//   * rbpr_comm_ipc_export / rbpr_comm_ipc_bind: cudaIpc handles of the library's accumulators and
+//     of the storages holding the item table / bias (unicast only).
+// NCCL stays the fallback when neither is available.  Replaces the DDP gradient all-reduce + dense
+// optimizer step of the reference (experiments/launcher.py:59-70, experiments/trainer.py:76-79).
+// Measured anatomy of the kernel on 2 and 8 B200s: profiles/round2/z_exchange_trace.txt, DESIGN.md §6.
 #include <algorithm>
 
 #include "train_kernels.cuh"
